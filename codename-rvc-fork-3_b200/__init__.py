@@ -1,0 +1,16 @@
+"""codename-rvc-fork-3_b200 -- B200-native RVC feature retrieval (faiss IVF-Flat search k=8 ->
+gather -> 1/score^2 weighting -> index_rate blend) behind the reference's own Python call sites.
+
+The directory name is not a Python identifier; import it with
+    importlib.import_module("codename-rvc-fork-3_b200")      (repo root on sys.path)
+or through the `rvcr` alias module at the repo root.
+
+Host side only: every number is computed by librvcr.so (hand-written sm_100a CUDA, include/rvcr.h).
+"""
+from ._ffi import RvcrError, device_count, lib  # noqa: F401
+from .faiss_compat import (METRIC_L2, IndexIVFFlat, extract_index_ivf, index_factory, read_index,  # noqa: F401
+                           write_index)
+from .retrieve import patch_pipeline, retrieve_speaker_embeddings  # noqa: F401
+
+__all__ = ["IndexIVFFlat", "read_index", "write_index", "index_factory", "extract_index_ivf", "METRIC_L2",
+           "retrieve_speaker_embeddings", "patch_pipeline", "RvcrError", "device_count", "lib"]

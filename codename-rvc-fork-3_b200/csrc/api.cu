@@ -1,0 +1,566 @@
+// api.cu -- the C ABI declared in include/rvcr.h (handle, orchestration, host-buffer variants).
+//
+// Call-site map (reference paths):
+//   rvcr_index_read / _info / rvcr_reconstruct_n  <- rvc/infer/pipeline.py:553-561
+//   rvcr_search / rvcr_retrieve_blend             <- rvc/infer/pipeline.py:497-507
+//   rvcr_index_create / _set_nprobe / _add / _write <- rvc/train/process/extract_index.py:59-71
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace rvcr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int read_index_file(const char* path, int device, int rank, int world, rvcr_index** out);
+int write_index_file(rvcr_index* h, const char* path);
+
+namespace {
+
+// RAII: select the handle's device for the duration of a call, restore the caller's afterwards.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            ok = false;
+            return;
+        }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define RVCR_ENTER(h)                                            \
+    if (!(h)) {                                                  \
+        rvcr::set_error("null index handle");                    \
+        return RVCR_ERR_INVALID;                                 \
+    }                                                            \
+    std::lock_guard<std::mutex> _lock((h)->mu);                  \
+    rvcr::DeviceGuard _guard((h)->device);                       \
+    if (!_guard.ok) {                                            \
+        rvcr::set_error("cannot select CUDA device %d: %s", (h)->device, cudaGetErrorString(cudaGetLastError())); \
+        return RVCR_ERR_CUDA;                                    \
+    }
+
+// Scratch buffers are shared by all calls on a handle: a call on a different stream than the
+// previous one first waits for the previous call's work.
+int stream_enter(rvcr_index* h, cudaStream_t s) {
+    if (h->have_last && h->last_stream != s) RVCR_CUDA(cudaStreamWaitEvent(s, h->last_done, 0));
+    return RVCR_OK;
+}
+int stream_leave(rvcr_index* h, cudaStream_t s) {
+    if (!h->last_done) RVCR_CUDA(cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming));
+    RVCR_CUDA(cudaEventRecord(h->last_done, s));
+    h->last_stream = s;
+    h->have_last = true;
+    return RVCR_OK;
+}
+
+int check_searchable(rvcr_index* h, int32_t k) {
+    if (!h->trained) {
+        set_error("index is not trained (no centroids)");
+        return RVCR_ERR_STATE;
+    }
+    if (k != RVCR_K) {
+        set_error("k=%d unsupported: the RVC pipeline always searches k=8 (pipeline.py:499)", k);
+        return RVCR_ERR_UNSUPPORTED;
+    }
+    if (h->nprobe != 1) {
+        set_error("nprobe=%lld unsupported: RVC indices are built with nprobe=1 (extract_index.py:64)",
+                  (long long)h->nprobe);
+        return RVCR_ERR_UNSUPPORTED;
+    }
+    return RVCR_OK;
+}
+
+// nearest centroid for n device queries; dispatch FFMA-exact vs tcgen05 + exact re-check
+int coarse_dispatch(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out, cudaStream_t s) {
+    int64_t mode = h->opt.coarse_mode;
+    if (mode == 0) {
+        // the tensor-core path pays a fixed conversion + re-check cost; use it once the
+        // contraction is large enough to matter (>= ~64 MFLOP)
+        const double flops = 2.0 * (double)n * (double)h->nlist * (double)h->d;
+        mode = (coarse_tc_available() && flops >= 6.4e7 && h->nlist >= 64 && n >= 1) ? 2 : 1;
+    }
+    if (mode >= 2) {
+        if (!coarse_tc_available()) {
+            set_error("coarse_mode=%lld requested but the tcgen05 path is not built", (long long)mode);
+            return RVCR_ERR_UNSUPPORTED;
+        }
+        h->opt.coarse_mode = h->opt.coarse_mode;  // unchanged; split factor is read by coarse_tc
+        return coarse_tc(h, q, n, list_out, dist_out, s);
+    }
+    return coarse_exact(h, q, n, nullptr, 0, list_out, dist_out, s);
+}
+
+int search_device(rvcr_index* h, float* feats_or_q, int64_t n, const int32_t* assign_in, bool blend, double index_rate,
+                  float* D_dev, int64_t* I_dev, cudaStream_t s) {
+    if (n < 0) {
+        set_error("negative query count");
+        return RVCR_ERR_INVALID;
+    }
+    RVCR_TRY(check_searchable(h, RVCR_K));
+    if (n == 0) return RVCR_OK;
+    RVCR_TRY(finalize_pending(h, s));
+    RVCR_TRY(stream_enter(h, s));
+    const int32_t* assign = assign_in;
+    if (!assign) {
+        RVCR_TRY(h->ws_assign.reserve((size_t)n * 4));
+        RVCR_TRY(coarse_dispatch(h, feats_or_q, n, h->ws_assign.as<int32_t>(), nullptr, s));
+        assign = h->ws_assign.as<int32_t>();
+    }
+    RVCR_TRY(group_queries(h, assign, n, assign_in != nullptr, s));
+    RVCR_TRY(h->ws_P.reserve((size_t)n * RVCR_K * 4));
+    float* D = D_dev;
+    if (!D) {
+        RVCR_TRY(h->ws_D.reserve((size_t)n * RVCR_K * 4));
+        D = h->ws_D.as<float>();
+    }
+    RVCR_TRY(scan_topk(h, feats_or_q, n, D, h->ws_P.as<int32_t>(), I_dev, s));
+    if (blend) RVCR_TRY(gather_blend(h, feats_or_q, n, D, h->ws_P.as<int32_t>(), assign_in, index_rate, s));
+    h->stats.calls_search += 1;
+    h->stats.queries += n;
+    return stream_leave(h, s);
+}
+
+// Append n rows (ids ntotal .. ntotal+n-1) with their list assignment to the id-ordered staging
+// area; grows geometrically (amortised O(1) per appended row).  Caller holds the handle lock.
+int stage_rows(rvcr_index* h, const float* x_dev, int64_t n, const int32_t* assign_dev, cudaStream_t s) {
+    if (n == 0) return RVCR_OK;
+    const int64_t need = h->npending + n;
+    if (need > h->stage_cap) {
+        int64_t cap = h->stage_cap ? h->stage_cap : 8192;
+        while (cap < need) cap *= 2;
+        float* nx = nullptr;
+        int32_t* na = nullptr;
+        cudaError_t e = cudaMalloc(&nx, (size_t)cap * h->d * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&na, (size_t)cap * 4);
+        if (e != cudaSuccess) {
+            if (nx) cudaFree(nx);
+            set_error("staging allocation for %lld rows failed: %s", (long long)cap, cudaGetErrorString(e));
+            return RVCR_ERR_OOM;
+        }
+        if (h->npending) {
+            RVCR_CUDA(cudaMemcpyAsync(nx, h->stage_x, (size_t)h->npending * h->d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            RVCR_CUDA(cudaMemcpyAsync(na, h->stage_assign, (size_t)h->npending * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        RVCR_CUDA(cudaStreamSynchronize(s));
+        if (h->stage_x) cudaFree(h->stage_x);
+        if (h->stage_assign) cudaFree(h->stage_assign);
+        h->stage_x = nx;
+        h->stage_assign = na;
+        h->stage_cap = cap;
+    }
+    RVCR_CUDA(cudaMemcpyAsync(h->stage_x + (size_t)h->npending * h->d, x_dev, (size_t)n * h->d * sizeof(float),
+                              cudaMemcpyDeviceToDevice, s));
+    RVCR_CUDA(cudaMemcpyAsync(h->stage_assign + h->npending, assign_dev, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    h->npending += n;
+    h->ntotal += n;
+    return RVCR_OK;
+}
+
+}  // namespace
+}  // namespace rvcr
+
+using namespace rvcr;
+
+extern "C" {
+
+const char* rvcr_last_error(void) { return get_error(); }
+int rvcr_version(void) { return RVCR_VERSION; }
+
+int rvcr_device_count(int* count_out) {
+    if (!count_out) return RVCR_ERR_INVALID;
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+        *count_out = 0;
+        return RVCR_ERR_CUDA;
+    }
+    *count_out = c;
+    return RVCR_OK;
+}
+
+int rvcr_index_create(int32_t d, int64_t nlist, int device, rvcr_index** out) {
+    if (!out || d <= 0 || nlist <= 0) {
+        set_error("rvcr_index_create: bad arguments (d=%d nlist=%lld)", d, (long long)nlist);
+        return RVCR_ERR_INVALID;
+    }
+    int ndev = 0;
+    RVCR_TRY(rvcr_device_count(&ndev));
+    if (device < 0 || device >= ndev) {
+        set_error("CUDA device %d not available (%d visible); this library has no CPU fallback", device, ndev);
+        return RVCR_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    RVCR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; librvcr is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return RVCR_ERR_CUDA;
+    }
+    rvcr_index* h = new rvcr_index();
+    h->device = device;
+    h->d = d;
+    h->nlist = nlist;
+    h->nlist_global = nlist;
+    h->num_sms = prop.multiProcessorCount;
+    h->offsets_host.assign((size_t)nlist + 1, 0);
+    *out = h;
+    return RVCR_OK;
+}
+
+int rvcr_index_read(const char* path, int device, rvcr_index** out) {
+    if (!path || !out) return RVCR_ERR_INVALID;
+    return read_index_file(path, device, 0, 1, out);
+}
+
+int rvcr_index_read_shard(const char* path, int device, int rank, int world, rvcr_index** out) {
+    if (!path || !out || world < 1 || rank < 0 || rank >= world) {
+        set_error("rvcr_index_read_shard: bad rank/world");
+        return RVCR_ERR_INVALID;
+    }
+    return read_index_file(path, device, rank, world, out);
+}
+
+int rvcr_index_write(rvcr_index* h, const char* path) {
+    RVCR_ENTER(h);
+    if (!path) return RVCR_ERR_INVALID;
+    RVCR_TRY(finalize_pending(h, nullptr));
+    RVCR_CUDA(cudaDeviceSynchronize());
+    return write_index_file(h, path);
+}
+
+void rvcr_index_free(rvcr_index* h) {
+    if (!h) return;
+    {
+        DeviceGuard g(h->device);
+        cudaDeviceSynchronize();
+        if (h->cent) cudaFree(h->cent);
+        if (h->cent_bf16) cudaFree(h->cent_bf16);
+        if (h->cent_norm) cudaFree(h->cent_norm);
+        if (h->vecs) cudaFree(h->vecs);
+        if (h->ids) cudaFree(h->ids);
+        if (h->offsets) cudaFree(h->offsets);
+        if (h->stage_x) cudaFree(h->stage_x);
+        if (h->stage_assign) cudaFree(h->stage_assign);
+        DevBuf* bufs[] = {&h->ws_assign, &h->ws_keys, &h->ws_vals, &h->ws_keys2, &h->ws_vals2, &h->ws_cub, &h->ws_items,
+                          &h->ws_flags, &h->ws_misc, &h->ws_D, &h->ws_P, &h->ws_I, &h->ws_best, &h->ws_q, &h->ws_tc0,
+                          &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_stage};
+        for (DevBuf* b : bufs) b->release();
+        if (h->last_done) cudaEventDestroy(h->last_done);
+    }
+    delete h;
+}
+
+int rvcr_index_info(rvcr_index* h, rvcr_info* out) {
+    if (!h || !out) return RVCR_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(h->mu);
+    out->d = h->d;
+    out->is_trained = h->trained ? 1 : 0;
+    out->ntotal = h->ntotal;
+    out->nlist = h->nlist;
+    out->nprobe = h->nprobe;
+    out->nstored = h->nstored + h->npending;
+    out->list_begin = h->list_begin;
+    out->nlist_global = h->nlist_global;
+    out->device = h->device;
+    out->metric = h->metric;
+    return RVCR_OK;
+}
+
+int rvcr_index_set_nprobe(rvcr_index* h, int64_t nprobe) {
+    if (!h || nprobe < 1) return RVCR_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(h->mu);
+    h->nprobe = nprobe;
+    return RVCR_OK;
+}
+
+int rvcr_index_set_centroids(rvcr_index* h, const float* centroids_host, int64_t nlist) {
+    RVCR_ENTER(h);
+    if (!centroids_host || nlist != h->nlist) {
+        set_error("set_centroids: expected %lld x %d centroids", (long long)h->nlist, h->d);
+        return RVCR_ERR_INVALID;
+    }
+    if (!h->cent) RVCR_CUDA(cudaMalloc(&h->cent, (size_t)nlist * h->d * sizeof(float)));
+    RVCR_CUDA(cudaMemcpy(h->cent, centroids_host, (size_t)nlist * h->d * sizeof(float), cudaMemcpyHostToDevice));
+    h->trained = true;
+    return coarse_tc_invalidate(h);
+}
+
+int rvcr_index_get_centroids(rvcr_index* h, float* centroids_host) {
+    RVCR_ENTER(h);
+    if (!centroids_host) return RVCR_ERR_INVALID;
+    if (!h->trained) {
+        set_error("index is not trained");
+        return RVCR_ERR_STATE;
+    }
+    RVCR_CUDA(cudaMemcpy(centroids_host, h->cent, (size_t)h->nlist * h->d * sizeof(float), cudaMemcpyDeviceToHost));
+    return RVCR_OK;
+}
+
+int rvcr_index_list_sizes(rvcr_index* h, int64_t* sizes_host) {
+    RVCR_ENTER(h);
+    if (!sizes_host) return RVCR_ERR_INVALID;
+    RVCR_TRY(finalize_pending(h, nullptr));
+    for (int64_t l = 0; l < h->nlist; ++l) sizes_host[l] = h->offsets_host[l + 1] - h->offsets_host[l];
+    return RVCR_OK;
+}
+
+int rvcr_index_train(rvcr_index* h, const float* x_host, int64_t n) {
+    (void)x_host;
+    (void)n;
+    if (!h) return RVCR_ERR_INVALID;
+    set_error("index.train (faiss k-means) is a SURVEY 8(f) 'next' row; supply centroids with rvcr_index_set_centroids");
+    return RVCR_ERR_UNSUPPORTED;
+}
+
+int rvcr_index_add_preassigned(rvcr_index* h, const float* x_dev, int64_t n, const int32_t* assign_dev, void* stream) {
+    RVCR_ENTER(h);
+    if (n < 0 || (n > 0 && (!x_dev || !assign_dev))) return RVCR_ERR_INVALID;
+    return stage_rows(h, x_dev, n, assign_dev, (cudaStream_t)stream);
+}
+
+int rvcr_index_add(rvcr_index* h, const float* x, int64_t n, int x_on_device, void* stream) {
+    RVCR_ENTER(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n < 0 || (n > 0 && !x)) return RVCR_ERR_INVALID;
+    if (n == 0) return RVCR_OK;
+    if (!h->trained) {
+        set_error("index.add on an untrained index");
+        return RVCR_ERR_STATE;
+    }
+    RVCR_TRY(stream_enter(h, s));
+    const float* xd = x;
+    if (!x_on_device) {
+        RVCR_TRY(h->ws_q.reserve((size_t)n * h->d * sizeof(float)));
+        RVCR_CUDA(cudaMemcpyAsync(h->ws_q.p, x, (size_t)n * h->d * sizeof(float), cudaMemcpyHostToDevice, s));
+        xd = h->ws_q.as<float>();
+    }
+    RVCR_TRY(h->ws_assign.reserve((size_t)n * 4));
+    int32_t* assign = h->ws_assign.as<int32_t>();
+    RVCR_TRY(coarse_dispatch(h, xd, n, assign, nullptr, s));
+    RVCR_TRY(stage_rows(h, xd, n, assign, s));
+    RVCR_TRY(stream_leave(h, s));
+    // a pageable host buffer may be reused by the caller as soon as we return
+    if (!x_on_device) RVCR_CUDA(cudaStreamSynchronize(s));
+    return RVCR_OK;
+}
+
+int rvcr_index_alloc_lists(rvcr_index* h, const int64_t* sizes_host, int64_t ntotal) {
+    RVCR_ENTER(h);
+    if (!sizes_host || ntotal < 0) return RVCR_ERR_INVALID;
+    if (h->npending) {
+        set_error("alloc_lists with staged adds pending");
+        return RVCR_ERR_STATE;
+    }
+    std::vector<int64_t> off((size_t)h->nlist + 1, 0);
+    for (int64_t l = 0; l < h->nlist; ++l) {
+        if (sizes_host[l] < 0) return RVCR_ERR_INVALID;
+        off[l + 1] = off[l] + sizes_host[l];
+    }
+    const int64_t nst = off[h->nlist];
+    if (h->vecs) cudaFree(h->vecs);
+    if (h->ids) cudaFree(h->ids);
+    h->vecs = nullptr;
+    h->ids = nullptr;
+    h->nstored = 0;
+    if (nst > 0) {
+        cudaError_t e = cudaMalloc(&h->vecs, (size_t)nst * h->d * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&h->ids, (size_t)nst * 8);
+        if (e != cudaSuccess) {
+            set_error("allocating %lld x %d list storage failed: %s", (long long)nst, h->d, cudaGetErrorString(e));
+            return RVCR_ERR_OOM;
+        }
+    }
+    if (!h->offsets) RVCR_CUDA(cudaMalloc(&h->offsets, (size_t)(h->nlist + 1) * 8));
+    RVCR_CUDA(cudaMemcpy(h->offsets, off.data(), (size_t)(h->nlist + 1) * 8, cudaMemcpyHostToDevice));
+    h->offsets_host = off;
+    h->nstored = nst;
+    h->ntotal = ntotal;
+    h->last_row_pos = -1;
+    return RVCR_OK;
+}
+
+int rvcr_index_device_ptrs(rvcr_index* h, float** vecs_dev, int64_t** ids_dev, int64_t** offsets_dev, float** centroids_dev) {
+    RVCR_ENTER(h);
+    RVCR_TRY(finalize_pending(h, nullptr));
+    if (vecs_dev) *vecs_dev = h->vecs;
+    if (ids_dev) *ids_dev = h->ids;
+    if (offsets_dev) *offsets_dev = h->offsets;
+    if (centroids_dev) *centroids_dev = h->cent;
+    return RVCR_OK;
+}
+
+int rvcr_index_commit(rvcr_index* h, void* stream) {
+    RVCR_ENTER(h);
+    RVCR_TRY(coarse_tc_invalidate(h));
+    return refresh_derived(h, (cudaStream_t)stream);
+}
+
+int rvcr_assign(rvcr_index* h, const float* x_dev, int64_t n, int32_t* list_out_dev, float* dist_out_dev, void* stream) {
+    RVCR_ENTER(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n < 0 || (n > 0 && (!x_dev || !list_out_dev))) return RVCR_ERR_INVALID;
+    if (!h->trained) {
+        set_error("index is not trained (no centroids)");
+        return RVCR_ERR_STATE;
+    }
+    if (n == 0) return RVCR_OK;
+    RVCR_TRY(stream_enter(h, s));
+    RVCR_TRY(coarse_dispatch(h, x_dev, n, list_out_dev, dist_out_dev, s));
+    return stream_leave(h, s);
+}
+
+int rvcr_search(rvcr_index* h, const float* q_dev, int64_t n, int32_t k, float* D_dev, int64_t* I_dev, void* stream) {
+    RVCR_ENTER(h);
+    if (n > 0 && (!q_dev || !D_dev || !I_dev)) return RVCR_ERR_INVALID;
+    RVCR_TRY(check_searchable(h, k));
+    return search_device(h, const_cast<float*>(q_dev), n, nullptr, false, 0.0, D_dev, I_dev, (cudaStream_t)stream);
+}
+
+int rvcr_search_host(rvcr_index* h, const float* q_host, int64_t n, int32_t k, float* D_host, int64_t* I_host) {
+    RVCR_ENTER(h);
+    if (n > 0 && (!q_host || !D_host || !I_host)) return RVCR_ERR_INVALID;
+    RVCR_TRY(check_searchable(h, k));
+    if (n <= 0) return n < 0 ? RVCR_ERR_INVALID : RVCR_OK;
+    cudaStream_t s = nullptr;
+    RVCR_TRY(h->ws_q.reserve((size_t)n * h->d * sizeof(float)));
+    RVCR_TRY(h->ws_D.reserve((size_t)n * RVCR_K * 4));
+    RVCR_TRY(h->ws_I.reserve((size_t)n * RVCR_K * 8));
+    RVCR_CUDA(cudaMemcpyAsync(h->ws_q.p, q_host, (size_t)n * h->d * sizeof(float), cudaMemcpyHostToDevice, s));
+    RVCR_TRY(search_device(h, h->ws_q.as<float>(), n, nullptr, false, 0.0, h->ws_D.as<float>(), h->ws_I.as<int64_t>(), s));
+    RVCR_CUDA(cudaMemcpyAsync(D_host, h->ws_D.p, (size_t)n * RVCR_K * 4, cudaMemcpyDeviceToHost, s));
+    RVCR_CUDA(cudaMemcpyAsync(I_host, h->ws_I.p, (size_t)n * RVCR_K * 8, cudaMemcpyDeviceToHost, s));
+    RVCR_CUDA(cudaStreamSynchronize(s));
+    return RVCR_OK;
+}
+
+int rvcr_retrieve_blend(rvcr_index* h, float* feats_dev, int64_t n, double index_rate, float* D_dev, int64_t* I_dev,
+                        void* stream) {
+    RVCR_ENTER(h);
+    if (n > 0 && !feats_dev) return RVCR_ERR_INVALID;
+    return search_device(h, feats_dev, n, nullptr, true, index_rate, D_dev, I_dev, (cudaStream_t)stream);
+}
+
+int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double index_rate) {
+    RVCR_ENTER(h);
+    if (n > 0 && !feats_host) return RVCR_ERR_INVALID;
+    if (n <= 0) return n < 0 ? RVCR_ERR_INVALID : RVCR_OK;
+    cudaStream_t s = nullptr;
+    const size_t bytes = (size_t)n * h->d * sizeof(float);
+    RVCR_TRY(h->ws_q.reserve(bytes));
+    RVCR_CUDA(cudaMemcpyAsync(h->ws_q.p, feats_host, bytes, cudaMemcpyHostToDevice, s));
+    RVCR_TRY(search_device(h, h->ws_q.as<float>(), n, nullptr, true, index_rate, nullptr, nullptr, s));
+    RVCR_CUDA(cudaMemcpyAsync(feats_host, h->ws_q.p, bytes, cudaMemcpyDeviceToHost, s));
+    RVCR_CUDA(cudaStreamSynchronize(s));
+    return RVCR_OK;
+}
+
+int rvcr_retrieve_blend_assigned(rvcr_index* h, float* feats_dev, int64_t n, const int32_t* assign_dev, double index_rate,
+                                 float* D_dev, int64_t* I_dev, void* stream) {
+    RVCR_ENTER(h);
+    if (n > 0 && (!feats_dev || !assign_dev)) return RVCR_ERR_INVALID;
+    return search_device(h, feats_dev, n, assign_dev, true, index_rate, D_dev, I_dev, (cudaStream_t)stream);
+}
+
+int rvcr_reconstruct_n(rvcr_index* h, int64_t i0, int64_t ni, float* out, int out_on_device) {
+    RVCR_ENTER(h);
+    if (i0 < 0 || ni < 0 || i0 + ni > h->ntotal || (ni > 0 && !out)) {
+        set_error("reconstruct_n(%lld, %lld) out of range (ntotal=%lld)", (long long)i0, (long long)ni, (long long)h->ntotal);
+        return RVCR_ERR_INVALID;
+    }
+    if (ni == 0) return RVCR_OK;
+    cudaStream_t s = nullptr;
+    RVCR_TRY(finalize_pending(h, s));
+    if (out_on_device) {
+        RVCR_TRY(reconstruct(h, i0, ni, out, s));
+        RVCR_CUDA(cudaStreamSynchronize(s));
+        return RVCR_OK;
+    }
+    // host output: reconstruct in id-range chunks of <= 256 MB through device scratch
+    const size_t rowb = (size_t)h->d * sizeof(float);
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((256u << 20) / rowb));
+    RVCR_TRY(h->ws_stage.reserve((size_t)std::min<int64_t>(chunk, ni) * rowb));
+    for (int64_t a = 0; a < ni; a += chunk) {
+        const int64_t m = std::min<int64_t>(chunk, ni - a);
+        RVCR_TRY(reconstruct(h, i0 + a, m, h->ws_stage.as<float>(), s));
+        RVCR_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(out) + (size_t)a * rowb, h->ws_stage.p, (size_t)m * rowb,
+                                  cudaMemcpyDeviceToHost, s));
+        RVCR_CUDA(cudaStreamSynchronize(s));
+    }
+    return RVCR_OK;
+}
+
+int rvcr_merge_coarse(const float* dist_all_dev, const int32_t* list_all_dev, int32_t G, int64_t n, int32_t* list_out_dev,
+                      int device, void* stream) {
+    if (G < 1 || n < 0 || (n > 0 && (!dist_all_dev || !list_all_dev || !list_out_dev))) return RVCR_ERR_INVALID;
+    DeviceGuard g(device);
+    if (!g.ok) return RVCR_ERR_CUDA;
+    return merge_coarse(dist_all_dev, list_all_dev, G, n, list_out_dev, (cudaStream_t)stream);
+}
+
+int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, int32_t G, int64_t n, int32_t k, float* D_out_dev,
+                    int64_t* I_out_dev, int device, void* stream) {
+    if (G < 1 || n < 0 || k < 1 || (n > 0 && (!D_all_dev || !I_all_dev || !D_out_dev || !I_out_dev))) return RVCR_ERR_INVALID;
+    DeviceGuard g(device);
+    if (!g.ok) return RVCR_ERR_CUDA;
+    return merge_topk(D_all_dev, I_all_dev, G, n, k, D_out_dev, I_out_dev, (cudaStream_t)stream);
+}
+
+int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
+    if (!h || !key) return RVCR_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!strcmp(key, "coarse_mode")) {
+        if (value < 0 || value > 3) return RVCR_ERR_INVALID;
+        h->opt.coarse_mode = value;
+    } else if (!strcmp(key, "nan_on_zero_score")) {
+        if (value != 1) {
+            set_error("only the reference behaviour (NaN row on a zero score) is implemented");
+            return RVCR_ERR_UNSUPPORTED;
+        }
+        h->opt.nan_on_zero_score = value;
+    } else {
+        set_error("unknown option '%s'", key);
+        return RVCR_ERR_INVALID;
+    }
+    return RVCR_OK;
+}
+
+int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out) {
+    if (!h || !key || !value_out) return RVCR_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!strcmp(key, "coarse_mode")) *value_out = h->opt.coarse_mode;
+    else if (!strcmp(key, "nan_on_zero_score")) *value_out = h->opt.nan_on_zero_score;
+    else if (!strcmp(key, "coarse_tc_available")) *value_out = coarse_tc_available() ? 1 : 0;
+    else {
+        set_error("unknown option '%s'", key);
+        return RVCR_ERR_INVALID;
+    }
+    return RVCR_OK;
+}
+
+int rvcr_get_stats(rvcr_index* h, rvcr_stats* out) {
+    if (!h || !out) return RVCR_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(h->mu);
+    *out = h->stats;
+    return RVCR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,184 @@
+// common.cuh -- shared definitions for the librvcr CUDA sources (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rvcr.h"
+
+#define RVCR_FLT_MAX 3.402823466e+38f
+#define RVCR_K 8  // k of index.search(npy, k=8), rvc/infer/pipeline.py:499
+
+namespace rvcr {
+
+// ---------------------------------------------------------------- error plumbing (host) ----
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define RVCR_CUDA(expr)                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            rvcr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                            __LINE__);                                                       \
+            return RVCR_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define RVCR_TRY(expr)            \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != RVCR_OK) return _r; \
+    } while (0)
+
+#define RVCR_CHECK_LAUNCH()                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) {                                                              \
+            rvcr::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
+                            __LINE__);                                                        \
+            return RVCR_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+// Device buffer grown on demand; never shrinks.  Growth synchronises the device (rare).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <class T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+struct Options {
+    int64_t coarse_mode = 0;  // 0 auto, 1 exact FFMA, 2 tcgen05 bf16, 3 tcgen05 3-way split
+    int64_t nan_on_zero_score = 1;
+};
+
+}  // namespace rvcr
+
+// The handle behind the C ABI.
+struct rvcr_index {
+    int device = 0;
+    int d = 0;
+    int metric = 1;
+    bool trained = false;
+    int64_t nlist = 0;         // lists held by this handle
+    int64_t nlist_global = 0;  // lists of the whole index
+    int64_t list_begin = 0;    // first global list id held
+    int64_t ntotal = 0;        // faiss ntotal of the whole index
+    int64_t nstored = 0;       // rows in `vecs`
+    int64_t nprobe = 1;
+    int num_sms = 148;
+
+    // quantizer
+    float* cent = nullptr;             // nlist x d fp32
+    // tcgen05 operands (built lazily by coarse_tc.cu)
+    void* cent_bf16 = nullptr;         // nlist_pad x kdim bf16, K-major
+    float* cent_norm = nullptr;        // nlist_pad fp32 ||c||^2 (pad rows = +inf)
+    float cent_norm_max = 0.f;         // max ||c||
+    int64_t cent_pad = 0;
+    int cent_kdim = 0;                 // d (mode 2) or 3d (mode 3)
+    int cent_split = 0;
+
+    // list-ordered storage
+    float* vecs = nullptr;             // nstored x d fp32
+    int64_t* ids = nullptr;            // nstored
+    int64_t* offsets = nullptr;        // nlist + 1 (device)
+    std::vector<int64_t> offsets_host; // nlist + 1
+    int64_t last_row_pos = -1;         // position of id ntotal-1 (numpy's big_npy[-1])
+    size_t vecs_cap = 0;               // rows allocated
+
+    // staged adds (id order), folded into the list layout by finalize_pending()
+    float* stage_x = nullptr;          // stage_cap x d
+    int32_t* stage_assign = nullptr;   // stage_cap
+    int64_t stage_cap = 0;
+    int64_t npending = 0;
+
+    // per-call scratch
+    rvcr::DevBuf ws_assign, ws_keys, ws_vals, ws_keys2, ws_vals2, ws_cub, ws_items, ws_flags, ws_misc,
+        ws_D, ws_P, ws_I, ws_best, ws_q, ws_tc0, ws_tc1, ws_tc2, ws_tc3, ws_stage;
+    cudaEvent_t last_done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
+
+    rvcr::Options opt;
+    rvcr_stats stats{};
+    std::mutex mu;
+};
+
+namespace rvcr {
+
+// ------------------------------------------------------------------ kernel entry points ----
+// (host wrappers; all enqueue on `stream`, return RVCR_* codes)
+
+// coarse_exact.cu : brute-force canonical nearest centroid (FFMA pipe)
+int coarse_exact(rvcr_index* h, const float* q, int64_t n, const int32_t* qsel /*nullable*/,
+                 int64_t nsel, int32_t* list_out, float* dist_out, cudaStream_t s);
+// coarse_tc.cu : tcgen05 bf16 approximate top-8 + exact re-check
+int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out,
+              cudaStream_t s);
+bool coarse_tc_available();
+int coarse_tc_invalidate(rvcr_index* h);
+// scan_topk.cu
+int group_queries(rvcr_index* h, const int32_t* assign, int64_t n, bool only_local, cudaStream_t s);
+int scan_topk(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, int64_t* I,
+              cudaStream_t s);
+// blend.cu
+int gather_blend(rvcr_index* h, float* feats, int64_t n, const float* D, const int32_t* P,
+                 const int32_t* assign /*nullable: restrict to owned*/, double index_rate,
+                 cudaStream_t s);
+int merge_coarse(const float* dist_all, const int32_t* list_all, int G, int64_t n, int32_t* out,
+                 cudaStream_t s);
+int merge_topk(const float* D_all, const int64_t* I_all, int G, int64_t n, int k, float* D, int64_t* I,
+               cudaStream_t s);
+// lists.cu
+int finalize_pending(rvcr_index* h, cudaStream_t s);
+int reconstruct(rvcr_index* h, int64_t i0, int64_t ni, float* out_dev, cudaStream_t s);
+int refresh_derived(rvcr_index* h, cudaStream_t s);
+
+inline void count_launch(rvcr_index* h, int n = 1) {
+    if (h) h->stats.kernels_launched += n;
+}
+
+}  // namespace rvcr
+
+// -------------------------------------------------------------------------- device helpers --
+#ifdef __CUDACC__
+namespace rvcr {
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// (dist, pos) strict total order used everywhere a top-k decision is made: distance ascending,
+// then list position ascending (== the entry faiss scans first).
+__device__ __forceinline__ bool cand_less(float da, int pa, float db, int pb) {
+    return (da < db) || (da == db && pa < pb);
+}
+
+// canonical 8-lane reduction of faiss fvec_L2sqr: lanes l (0..7) hold acc[l]; afterwards every
+// lane holds ((a0+a4)+(a1+a5))+((a2+a6)+(a3+a7)).  fp32 add is commutative, so the xor
+// butterfly gives bit-identical results on all 8 lanes.
+__device__ __forceinline__ float reduce8_canonical(float a) {
+    a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 4));
+    a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 1));
+    a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 2));
+    return a;
+}
+
+}  // namespace rvcr
+#endif

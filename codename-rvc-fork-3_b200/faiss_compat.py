@@ -1,0 +1,329 @@
+"""faiss-shaped host objects over the C ABI, so the reference call sites run unmodified.
+
+Mirrors exactly the surface the reference uses:
+
+    rvc/infer/pipeline.py:555-556      index = faiss.read_index(path); big_npy = index.reconstruct_n(0, index.ntotal)
+    rvc/infer/pipeline.py:456-457      if index:                      (object must be truthy)
+    rvc/infer/pipeline.py:499          score, ix = index.search(npy, k=8)
+    rvc/train/process/extract_index.py:62-71
+                                       index_factory(768, "IVF{n},Flat"); extract_index_ivf(i).nprobe = 1;
+                                       i.train(x); i.add(x[a:b]); write_index(i, path)
+
+Same names, argument meaning and error behaviour as faiss's Python wrapper: `search`
+wants an (n, d) array, casts to C-contiguous float32 and returns new (n, k) float32 / int64 arrays;
+failures raise (RvcrError is a RuntimeError) and the reference's own try/except handles them.
+All arithmetic runs in librvcr.so on the GPU; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import Info, RvcrError, Stats, check, lib
+
+METRIC_L2 = 1
+
+
+def _default_device() -> int:
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_device())
+    except Exception:
+        pass
+    return 0
+
+
+def _as_f32_2d(x, d: int, what: str) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim != 2 or x.shape[1] != d:
+        raise AssertionError(f"{what}: expected shape (n, {d}), got {x.shape}")
+    return x
+
+
+class IndexIVFFlat:
+    """Device-resident IVF-Flat index (faiss.IndexIVFFlat stand-in)."""
+
+    def __init__(self, handle: int, owner: bool = True):
+        self._h = C.c_void_p(handle)
+        self._owner = owner
+
+    # -- lifecycle -------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value and self._owner:
+            lib().rvcr_index_free(self._h)
+        self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __bool__(self) -> bool:  # `if index:` at pipeline.py:456-457
+        return True
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if not self._h.value:
+            raise RvcrError(-6, "index handle is closed")
+        return self._h
+
+    def _info(self) -> Info:
+        inf = Info()
+        check(lib().rvcr_index_info(self.handle, C.byref(inf)))
+        return inf
+
+    # -- faiss attributes ------------------------------------------------------------------
+    @property
+    def d(self) -> int:
+        return int(self._info().d)
+
+    @property
+    def ntotal(self) -> int:
+        return int(self._info().ntotal)
+
+    @property
+    def nlist(self) -> int:
+        return int(self._info().nlist)
+
+    @property
+    def is_trained(self) -> bool:
+        return bool(self._info().is_trained)
+
+    @property
+    def metric_type(self) -> int:
+        return int(self._info().metric)
+
+    @property
+    def nprobe(self) -> int:
+        return int(self._info().nprobe)
+
+    @nprobe.setter
+    def nprobe(self, v: int) -> None:  # extract_index.py:64
+        check(lib().rvcr_index_set_nprobe(self.handle, int(v)))
+
+    @property
+    def device(self) -> int:
+        return int(self._info().device)
+
+    @property
+    def info(self) -> dict:
+        inf = self._info()
+        return {k: int(getattr(inf, k)) for k, _ in Info._fields_}
+
+    # -- quantizer -------------------------------------------------------------------------
+    def set_centroids(self, centroids) -> None:
+        inf = self._info()
+        c = _as_f32_2d(centroids, inf.d, "set_centroids")
+        check(lib().rvcr_index_set_centroids(self.handle, c.ctypes.data_as(C.c_void_p), c.shape[0]))
+
+    def get_centroids(self) -> np.ndarray:
+        inf = self._info()
+        out = np.empty((inf.nlist, inf.d), np.float32)
+        check(lib().rvcr_index_get_centroids(self.handle, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def list_sizes(self) -> np.ndarray:
+        out = np.empty(self._info().nlist, np.int64)
+        check(lib().rvcr_index_list_sizes(self.handle, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # -- build (extract_index.py:65-69) ----------------------------------------------------
+    def train(self, x) -> None:
+        """faiss Clustering k-means: host-side Lloyd loop over the GPU assignment."""
+        from .kmeans import train_ivf_centroids
+        inf = self._info()
+        x = _as_f32_2d(x, inf.d, "train")
+        self.set_centroids(train_ivf_centroids(self, x, int(inf.nlist)))
+
+    def add(self, x) -> None:
+        """index.add(x): host (numpy) or device (torch.cuda) rows."""
+        inf = self._info()
+        if _is_cuda_tensor(x):
+            t = _check_cuda_tensor(x, inf, "add")
+            check(lib().rvcr_index_add(self.handle, C.c_void_p(t.data_ptr()), t.shape[0], 1, _stream_of(t)))
+            return
+        x = _as_f32_2d(x, inf.d, "add")
+        check(lib().rvcr_index_add(self.handle, x.ctypes.data_as(C.c_void_p), x.shape[0], 0, None))
+
+    # -- query (pipeline.py:499, 556) ------------------------------------------------------
+    def search(self, x, k: int = 8):
+        """index.search(x, k): (D (n,k) float32 squared-L2 ascending, I (n,k) int64), padded with
+        (FLT_MAX, -1).  numpy in -> numpy out (H2D + D2H inside); torch.cuda in -> torch.cuda out."""
+        inf = self._info()
+        if _is_cuda_tensor(x):
+            import torch
+            t = _check_cuda_tensor(x, inf, "search")
+            D = torch.empty((t.shape[0], k), dtype=torch.float32, device=t.device)
+            I = torch.empty((t.shape[0], k), dtype=torch.int64, device=t.device)
+            check(lib().rvcr_search(self.handle, C.c_void_p(t.data_ptr()), t.shape[0], k,
+                                    C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()), _stream_of(t)))
+            return D, I
+        x = _as_f32_2d(x, inf.d, "search")
+        n = x.shape[0]
+        D = np.empty((n, k), np.float32)
+        I = np.empty((n, k), np.int64)
+        check(lib().rvcr_search_host(self.handle, x.ctypes.data_as(C.c_void_p), n, k,
+                                     D.ctypes.data_as(C.c_void_p), I.ctypes.data_as(C.c_void_p)))
+        return D, I
+
+    def assign(self, x):
+        """quantizer.assign: nearest-centroid list id (int32) and canonical distance per row."""
+        import torch
+        inf = self._info()
+        t = _check_cuda_tensor(x, inf, "assign")
+        lst = torch.empty(t.shape[0], dtype=torch.int32, device=t.device)
+        dist = torch.empty(t.shape[0], dtype=torch.float32, device=t.device)
+        check(lib().rvcr_assign(self.handle, C.c_void_p(t.data_ptr()), t.shape[0], C.c_void_p(lst.data_ptr()),
+                                C.c_void_p(dist.data_ptr()), _stream_of(t)))
+        return lst, dist
+
+    def reconstruct_n(self, n0: int = 0, ni: int | None = None) -> np.ndarray:
+        """index.reconstruct_n(n0, ni) -> new (ni, d) float32 array (`big_npy`)."""
+        inf = self._info()
+        ni = inf.ntotal - n0 if ni is None or ni < 0 else ni
+        out = np.empty((ni, inf.d), np.float32)
+        check(lib().rvcr_reconstruct_n(self.handle, int(n0), int(ni), out.ctypes.data_as(C.c_void_p), 0))
+        return out
+
+    def retrieve_blend_(self, feats, index_rate: float, want_neighbours: bool = False):
+        """Fused replacement of the body of `_retrieve_speaker_embeddings` (pipeline.py:498-506):
+        search(k=8) + 1/score^2 weights + gather + blend, IN PLACE on a (n, d) or (1, n, d) CUDA
+        float32 tensor.  Returns feats (and (D, I) when asked)."""
+        import torch
+        inf = self._info()
+        t = feats
+        if t.dim() == 3:
+            if t.shape[0] != 1:
+                raise AssertionError("retrieve_blend_: batch dimension must be 1 (pipeline.py:498 uses feats[0])")
+            t = t[0]
+        t = _check_cuda_tensor(t, inf, "retrieve_blend_")
+        n = t.shape[0]
+        D = I = None
+        if want_neighbours:
+            D = torch.empty((n, 8), dtype=torch.float32, device=t.device)
+            I = torch.empty((n, 8), dtype=torch.int64, device=t.device)
+        check(lib().rvcr_retrieve_blend(self.handle, C.c_void_p(t.data_ptr()), n, float(index_rate),
+                                        C.c_void_p(D.data_ptr()) if D is not None else None,
+                                        C.c_void_p(I.data_ptr()) if I is not None else None, _stream_of(t)))
+        return (feats, D, I) if want_neighbours else feats
+
+    def retrieve_blend_host_(self, feats: np.ndarray, index_rate: float) -> np.ndarray:
+        """Same, on a host (n, d) float32 C-contiguous array, in place (H2D / D2H inside)."""
+        inf = self._info()
+        if not (isinstance(feats, np.ndarray) and feats.dtype == np.float32 and feats.flags.c_contiguous
+                and feats.ndim == 2 and feats.shape[1] == inf.d):
+            raise AssertionError(f"retrieve_blend_host_: need a C-contiguous float32 (n, {inf.d}) array")
+        check(lib().rvcr_retrieve_blend_host(self.handle, feats.ctypes.data_as(C.c_void_p), feats.shape[0],
+                                             float(index_rate)))
+        return feats
+
+    # -- options / stats -------------------------------------------------------------------
+    def set_option(self, key: str, value: int) -> None:
+        check(lib().rvcr_set_option(self.handle, key.encode(), int(value)))
+
+    def get_option(self, key: str) -> int:
+        v = C.c_int64(0)
+        check(lib().rvcr_get_option(self.handle, key.encode(), C.byref(v)))
+        return int(v.value)
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(lib().rvcr_get_stats(self.handle, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_ if k != "reserved"}
+
+    # -- zero-copy construction ------------------------------------------------------------
+    def alloc_lists(self, sizes, ntotal: int) -> None:
+        sizes = np.ascontiguousarray(sizes, np.int64)
+        assert sizes.shape == (self._info().nlist,)
+        check(lib().rvcr_index_alloc_lists(self.handle, sizes.ctypes.data_as(C.c_void_p), int(ntotal)))
+
+    def device_views(self):
+        """torch views (no copy) of the list-ordered storage: (vecs (nstored,d) f32, ids (nstored,)
+        i64, offsets (nlist+1,) i64, centroids (nlist,d) f32).  Call commit() after writing."""
+        inf = self._info()
+        pv, pi, po, pc = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().rvcr_index_device_ptrs(self.handle, C.byref(pv), C.byref(pi), C.byref(po), C.byref(pc)))
+        inf = self._info()
+        dev = int(inf.device)
+        return (_view(pv.value, (int(inf.nstored), int(inf.d)), "<f4", dev),
+                _view(pi.value, (int(inf.nstored),), "<i8", dev),
+                _view(po.value, (int(inf.nlist) + 1,), "<i8", dev),
+                _view(pc.value, (int(inf.nlist), int(inf.d)), "<f4", dev) if inf.is_trained else None)
+
+    def commit(self) -> None:
+        check(lib().rvcr_index_commit(self.handle, None))
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (ptr, False), "shape": tuple(shape), "typestr": typestr,
+                                         "version": 2, "strides": None}
+
+
+def _view(ptr, shape, typestr, device):
+    import torch
+    if not ptr or int(np.prod(shape)) == 0:
+        dt = torch.float32 if typestr == "<f4" else torch.int64
+        return torch.empty(shape, dtype=dt, device=f"cuda:{device}")
+    with torch.cuda.device(device):
+        return torch.as_tensor(_CudaArray(ptr, shape, typestr), device=f"cuda:{device}")
+
+
+def _is_cuda_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and getattr(x, "is_cuda", False)
+
+
+def _check_cuda_tensor(t, inf: Info, what: str):
+    import torch
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] == inf.d and t.is_contiguous()):
+        raise AssertionError(f"{what}: need a contiguous float32 CUDA tensor of shape (n, {inf.d}), "
+                             f"got {tuple(t.shape)} {t.dtype} {t.device}")
+    if t.device.index != inf.device:
+        raise AssertionError(f"{what}: tensor is on {t.device}, index lives on cuda:{inf.device}")
+    return t
+
+
+def _stream_of(t):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+# ---- module-level faiss functions ------------------------------------------------------------
+
+def read_index(path: str, device: int | None = None, shard: tuple[int, int] | None = None) -> IndexIVFFlat:
+    """faiss.read_index(path) (pipeline.py:555).  `shard=(rank, world)` keeps one shard's lists."""
+    h = C.c_void_p()
+    dev = _default_device() if device is None else int(device)
+    if shard is None:
+        check(lib().rvcr_index_read(str(path).encode(), dev, C.byref(h)))
+    else:
+        check(lib().rvcr_index_read_shard(str(path).encode(), dev, int(shard[0]), int(shard[1]), C.byref(h)))
+    return IndexIVFFlat(h.value)
+
+
+def write_index(index: IndexIVFFlat, path: str) -> None:
+    """faiss.write_index(index, path) (extract_index.py:71)."""
+    check(lib().rvcr_index_write(index.handle, str(path).encode()))
+
+
+def index_factory(d: int, description: str, metric: int = METRIC_L2, device: int | None = None) -> IndexIVFFlat:
+    """faiss.index_factory(d, "IVF{nlist},Flat") (extract_index.py:62); other strings are out of scope."""
+    m = re.fullmatch(r"IVF(\d+),Flat", description.strip())
+    if not m:
+        raise RvcrError(-5, f"index_factory: only 'IVF<nlist>,Flat' is supported, got {description!r}")
+    if metric != METRIC_L2:
+        raise RvcrError(-5, "index_factory: only METRIC_L2 is supported")
+    h = C.c_void_p()
+    dev = _default_device() if device is None else int(device)
+    check(lib().rvcr_index_create(int(d), int(m.group(1)), dev, C.byref(h)))
+    return IndexIVFFlat(h.value)
+
+
+def extract_index_ivf(index: IndexIVFFlat) -> IndexIVFFlat:
+    """faiss.extract_index_ivf(index) (extract_index.py:63): the IVF index is the object itself."""
+    return index

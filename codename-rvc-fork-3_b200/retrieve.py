@@ -1,0 +1,47 @@
+"""Drop-in for `Pipeline._retrieve_speaker_embeddings` (rvc/infer/pipeline.py:497-507).
+
+    def _retrieve_speaker_embeddings(self, feats, index, big_npy, index_rate): ...
+
+Same signature, same return value (a (1, n, d) float32 tensor on feats' device), but the whole body
+-- D2H copy, faiss search, numpy weighting / gather / sum, H2D copy, blend -- is one call into
+librvcr that never leaves the GPU.  `big_npy` is accepted and ignored: the gather reads the index's
+own list-ordered storage.  The reference returns a NEW tensor and keeps `feats0 = feats.clone()`
+taken before the call (pipeline.py:455), so blending in place on `feats` is safe; pass
+`inplace=False` to keep the input untouched.
+"""
+from __future__ import annotations
+
+from .faiss_compat import IndexIVFFlat
+
+
+def retrieve_speaker_embeddings(feats, index: IndexIVFFlat, big_npy=None, index_rate: float = 0.75,
+                                inplace: bool = True):
+    """feats: (1, n, d) float32 CUDA tensor (HuBERT / ContentVec last_hidden_state)."""
+    if not isinstance(index, IndexIVFFlat):
+        raise TypeError("index must come from codename-rvc-fork-3_b200.read_index / index_factory")
+    f = feats if inplace else feats.clone()
+    if not f.is_contiguous():
+        f = f.contiguous()
+    index.retrieve_blend_(f, index_rate)
+    return f
+
+
+def _method(self, feats, index, big_npy, index_rate):
+    return retrieve_speaker_embeddings(feats, index, big_npy, index_rate)
+
+
+def patch_pipeline(pipeline_cls_or_module, faiss_module_name: str = "faiss") -> None:
+    """Install the fused path on the reference without editing it:
+
+        import rvc.infer.pipeline as P
+        patch_pipeline(P)            # P.faiss -> this package, P.Pipeline._retrieve_speaker_embeddings -> fused
+
+    After this `faiss.read_index` / `index.reconstruct_n` at pipeline.py:555-556 build a device-resident
+    index (big_npy becomes a cheap placeholder) and pipeline.py:459 calls the fused kernel path."""
+    import sys
+    pkg = sys.modules[__package__]
+    target = pipeline_cls_or_module
+    if hasattr(target, "Pipeline"):
+        setattr(target, faiss_module_name, pkg)
+        target = target.Pipeline
+    target._retrieve_speaker_embeddings = _method

@@ -1,0 +1,175 @@
+/*
+ * rvcr.h -- C ABI of the B200-native RVC feature-retrieval library (librvcr.so).
+ *
+ * The reference (codename0og/codename-rvc-fork-3) reaches this path only through the faiss
+ * Python object and eleven lines of numpy/torch; it has no FFI of its own.  Each entry point
+ * below names the reference call it replaces (paths relative to the reference root).  Plain
+ * pointers and sizes only: no torch / numpy types cross this boundary.  The Python host side
+ * (codename-rvc-fork-3_b200/) binds it with ctypes; INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns RVCR_OK (0) or a negative RVCR_ERR_* code; rvcr_last_error() returns
+ *     a thread-local message for the last failure.  Nothing aborts, nothing falls back to a CPU
+ *     implementation: without a CUDA device the compute entry points fail with RVCR_ERR_CUDA.
+ *   - "_dev" pointers are device memory on the index's device, "_host" pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (0 = the legacy default stream).  Compute entry
+ *     points enqueue on it and do not synchronise unless stated.
+ *   - a handle may be used from several threads; calls on one handle are serialised internally.
+ *   - distances are squared L2, in the canonical fp32 evaluation order of faiss fvec_L2sqr
+ *     (8 lanes, fused multiply-add, (m0+m1)+(m2+m3) reduction) -- see DESIGN.md "Numerics".
+ */
+#ifndef RVCR_H_
+#define RVCR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVCR_OK 0
+#define RVCR_ERR_INVALID (-1)      /* bad argument                                   */
+#define RVCR_ERR_IO (-2)           /* file could not be opened / read / written      */
+#define RVCR_ERR_FORMAT (-3)       /* not an IVF-Flat .index file we understand       */
+#define RVCR_ERR_CUDA (-4)         /* CUDA runtime error, or no usable device         */
+#define RVCR_ERR_UNSUPPORTED (-5)  /* valid request outside this library's scope      */
+#define RVCR_ERR_STATE (-6)        /* e.g. search on an untrained index               */
+#define RVCR_ERR_OOM (-7)
+
+#define RVCR_VERSION 100
+
+#if defined(__GNUC__)
+#define RVCR_API __attribute__((visibility("default")))
+#else
+#define RVCR_API
+#endif
+
+typedef struct rvcr_index rvcr_index;
+
+typedef struct rvcr_info {
+    int32_t d;            /* vector dimension (768 for v2 / ContentVec, 256 for v1)             */
+    int32_t is_trained;   /* quantizer holds centroids                                          */
+    int64_t ntotal;       /* faiss Index::ntotal                                                */
+    int64_t nlist;        /* number of inverted lists == number of centroids held by this shard  */
+    int64_t nprobe;       /* value persisted in the file (extract_index.py:64 sets 1)           */
+    int64_t nstored;      /* vectors stored in this handle's lists (== ntotal unless sharded)   */
+    int64_t list_begin;   /* first global list id held (0 unless sharded)                       */
+    int64_t nlist_global; /* number of lists of the whole index                                 */
+    int32_t device;
+    int32_t metric;       /* 1 = METRIC_L2                                                      */
+} rvcr_info;
+
+typedef struct rvcr_stats {
+    int64_t calls_search;       /* search / retrieve_blend calls served                          */
+    int64_t queries;            /* queries processed                                             */
+    int64_t kernels_launched;   /* kernels of this library launched so far (all entry points)    */
+    int64_t coarse_tc_queries;  /* queries whose coarse step ran on the tcgen05 path             */
+    int64_t coarse_candidates;  /* candidates exactly re-checked after the tcgen05 path           */
+    int64_t coarse_fallback;    /* queries re-done by the exact FFMA kernel (margin overflow)     */
+    int64_t scan_items;         /* (list, query-block) work items of the last scan               */
+    int64_t reserved[8];
+} rvcr_stats;
+
+RVCR_API const char* rvcr_last_error(void);
+RVCR_API int rvcr_version(void);
+/* number of CUDA devices visible; RVCR_ERR_CUDA if the runtime cannot be initialised */
+RVCR_API int rvcr_device_count(int* count_out);
+
+/* ---------------------------------------------------------------- lifecycle / persistence -- */
+
+/* faiss.index_factory(d, "IVF{nlist},Flat")            rvc/train/process/extract_index.py:62 */
+RVCR_API int rvcr_index_create(int32_t d, int64_t nlist, int device, rvcr_index** out);
+/* faiss.read_index(path)                                rvc/infer/pipeline.py:555
+ * Streams the file straight into list-ordered device storage; no host copy of the vectors. */
+RVCR_API int rvcr_index_read(const char* path, int device, rvcr_index** out);
+/* Same file, but keeps only the lists of shard `rank` of `world` (contiguous centroid ranges
+ * balanced by vector count).  List ids reported by this handle stay global. */
+RVCR_API int rvcr_index_read_shard(const char* path, int device, int rank, int world, rvcr_index** out);
+/* faiss.write_index(index, path)                        rvc/train/process/extract_index.py:71 */
+RVCR_API int rvcr_index_write(rvcr_index* h, const char* path);
+RVCR_API void rvcr_index_free(rvcr_index* h);
+RVCR_API int rvcr_index_info(rvcr_index* h, rvcr_info* out);
+/* faiss.extract_index_ivf(index).nprobe = v             rvc/train/process/extract_index.py:63-64
+ * The value is persisted; search itself supports nprobe == 1 only (RVCR_ERR_UNSUPPORTED). */
+RVCR_API int rvcr_index_set_nprobe(rvcr_index* h, int64_t nprobe);
+/* Quantizer centroids (nlist x d, row-major fp32, host memory). `set` marks the index trained;
+ * it is what index.train() produces (extract_index.py:65). */
+RVCR_API int rvcr_index_set_centroids(rvcr_index* h, const float* centroids_host, int64_t nlist);
+RVCR_API int rvcr_index_get_centroids(rvcr_index* h, float* centroids_host);
+/* per-list sizes, nlist x int64, host memory */
+RVCR_API int rvcr_index_list_sizes(rvcr_index* h, int64_t* sizes_host);
+
+/* -------------------------------------------------------------------------------- build --- */
+
+/* index.train(x)   (faiss Clustering, niter=10, seed=1234)   extract_index.py:65 */
+RVCR_API int rvcr_index_train(rvcr_index* h, const float* x_host, int64_t n);
+/* index.add(x)     extract_index.py:67-69 : nearest-centroid assignment + list append; ids are
+ * ntotal .. ntotal+n-1; per-list order is ascending id.  x may be host or device memory. */
+RVCR_API int rvcr_index_add(rvcr_index* h, const float* x, int64_t n, int x_on_device, void* stream);
+/* The same append with the assignment supplied by the caller (int32 list ids, device). */
+RVCR_API int rvcr_index_add_preassigned(rvcr_index* h, const float* x_dev, int64_t n, const int32_t* assign_dev,
+                               void* stream);
+/* Allocate list storage for the given final list sizes (host, nlist x int64) and mark every
+ * list full: the caller fills the storage in place through rvcr_index_device_ptrs.  Used for
+ * zero-copy construction of very large indices (98 GB at 32M x 768). */
+RVCR_API int rvcr_index_alloc_lists(rvcr_index* h, const int64_t* sizes_host, int64_t ntotal);
+/* Raw device views of the list-ordered storage: vectors (nstored x d fp32), ids (nstored x
+ * int64), list offsets (nlist+1 x int64), centroids (nlist x d fp32).  Any may be NULL. */
+RVCR_API int rvcr_index_device_ptrs(rvcr_index* h, float** vecs_dev, int64_t** ids_dev, int64_t** offsets_dev,
+                           float** centroids_dev);
+/* Call after writing storage obtained from rvcr_index_device_ptrs (refreshes derived data). */
+RVCR_API int rvcr_index_commit(rvcr_index* h, void* stream);
+
+/* ------------------------------------------------------------------------------- search --- */
+
+/* quantizer->assign(n, x): nearest centroid (global list id), lowest id on ties; optional
+ * canonical distance to it.                  faiss IndexFlatL2::search(k=1), pipeline.py:499 */
+RVCR_API int rvcr_assign(rvcr_index* h, const float* x_dev, int64_t n, int32_t* list_out_dev,
+                float* dist_out_dev /* may be NULL */, void* stream);
+/* index.search(x, k=8)                                        rvc/infer/pipeline.py:499
+ * D: n x k fp32 ascending, I: n x k int64, padded with (FLT_MAX, -1). k must be 8. */
+RVCR_API int rvcr_search(rvcr_index* h, const float* q_dev, int64_t n, int32_t k, float* D_dev, int64_t* I_dev,
+                void* stream);
+/* The faiss-shaped host call: H2D copy, search, D2H copy, synchronises. */
+RVCR_API int rvcr_search_host(rvcr_index* h, const float* q_host, int64_t n, int32_t k, float* D_host,
+                     int64_t* I_host);
+/* _retrieve_speaker_embeddings(feats, index, big_npy, index_rate)   pipeline.py:497-507
+ * search(k=8) + 1/score^2 weights + gather + weighted sum + index_rate blend, written IN PLACE
+ * into feats_dev (n x d fp32).  D_dev / I_dev (n x 8) are optional outputs. */
+RVCR_API int rvcr_retrieve_blend(rvcr_index* h, float* feats_dev, int64_t n, double index_rate, float* D_dev,
+                        int64_t* I_dev, void* stream);
+/* Same with host buffers (pinned or pageable): H2D, retrieve_blend, D2H, synchronises. */
+RVCR_API int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double index_rate);
+/* index.reconstruct_n(i0, ni)  ->  big_npy                      rvc/infer/pipeline.py:556 */
+RVCR_API int rvcr_reconstruct_n(rvcr_index* h, int64_t i0, int64_t ni, float* out, int out_on_device);
+
+/* ------------------------------------------------------------------- multi-GPU (shards) --- */
+
+/* Global argmin over G shards' (distance, list id) pairs, lowest list id on equal distance.
+ * dist_all / list_all are G x n (shard-major, as produced by an all-gather of rvcr_assign
+ * outputs).  Output: n global list ids. */
+RVCR_API int rvcr_merge_coarse(const float* dist_all_dev, const int32_t* list_all_dev, int32_t G, int64_t n,
+                      int32_t* list_out_dev, int device, void* stream);
+/* retrieve_blend for the queries whose list (global id in assign_dev) this shard holds; rows
+ * of other queries are left untouched and their D / I rows are set to (FLT_MAX, -1). */
+RVCR_API int rvcr_retrieve_blend_assigned(rvcr_index* h, float* feats_dev, int64_t n, const int32_t* assign_dev,
+                                 double index_rate, float* D_dev, int64_t* I_dev, void* stream);
+/* Merge G shards' top-8 candidate lists (G x n x 8, after an all-gather) into the global
+ * top-8 by (distance, id). */
+RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, int32_t G, int64_t n, int32_t k,
+                    float* D_out_dev, int64_t* I_out_dev, int device, void* stream);
+
+/* --------------------------------------------------------------------- options / stats ---- */
+
+/* keys: "coarse_mode" 0 = auto, 1 = exact FFMA kernel, 2 = tcgen05 bf16 + exact re-check,
+ *                     3 = tcgen05 3-way split bf16 + exact re-check
+ *       "nan_on_zero_score" 1 (default, reference behaviour: exact-match query -> NaN row) */
+RVCR_API int rvcr_set_option(rvcr_index* h, const char* key, int64_t value);
+RVCR_API int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out);
+RVCR_API int rvcr_get_stats(rvcr_index* h, rvcr_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVCR_H_ */

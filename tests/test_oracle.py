@@ -1,0 +1,142 @@
+"""CPU: the oracle against the committed golden vectors and against independent restatements."""
+import numpy as np
+import pytest
+
+FLT_MAX = np.float32(3.4028234663852886e38)
+
+
+def py_l2sqr_canonical(x, y):
+    """Pure-Python restatement of faiss fvec_L2sqr (AVX order) with an exact FMA:
+    fma(t, t, acc) is computed in exact rational arithmetic and rounded once to float32."""
+    from fractions import Fraction
+    acc = [Fraction(0)] * 8
+    accf = [np.float32(0)] * 8
+    for i in range(0, len(x), 8):
+        for l in range(8):
+            t = np.float32(x[i + l]) - np.float32(y[i + l])
+            exact = Fraction(float(t)) * Fraction(float(t)) + Fraction(float(accf[l]))
+            accf[l] = _round_f32(exact)
+    m = [np.float32(accf[l] + accf[l + 4]) for l in range(4)]
+    return np.float32(np.float32(m[0] + m[1]) + np.float32(m[2] + m[3]))
+
+
+def _round_f32(fr):
+    """Round an exact Fraction to the nearest float32 (ties to even)."""
+    if fr == 0:
+        return np.float32(0)
+    f = float(fr)              # rounds to double first; refine below to avoid double rounding
+    lo = np.float32(f)
+    # candidates: lo and its neighbours
+    cands = {lo, np.nextafter(lo, np.float32(np.inf)), np.nextafter(lo, np.float32(-np.inf))}
+    from fractions import Fraction
+    best = None
+    for c in cands:
+        err = abs(Fraction(float(c)) - fr)
+        key = (err, int(np.float32(c).view(np.uint32)) & 1)
+        if best is None or key < best[0]:
+            best = (key, c)
+    return np.float32(best[1])
+
+
+def test_canonical_distance_matches_python_restatement(oracle):
+    rng = np.random.default_rng(1)
+    for d in (8, 64, 256):
+        for _ in range(6):
+            x = (rng.standard_normal(d) * 0.33).astype(np.float32)
+            y = (rng.standard_normal(d) * 0.33).astype(np.float32)
+            assert oracle.l2sqr(x, y) == py_l2sqr_canonical(x, y)
+    x = (rng.standard_normal(768) * 0.33).astype(np.float32)
+    assert oracle.l2sqr(x, x) == 0.0
+    # the non-FMA variant stays within a few ulp (tie-zone classification input)
+    y = (rng.standard_normal(768) * 0.33).astype(np.float32)
+    a, b = oracle.l2sqr(x, y), oracle.l2sqr(x, y, fma=False)
+    assert abs(float(a) - float(b)) <= 1e-5 * float(a)
+
+
+@pytest.mark.parametrize("name", ["retrieve_v2_768", "retrieve_v1_256"])
+def test_tail_matches_reference_function_output(oracle, golden, name):
+    """PINNED: oracle.tail == the reference's own _retrieve_speaker_embeddings body (pipeline.py:500-506)
+    executed in the build container on real ContentVec fixtures, bit for bit (NaN rows included)."""
+    g = golden(name)
+    with np.errstate(all="ignore"):
+        out = oracle.tail(g["score"], g["ix"], g["x"], float(g["index_rate"]), g["q"])
+        out2 = oracle.tail_numpy_verbatim(g["score"], g["ix"], g["x"], float(g["index_rate"]), g["q"])
+    assert np.array_equal(out, g["out"], equal_nan=True)
+    assert np.array_equal(out2, g["out"], equal_nan=True)
+    if name == "retrieve_v2_768":
+        assert np.isnan(g["out"]).any(axis=1).sum() == 3      # queries equal to an indexed row
+    assert (g["ix"] < 0).any()                                 # lists shorter than 8 exercise the padding
+
+
+@pytest.mark.parametrize("name", ["retrieve_v2_768", "retrieve_v1_256"])
+def test_search_reproduces_golden(oracle, golden, name):
+    g = golden(name)
+    idx = oracle.OracleIndex.from_vectors(g["x"], g["centroids"])
+    assert np.array_equal(idx.list_off, g["list_off"]) and np.array_equal(idx.ids, g["list_ids"])
+    D, I = idx.search(g["q"], k=8)
+    assert np.array_equal(D, g["score"]) and np.array_equal(I, g["ix"])
+    a, cd = oracle.coarse_assign(g["q"], g["centroids"])
+    assert np.array_equal(a, g["assign"]) and np.array_equal(cd, g["coarse_dist"])
+
+
+def test_scan_semantics_against_bruteforce(oracle):
+    """top-8 == stable argsort of canonical distances by (distance, list position); pads (FLT_MAX,-1)."""
+    rng = np.random.default_rng(7)
+    d = 64
+    x = (rng.standard_normal((500, d)) * 0.33).astype(np.float32)
+    x[100:140] = x[50]                       # 41 identical rows -> ties at the k-th boundary
+    cent = x[rng.choice(500, 40, replace=False)].copy()
+    idx = oracle.OracleIndex.from_vectors(x, cent)
+    q = np.concatenate([x[45:55] + 0.01, x[:5], (rng.standard_normal((20, d)) * 0.33)]).astype(np.float32)
+    D, I, P = oracle.scan_topk(q, oracle.coarse_assign(q, cent)[0], idx.list_off, idx.vecs, idx.ids, want_pos=True)
+    a, _ = oracle.coarse_assign(q, cent)
+    for i in range(len(q)):
+        b, e = idx.list_off[a[i]], idx.list_off[a[i] + 1]
+        dist = np.array([oracle.l2sqr(q[i], idx.vecs[p]) for p in range(b, e)], np.float32)
+        order = np.argsort(dist, kind="stable")[:8]
+        n = len(order)
+        assert np.array_equal(D[i, :n], dist[order]) and np.array_equal(P[i, :n], b + order)
+        assert np.array_equal(I[i, :n], idx.ids[b + order])
+        assert (D[i, n:] == FLT_MAX).all() and (I[i, n:] == -1).all()
+        # ids ascend with list position (faiss add order), so ties resolve to the lower id
+        assert (np.diff(idx.ids[b:e]) > 0).all()
+
+
+def test_coarse_lowest_id_on_ties_and_blas_agreement(oracle):
+    rng = np.random.default_rng(3)
+    cent = (rng.standard_normal((200, 128)) * 0.33).astype(np.float32)
+    cent[150] = cent[20]                      # duplicate centroid: the lower id must win
+    q = (cent[[20, 150, 7]] + 0.001).astype(np.float32)
+    a, dist, gap = oracle.coarse_assign(q, cent, want_gap=True)
+    assert a.tolist() == [20, 20, 7] and gap[0] == 0.0
+    q2 = (rng.standard_normal((300, 128)) * 0.33).astype(np.float32)
+    a2, _, gap2 = oracle.coarse_assign(q2, cent, want_gap=True)
+    a3, _ = oracle.coarse_assign_blas(q2, cent)
+    a4, _ = oracle.coarse_assign(q2, cent, fma=False)
+    clear = gap2 > 1e-3                      # outside the tie zone every evaluation order agrees
+    assert (a2[clear] == a3[clear]).all() and (a2[clear] == a4[clear]).all()
+
+
+def test_add_builds_ascending_id_lists_and_reconstructs(oracle):
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((1000, 64)) * 0.33).astype(np.float32)
+    cent = x[:30].copy()
+    idx = oracle.OracleIndex.from_vectors(x, cent)
+    assert idx.list_off[-1] == 1000
+    for l in range(30):
+        ids = idx.ids[idx.list_off[l]:idx.list_off[l + 1]]
+        assert (np.diff(ids) > 0).all()
+    assert np.array_equal(idx.reconstruct_n(0, 1000), x)
+    assert np.array_equal(idx.reconstruct_n(100, 50), x[100:150])
+
+
+def test_tail_edge_cases(oracle):
+    big = np.arange(40, dtype=np.float32).reshape(5, 8) + 1
+    feats = np.ones((2, 8), np.float32)
+    score = np.array([[1, 2, 3, 4, 5, 6, 7, FLT_MAX], [FLT_MAX] * 8], np.float32)
+    ix = np.array([[0, 1, 2, 3, 4, 0, 1, -1], [-1] * 8], np.int64)
+    with np.errstate(all="ignore"):
+        out = oracle.tail(score, ix, big, 1.0, feats)
+        ref = oracle.tail_numpy_verbatim(score, ix, big, 1.0, feats)
+    assert np.array_equal(out, ref, equal_nan=True)
+    assert np.isfinite(out[0]).all() and np.isnan(out[1]).all()   # all-pad row: 0/0 weights
