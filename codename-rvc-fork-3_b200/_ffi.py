@@ -73,6 +73,7 @@ SIGNATURES = {
     "rvcr_set_option": (C.c_int, [_H, C.c_char_p, _I64]),
     "rvcr_get_option": (C.c_int, [_H, C.c_char_p, C.POINTER(_I64)]),
     "rvcr_get_stats": (C.c_int, [_H, C.POINTER(Stats)]),
+    "rvcr_get_phase_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
 }
 
 _lib = None

@@ -105,6 +105,7 @@ int coarse_dispatch(rvcr_index* h, const float* q, int64_t n, int32_t* list_out,
         h->opt.coarse_mode = h->opt.coarse_mode;  // unchanged; split factor is read by coarse_tc
         return coarse_tc(h, q, n, list_out, dist_out, s);
     }
+    PhaseTimer pt(h, RVCR_PHASE_COARSE_MAIN, s);
     return coarse_exact(h, q, n, nullptr, 0, list_out, dist_out, s);
 }
 
@@ -118,21 +119,31 @@ int search_device(rvcr_index* h, float* feats_or_q, int64_t n, const int32_t* as
     if (n == 0) return RVCR_OK;
     RVCR_TRY(finalize_pending(h, s));
     RVCR_TRY(stream_enter(h, s));
+    for (int i = 0; i < RVCR_NUM_PHASES; ++i) h->pev_used[i] = false;
     const int32_t* assign = assign_in;
     if (!assign) {
         RVCR_TRY(h->ws_assign.reserve((size_t)n * 4));
         RVCR_TRY(coarse_dispatch(h, feats_or_q, n, h->ws_assign.as<int32_t>(), nullptr, s));
         assign = h->ws_assign.as<int32_t>();
     }
-    RVCR_TRY(group_queries(h, assign, n, assign_in != nullptr, s));
+    {
+        PhaseTimer pt(h, RVCR_PHASE_GROUP, s);
+        RVCR_TRY(group_queries(h, assign, n, assign_in != nullptr, s));
+    }
     RVCR_TRY(h->ws_P.reserve((size_t)n * RVCR_K * 4));
     float* D = D_dev;
     if (!D) {
         RVCR_TRY(h->ws_D.reserve((size_t)n * RVCR_K * 4));
         D = h->ws_D.as<float>();
     }
-    RVCR_TRY(scan_topk(h, feats_or_q, n, D, h->ws_P.as<int32_t>(), I_dev, s));
-    if (blend) RVCR_TRY(gather_blend(h, feats_or_q, n, D, h->ws_P.as<int32_t>(), assign_in, index_rate, s));
+    {
+        PhaseTimer pt(h, RVCR_PHASE_SCAN, s);
+        RVCR_TRY(scan_topk(h, feats_or_q, n, D, h->ws_P.as<int32_t>(), I_dev, s));
+    }
+    if (blend) {
+        PhaseTimer pt(h, RVCR_PHASE_BLEND, s);
+        RVCR_TRY(gather_blend(h, feats_or_q, n, D, h->ws_P.as<int32_t>(), assign_in, index_rate, s));
+    }
     h->stats.calls_search += 1;
     h->stats.queries += n;
     return stream_leave(h, s);
@@ -265,6 +276,9 @@ void rvcr_index_free(rvcr_index* h) {
                           &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_stage};
         for (DevBuf* b : bufs) b->release();
         if (h->last_done) cudaEventDestroy(h->last_done);
+        for (int i = 0; i < RVCR_NUM_PHASES; ++i)
+            for (int k = 0; k < 2; ++k)
+                if (h->pev[i][k]) cudaEventDestroy(h->pev[i][k]);
     }
     delete h;
 }
@@ -530,6 +544,8 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
     if (!strcmp(key, "coarse_mode")) {
         if (value < 0 || value > 3) return RVCR_ERR_INVALID;
         h->opt.coarse_mode = value;
+    } else if (!strcmp(key, "profile")) {
+        h->opt.profile = value ? 1 : 0;
     } else if (!strcmp(key, "nan_on_zero_score")) {
         if (value != 1) {
             set_error("only the reference behaviour (NaN row on a zero score) is implemented");
@@ -548,10 +564,24 @@ int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out) {
     std::lock_guard<std::mutex> lock(h->mu);
     if (!strcmp(key, "coarse_mode")) *value_out = h->opt.coarse_mode;
     else if (!strcmp(key, "nan_on_zero_score")) *value_out = h->opt.nan_on_zero_score;
+    else if (!strcmp(key, "profile")) *value_out = h->opt.profile;
     else if (!strcmp(key, "coarse_tc_available")) *value_out = coarse_tc_available() ? 1 : 0;
     else {
         set_error("unknown option '%s'", key);
         return RVCR_ERR_INVALID;
+    }
+    return RVCR_OK;
+}
+
+int rvcr_get_phase_ms(rvcr_index* h, float* ms_out) {
+    RVCR_ENTER(h);
+    if (!ms_out) return RVCR_ERR_INVALID;
+    for (int i = 0; i < RVCR_NUM_PHASES; ++i) {
+        ms_out[i] = -1.f;
+        if (h->pev_used[i]) {
+            RVCR_CUDA(cudaEventSynchronize(h->pev[i][1]));
+            RVCR_CUDA(cudaEventElapsedTime(&ms_out[i], h->pev[i][0], h->pev[i][1]));
+        }
     }
     return RVCR_OK;
 }

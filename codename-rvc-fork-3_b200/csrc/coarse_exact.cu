@@ -164,14 +164,14 @@ int coarse_exact(rvcr_index* h, const float* q, int64_t n, const int32_t* qsel, 
     const int64_t nwork = qsel ? nsel : n;
     if (nwork <= 0) return RVCR_OK;
     const size_t smem = ce_smem_bytes(h->d);
-    if (smem > 227 * 1024) {
+    if (smem > 226 * 1024) {
         set_error("d=%d needs %zu B of shared memory", h->d, smem);
         return RVCR_ERR_UNSUPPORTED;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        RVCR_CUDA(cudaFuncSetAttribute(coarse_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
+    static size_t attr_smem = 0;  // largest dynamic shared memory size opted into so far
+    if (smem > attr_smem) {
+        RVCR_CUDA(cudaFuncSetAttribute(coarse_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
     }
     RVCR_TRY(h->ws_best.reserve((size_t)n * 8));
     unsigned long long* best = h->ws_best.as<unsigned long long>();

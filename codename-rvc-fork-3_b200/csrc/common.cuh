@@ -60,6 +60,7 @@ struct DevBuf {
 struct Options {
     int64_t coarse_mode = 0;  // 0 auto, 1 exact FFMA, 2 tcgen05 bf16, 3 tcgen05 3-way split
     int64_t nan_on_zero_score = 1;
+    int64_t profile = 0;      // record CUDA events around each phase's kernels
 };
 
 }  // namespace rvcr
@@ -109,6 +110,10 @@ struct rvcr_index {
     cudaStream_t last_stream = nullptr;
     bool have_last = false;
 
+    // optional per-phase CUDA-event timing (option "profile"), read back by rvcr_get_phase_ms
+    cudaEvent_t pev[RVCR_NUM_PHASES][2] = {};
+    bool pev_used[RVCR_NUM_PHASES] = {};
+
     rvcr::Options opt;
     rvcr_stats stats{};
     std::mutex mu;
@@ -147,6 +152,24 @@ int refresh_derived(rvcr_index* h, cudaStream_t s);
 inline void count_launch(rvcr_index* h, int n = 1) {
     if (h) h->stats.kernels_launched += n;
 }
+
+// Phase timing: events on the launching stream, bracketing exactly the kernels of one phase.
+struct PhaseTimer {
+    rvcr_index* h;
+    int id;
+    cudaStream_t s;
+    PhaseTimer(rvcr_index* h_, int id_, cudaStream_t s_) : h(h_), id(id_), s(s_) {
+        if (!h->opt.profile) return;
+        for (int k = 0; k < 2; ++k)
+            if (!h->pev[id][k]) cudaEventCreate(&h->pev[id][k]);
+        cudaEventRecord(h->pev[id][0], s);
+    }
+    ~PhaseTimer() {
+        if (!h->opt.profile) return;
+        cudaEventRecord(h->pev[id][1], s);
+        h->pev_used[id] = true;
+    }
+};
 
 }  // namespace rvcr
 

@@ -280,12 +280,12 @@ int scan_topk(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, in
         return RVCR_ERR_UNSUPPORTED;
     }
     const size_t smem = scan_smem_bytes(h->d);
-    static bool attr_done = false;
-    if (!attr_done) {
-        RVCR_CUDA(cudaFuncSetAttribute(scan_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
+    static size_t attr_smem = 0;  // largest dynamic shared memory size opted into so far
+    if (smem > attr_smem) {
+        RVCR_CUDA(cudaFuncSetAttribute(scan_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
     }
-    if (smem > 227 * 1024) {
+    if (smem > 226 * 1024) {
         set_error("d=%d needs %zu B of shared memory", h->d, smem);
         return RVCR_ERR_UNSUPPORTED;
     }

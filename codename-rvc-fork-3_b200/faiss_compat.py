@@ -236,6 +236,14 @@ class IndexIVFFlat:
         check(lib().rvcr_get_stats(self.handle, C.byref(s)))
         return {k: int(getattr(s, k)) for k, _ in Stats._fields_ if k != "reserved"}
 
+    PHASES = ("coarse_prep", "coarse_main", "coarse_recheck", "group", "scan", "blend")
+
+    def phase_ms(self) -> dict:
+        """Per-phase device time (ms) of the last search-type call; needs set_option("profile", 1)."""
+        arr = (C.c_float * 8)()
+        check(lib().rvcr_get_phase_ms(self.handle, arr))
+        return {name: float(arr[i]) for i, name in enumerate(self.PHASES) if arr[i] >= 0}
+
     # -- zero-copy construction ------------------------------------------------------------
     def alloc_lists(self, sizes, ntotal: int) -> None:
         sizes = np.ascontiguousarray(sizes, np.int64)

@@ -39,6 +39,15 @@ extern "C" {
 
 #define RVCR_VERSION 100
 
+/* phases timed when option "profile" is 1 (rvcr_get_phase_ms) */
+#define RVCR_PHASE_COARSE_PREP 0    /* fp32 -> bf16 operands, norms                         */
+#define RVCR_PHASE_COARSE_MAIN 1    /* the query x centroid contraction (tcgen05 or FFMA)   */
+#define RVCR_PHASE_COARSE_RECHECK 2 /* exact re-check of tensor-core candidates + fallback  */
+#define RVCR_PHASE_GROUP 3          /* sort queries by probed list, build work items        */
+#define RVCR_PHASE_SCAN 4           /* inverted-list scan + top-8                           */
+#define RVCR_PHASE_BLEND 5          /* gather + 1/score^2 weights + index_rate blend        */
+#define RVCR_NUM_PHASES 8
+
 #if defined(__GNUC__)
 #define RVCR_API __attribute__((visibility("default")))
 #else
@@ -164,10 +173,15 @@ RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, i
 
 /* keys: "coarse_mode" 0 = auto, 1 = exact FFMA kernel, 2 = tcgen05 bf16 + exact re-check,
  *                     3 = tcgen05 3-way split bf16 + exact re-check
- *       "nan_on_zero_score" 1 (default, reference behaviour: exact-match query -> NaN row) */
+ *       "nan_on_zero_score" 1 (default, reference behaviour: exact-match query -> NaN row)
+ *       "profile" 0/1 record per-phase CUDA events (see rvcr_get_phase_ms) */
 RVCR_API int rvcr_set_option(rvcr_index* h, const char* key, int64_t value);
 RVCR_API int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out);
 RVCR_API int rvcr_get_stats(rvcr_index* h, rvcr_stats* out);
+/* With option "profile" = 1 every search-type call records CUDA events (on the caller's stream)
+ * around each phase; this synchronises on them and returns the last call's per-phase device time
+ * in milliseconds (RVCR_NUM_PHASES floats, -1 for phases that did not run). */
+RVCR_API int rvcr_get_phase_ms(rvcr_index* h, float* ms_out);
 
 #ifdef __cplusplus
 }
