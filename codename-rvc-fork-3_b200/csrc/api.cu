@@ -233,6 +233,16 @@ int rvcr_index_create(int32_t d, int64_t nlist, int device, rvcr_index** out) {
     h->nlist_global = nlist;
     h->num_sms = prop.multiProcessorCount;
     h->offsets_host.assign((size_t)nlist + 1, 0);
+    {
+        // small fixed scratch block: work-item counters, ticket, re-check counters (layout: see users)
+        DeviceGuard g(device);
+        int rc = h->ws_misc.reserve(1024);
+        if (rc == RVCR_OK && cudaMemset(h->ws_misc.p, 0, 1024) != cudaSuccess) rc = RVCR_ERR_CUDA;
+        if (rc != RVCR_OK) {
+            delete h;
+            return rc;
+        }
+    }
     *out = h;
     return RVCR_OK;
 }
@@ -546,6 +556,9 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
         h->opt.coarse_mode = value;
     } else if (!strcmp(key, "profile")) {
         h->opt.profile = value ? 1 : 0;
+    } else if (!strcmp(key, "tc_cluster")) {
+        if (value != 1 && value != 2) return RVCR_ERR_INVALID;
+        h->opt.tc_cluster = value;
     } else if (!strcmp(key, "nan_on_zero_score")) {
         if (value != 1) {
             set_error("only the reference behaviour (NaN row on a zero score) is implemented");
@@ -565,6 +578,7 @@ int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out) {
     if (!strcmp(key, "coarse_mode")) *value_out = h->opt.coarse_mode;
     else if (!strcmp(key, "nan_on_zero_score")) *value_out = h->opt.nan_on_zero_score;
     else if (!strcmp(key, "profile")) *value_out = h->opt.profile;
+    else if (!strcmp(key, "tc_cluster")) *value_out = h->opt.tc_cluster;
     else if (!strcmp(key, "coarse_tc_available")) *value_out = coarse_tc_available() ? 1 : 0;
     else {
         set_error("unknown option '%s'", key);
@@ -587,9 +601,44 @@ int rvcr_get_phase_ms(rvcr_index* h, float* ms_out) {
 }
 
 int rvcr_get_stats(rvcr_index* h, rvcr_stats* out) {
-    if (!h || !out) return RVCR_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(h->mu);
+    RVCR_ENTER(h);
+    if (!out) return RVCR_ERR_INVALID;
+    if (h->tc_counters_dirty) {   // running totals kept on the device by the re-check kernel
+        unsigned long long tot[2] = {0, 0};
+        RVCR_CUDA(cudaDeviceSynchronize());
+        RVCR_CUDA(cudaMemcpy(tot, h->ws_misc.as<int32_t>() + 24, sizeof(tot), cudaMemcpyDeviceToHost));
+        h->stats.coarse_fallback = (int64_t)tot[0];
+        h->stats.coarse_candidates = (int64_t)tot[1];
+        h->tc_counters_dirty = false;
+    }
     *out = h->stats;
+    return RVCR_OK;
+}
+
+int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t split, int32_t cluster, int32_t cap_pairs,
+                         float* v_host, int32_t* j_host, int32_t* pairs_out, float* qnorm2_host, float* cmax_out, void* stream) {
+    RVCR_ENTER(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n <= 0 || !q_dev || !v_host || !j_host || !pairs_out || (cluster != 1 && cluster != 2)) return RVCR_ERR_INVALID;
+    if (!h->trained) {
+        set_error("index is not trained");
+        return RVCR_ERR_STATE;
+    }
+    float *topv, *qnorm;
+    int* topj;
+    int nsplit = 0;
+    RVCR_TRY(coarse_tc_top8(h, q_dev, n, split ? 1 : 0, cluster, &topv, &topj, &nsplit, &qnorm, s));
+    const int pairs = nsplit * 8;
+    *pairs_out = pairs;
+    if (pairs > cap_pairs) {
+        set_error("debug buffer too small: %d pairs per query needed", pairs);
+        return RVCR_ERR_INVALID;
+    }
+    RVCR_CUDA(cudaMemcpyAsync(v_host, topv, (size_t)n * pairs * 4, cudaMemcpyDeviceToHost, s));
+    RVCR_CUDA(cudaMemcpyAsync(j_host, topj, (size_t)n * pairs * 4, cudaMemcpyDeviceToHost, s));
+    if (qnorm2_host) RVCR_CUDA(cudaMemcpyAsync(qnorm2_host, qnorm, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    RVCR_CUDA(cudaStreamSynchronize(s));
+    if (cmax_out) *cmax_out = h->cent_norm_max;
     return RVCR_OK;
 }
 

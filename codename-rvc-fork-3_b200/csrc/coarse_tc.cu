@@ -1,10 +1,769 @@
-// coarse_tc.cu -- placeholder until the tcgen05 kernel lands (next commit).
+// coarse_tc.cu -- coarse-quantizer assignment on the 5th-gen tensor cores (tcgen05 + TMEM + TMA),
+// made FP32-exact by an exact re-check.
+//
+// Replaces the same reference step as coarse_exact.cu: quantizer->search(n, x, k=1) inside
+// index.search (rvc/infer/pipeline.py:499) and index.add (rvc/train/process/extract_index.py:69);
+// faiss does this with an OpenBLAS sgemm.  At the BASELINE configs this contraction
+// (2*nq*nlist*d flops) is ~256x the scan's flops, so it decides the end-to-end frames/s.
+//
+// Scheme ("validated split precision"):
+//   1. prep        q, c  ->  bf16 operands (optionally a 3-way split [h|l|h] x [h|h|l] along K) and
+//                  fp32 norms  (coarse_prep kernels)
+//   2. tc kernel   v(q,j) = ||c_j||^2 - 2 * <q_bf16, c_bf16>  on tcgen05.mma (fp32 accumulation in
+//                  TMEM); the epilogue keeps, per query, the 8 smallest v and their centroid ids
+//   3. recheck     candidates whose v is within a rigorous error margin of the smallest v get
+//                  their canonical fp32 distance (same fvec_L2sqr order as everywhere else);
+//                  argmin by (distance, id).  If all 8 kept values lie inside the margin the
+//                  candidate list may be truncated: the query is re-done by coarse_exact.cu.
+//   The result is therefore identical to coarse_exact.cu bit for bit (tests assert this); the
+//   margin derivation is in DESIGN.md "Numerics".
+//
+// tc kernel: persistent, warp-specialised, one CTA (or a CTA pair, cta_group::2) per SM (pair):
+//   warp 0   TMA producer: A = 128 queries x 64 k, B = 256 (128 per CTA of a pair) centroids x 64 k,
+//            128B-swizzled K-major tiles, 4-6 stage mbarrier ring
+//   warp 1   MMA issuer (one elected thread; leader CTA only): 4 x tcgen05.mma (K = 16) per stage
+//            into a 128 x 256 fp32 accumulator, double-buffered in TMEM (2 x 256 columns)
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld 32 columns at a time, v = fma(-2, acc, ||c||^2), running top-8
+//            per row in registers; overlaps the next tile's MMAs
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
 #include "common.cuh"
+
 namespace rvcr {
-bool coarse_tc_available() { return false; }
-int coarse_tc_invalidate(rvcr_index*) { return RVCR_OK; }
-int coarse_tc(rvcr_index*, const float*, int64_t, int32_t*, float*, cudaStream_t) {
-    set_error("tcgen05 coarse path not built");
-    return RVCR_ERR_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;   // queries per CTA
+constexpr int BLOCK_N = 256;   // centroids per accumulator tile
+constexpr int BLOCK_K = 64;    // bf16 elements per stage row = 128 B = one swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int TOPT = 8;        // approximate nearest centroids kept per (query, split)
+constexpr int THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// ---- mbarrier ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a mis-programmed pipeline traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
+        if (it > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(
+            smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+
+// ---- TMA -----------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+template <int CLUSTER>
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int crd0, int crd1) {
+    if constexpr (CLUSTER == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                smem_u32(dst)),
+            "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1)
+            : "memory");
+    } else {
+        // both CTAs of the pair issue this; clearing the peer bit routes complete_tx to the
+        // leader CTA's barrier
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                smem_u32(dst)),
+            "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(crd0), "r"(crd1)
+            : "memory");
+    }
+}
+
+// ---- tcgen05 -------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CLUSTER>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    if constexpr (CLUSTER == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int CLUSTER>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    if constexpr (CLUSTER == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+template <int CLUSTER>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CLUSTER == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(
+                tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(
+                tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// all previously issued MMAs of this thread arrive on `bar` when they complete
+template <int CLUSTER>
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    if constexpr (CLUSTER == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    } else {
+        const uint16_t mask = 3;  // both CTAs of the pair
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                smem_u32(bar)),
+            "h"(mask)
+            : "memory");
+    }
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);       // start address, 16-byte units
+    d |= (uint64_t)0 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4)                    // D format: fp32
+           | (1u << 7)                  // A format: bf16
+           | (1u << 10)                 // B format: bf16
+           | ((uint32_t)(N >> 3) << 17) // N / 8
+           | ((uint32_t)(M >> 4) << 24);// M / 16    (A, B K-major; no negate; dense)
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// sorted (ascending) top-T insertion, fully unrolled, registers only
+__device__ __forceinline__ void top_insert(float (&tv)[TOPT], int (&tj)[TOPT], float x, int j) {
+    if (!(x < tv[TOPT - 1])) return;
+    tv[TOPT - 1] = x;
+    tj[TOPT - 1] = j;
+#pragma unroll
+    for (int i = TOPT - 1; i > 0; --i) {
+        if (tv[i] < tv[i - 1]) {
+            float fv = tv[i]; tv[i] = tv[i - 1]; tv[i - 1] = fv;
+            int fj = tj[i]; tj[i] = tj[i - 1]; tj[i - 1] = fj;
+        }
+    }
+}
+
+template <int CLUSTER>
+struct Cfg {
+    static constexpr int LOAD_N = BLOCK_N / CLUSTER;                      // B rows loaded per CTA
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;                 // 16 KB
+    static constexpr int B_BYTES = LOAD_N * BLOCK_K * 2;                  // 32 KB / 16 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = CLUSTER == 1 ? 4 : 6;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
+    static constexpr int UMMA_M = BLOCK_M * CLUSTER;
+};
+
+// grid = persistent CTAs (multiple of CLUSTER); work item = (m-block of 128*CLUSTER queries, split
+// of the centroid tiles); item i is taken by cluster (i mod nclusters).
+template <int CLUSTER>
+__global__ void __launch_bounds__(THREADS, 1)
+coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const float* __restrict__ cn, int num_mblocks, int num_ntiles, int nsplit, int tiles_per_split,
+                 int num_kblocks, float* __restrict__ topv, int* __restrict__ topj) {
+    using C = Cfg<CLUSTER>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full_bar = bars;                      // [STAGES]  TMA -> MMA       (leader CTA's are used)
+    uint64_t* empty_bar = bars + C::STAGES;         // [STAGES]  MMA -> TMA       (each CTA its own)
+    uint64_t* tmem_full_bar = bars + 2 * C::STAGES; // [2]       MMA -> epilogue  (each CTA its own)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]       epilogue -> MMA  (leader CTA's are used)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CLUSTER == 1 ? 0u : cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x / CLUSTER;
+    const int nclusters = gridDim.x / CLUSTER;
+    const int nitems = num_mblocks * nsplit;
+
+    if constexpr (CLUSTER > 1) cluster_sync_all();
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::STAGES; ++i) {
+            mbar_init(&full_bar[i], CLUSTER);   // one arrive per CTA's producer (+ tx bytes)
+            mbar_init(&empty_bar[i], 1);        // one tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);                // one tcgen05.commit
+            mbar_init(&tmem_empty_bar[i], CLUSTER * 128);   // every epilogue thread of the pair
+        }
+        fence_mbar_init();
+    } else if (warp == 2) {
+        tmem_alloc<CLUSTER>(tmem_ptr_smem, 512);
+    }
+    tc_fence_before();
+    if constexpr (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ================================ TMA producer =================================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (int item = cluster_id; item < nitems; item += nclusters) {
+                const int mb = item / nsplit, sp = item - mb * nsplit;
+                const int m0 = mb * (BLOCK_M * CLUSTER) + (int)cta_rank * BLOCK_M;
+                const int t0 = sp * tiles_per_split;
+                const int t1 = min(t0 + tiles_per_split, num_ntiles);
+                for (int t = t0; t < t1; ++t) {
+                    const int n0 = t * BLOCK_N + (int)cta_rank * C::LOAD_N;
+                    for (int kb = 0; kb < num_kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        tma_load_2d<CLUSTER>(&tmap_a, &full_bar[stage], sA + stage * C::A_BYTES, kb * BLOCK_K, m0);
+                        tma_load_2d<CLUSTER>(&tmap_b, &full_bar[stage], sB + stage * C::B_BYTES, kb * BLOCK_K, n0);
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * CLUSTER);
+                        else mbar_arrive_cluster(&full_bar[stage], 0);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ===================================
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = make_idesc(C::UMMA_M, BLOCK_N);
+            uint32_t stage = 0, phase = 0, tile_cnt = 0;
+            for (int item = cluster_id; item < nitems; item += nclusters) {
+                const int sp = item % nsplit;
+                const int t0 = sp * tiles_per_split;
+                const int t1 = min(t0 + tiles_per_split, num_ntiles);
+                for (int t = t0; t < t1; ++t, ++tile_cnt) {
+                    const uint32_t as = tile_cnt & 1, aphase = (tile_cnt >> 1) & 1;
+                    mbar_wait(&tmem_empty_bar[as], aphase ^ 1);   // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                    for (int kb = 0; kb < num_kblocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint64_t da = make_smem_desc(smem_u32(sA + stage * C::A_BYTES));
+                        const uint64_t db = make_smem_desc(smem_u32(sB + stage * C::B_BYTES));
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte units
+                            umma_bf16<CLUSTER>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                               (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit<CLUSTER>(&empty_bar[stage]);   // frees the smem stage when the MMAs retire
+                        if (kb == num_kblocks - 1) umma_commit<CLUSTER>(&tmem_full_bar[as]);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ================================ epilogue =====================================
+        const int ew = warp - EPI_WARP0;               // == warp % 4: TMEM lane quarter of this warp
+        const int row = ew * 32 + lane;                // accumulator row == TMEM lane
+        uint32_t tile_cnt = 0;
+        for (int item = cluster_id; item < nitems; item += nclusters) {
+            const int mb = item / nsplit, sp = item - mb * nsplit;
+            const int t0 = sp * tiles_per_split;
+            const int t1 = min(t0 + tiles_per_split, num_ntiles);
+            float tv[TOPT];
+            int tj[TOPT];
+#pragma unroll
+            for (int i = 0; i < TOPT; ++i) { tv[i] = __int_as_float(0x7f800000); tj[i] = -1; }
+            for (int t = t0; t < t1; ++t, ++tile_cnt) {
+                const uint32_t as = tile_cnt & 1, aphase = (tile_cnt >> 1) & 1;
+                mbar_wait(&tmem_full_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N;
+                const int n0 = t * BLOCK_N;
+                const float4* cn4 = reinterpret_cast<const float4*>(cn + n0);
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    float4 nn[8];
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) nn[g] = __ldg(cn4 + c * 8 + g);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float x0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), nn[g].x);
+                        const float x1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), nn[g].y);
+                        const float x2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), nn[g].z);
+                        const float x3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), nn[g].w);
+                        const float m = fminf(fminf(x0, x1), fminf(x2, x3));
+                        if (m < tv[TOPT - 1]) {
+                            const int jb = n0 + c * 32 + 4 * g;
+                            top_insert(tv, tj, x0, jb + 0);
+                            top_insert(tv, tj, x1, jb + 1);
+                            top_insert(tv, tj, x2, jb + 2);
+                            top_insert(tv, tj, x3, jb + 3);
+                        }
+                    }
+                }
+                // accumulator fully read: hand it back to the MMA issuer (leader CTA's barrier)
+                tc_fence_before();
+                if (CLUSTER == 1 || leader) mbar_arrive_local(&tmem_empty_bar[as]);
+                else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+            }
+            // write this (query, split)'s approximate top-8
+            const int64_t q = (int64_t)mb * (BLOCK_M * CLUSTER) + (int64_t)cta_rank * BLOCK_M + row;
+            float4* ov = reinterpret_cast<float4*>(topv + (q * nsplit + sp) * TOPT);
+            int4* oj = reinterpret_cast<int4*>(topj + (q * nsplit + sp) * TOPT);
+            ov[0] = make_float4(tv[0], tv[1], tv[2], tv[3]);
+            ov[1] = make_float4(tv[4], tv[5], tv[6], tv[7]);
+            oj[0] = make_int4(tj[0], tj[1], tj[2], tj[3]);
+            oj[1] = make_int4(tj[4], tj[5], tj[6], tj[7]);
+        }
+    }
+
+    tc_fence_before();
+    if constexpr (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) tmem_dealloc<CLUSTER>(tmem_base, 512);
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------- operand preparation ----
+
+// one warp per row: fp32 row -> bf16 operand row(s) of width kdim (= d, or 3d for the split form
+// [h | l | h] for queries / [h | h | l] for centroids) and the row's squared norm
+__global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d, int split, int is_centroid,
+                                    __nv_bfloat16* __restrict__ out, float* __restrict__ norm2, float pad_norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_pad) return;
+    const int kdim = split ? 3 * d : d;
+    __nv_bfloat16* o = out + r * kdim;
+    if (r >= n) {
+        for (int c = lane; c < kdim; c += 32) o[c] = __float2bfloat16(0.f);
+        if (lane == 0 && norm2) norm2[r] = pad_norm;
+        return;
+    }
+    const float* xr = x + r * d;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        const float v = xr[c];
+        s = fmaf(v, v, s);
+        const __nv_bfloat16 h = __float2bfloat16(v);
+        o[c] = h;
+        if (split) {
+            const __nv_bfloat16 l = __float2bfloat16(v - __bfloat162float(h));
+            if (is_centroid) {
+                o[d + c] = h;
+                o[2 * d + c] = l;
+            } else {
+                o[d + c] = l;
+                o[2 * d + c] = h;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0 && norm2) norm2[r] = s;
+}
+
+__global__ void tc_max_kernel(const float* __restrict__ v, int64_t n, unsigned int* __restrict__ out_bits) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    float m = 0.f;
+    if (i < n) m = v[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order as uints
+}
+
+// ------------------------------------------------------------------------- exact re-check ----
+
+// One warp per query.  Gathers the nsplit x 8 approximate (v, j) pairs, keeps those with
+// v <= vmin + margin(q), evaluates their canonical fp32 distance (8 lanes per candidate, 4 candidates
+// per pass) and takes the argmin by (distance, id).  Flags the query for the exact kernel when a
+// split's 8th value is inside the margin (its candidate list may be truncated) or no candidate is
+// valid.
+__global__ void tc_recheck_kernel(const float* __restrict__ q, int64_t n, int d, const float* __restrict__ cent, int64_t nlist,
+                                  const float* __restrict__ qnorm2, float cmax, float rel_margin, float abs_margin,
+                                  const float* __restrict__ topv, const int* __restrict__ topj, int nsplit, int64_t list_begin,
+                                  int32_t* __restrict__ list_out, float* __restrict__ dist_out, int32_t* __restrict__ fb_list,
+                                  int32_t* __restrict__ counters /*[0] fallbacks of this call; [8..9], [10..11] u64 running totals*/) {
+    const int lane = threadIdx.x & 31;
+    const int64_t qi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (qi >= n) return;
+    const float qn2 = qnorm2[qi];
+    const float qn = sqrtf(qn2);
+    // |v_approx - v_true| <= margin/2 for every centroid  (DESIGN.md "Numerics")
+    const float margin = rel_margin * qn * cmax + abs_margin * (qn2 + cmax * cmax);
+    const int total = nsplit * tc::TOPT;
+    const float* tv = topv + qi * total;
+    const int* tj = topj + qi * total;
+    float vmin = __int_as_float(0x7f800000);
+    for (int e = lane; e < total; e += 32) {
+        const int j = tj[e];
+        if (j >= 0 && j < nlist) vmin = fminf(vmin, tv[e]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, off));
+    const float thr = vmin + margin;
+    bool overflow = !(vmin < __int_as_float(0x7f800000));   // no valid candidate at all (e.g. NaN query)
+    // truncation check: the 8th (largest kept) value of any split inside the margin
+    for (int s = lane; s < nsplit; s += 32) {
+        const int j7 = tj[s * tc::TOPT + tc::TOPT - 1];
+        if (j7 >= 0 && tv[s * tc::TOPT + tc::TOPT - 1] <= thr) overflow = true;
+    }
+    overflow = __any_sync(0xffffffffu, overflow);
+    if (overflow) {
+        if (lane == 0) {
+            const int slot = atomicAdd(&counters[0], 1);
+            fb_list[slot] = (int32_t)qi;
+            list_out[qi] = -1;
+            if (dist_out) dist_out[qi] = RVCR_FLT_MAX;
+            atomicAdd(reinterpret_cast<unsigned long long*>(&counters[8]), 1ull);
+        }
+        return;
+    }
+    const int l8 = lane & 7, grp = lane >> 3;
+    const float* qrow = q + qi * d;
+    float bd = RVCR_FLT_MAX;
+    int bj = -1;
+    int ncand = 0;
+    for (int e0 = 0; e0 < total; e0 += 4) {
+        const int e = e0 + grp;
+        int j = -1;
+        float v = 0.f;
+        if (e < total) {
+            j = tj[e];
+            v = tv[e];
+        }
+        const bool take = j >= 0 && j < nlist && v <= thr;
+        if (!__any_sync(0xffffffffu, take)) continue;
+        float acc = 0.f;
+        if (take) {
+            const float* crow = cent + (int64_t)j * d;
+            for (int i = 0; i < d; i += 8) {
+                const float t = __fsub_rn(qrow[i + l8], crow[i + l8]);
+                acc = __fmaf_rn(t, t, acc);
+            }
+        }
+        acc = reduce8_canonical(acc);
+        if (take) {
+            ++ncand;
+            if (acc < bd || (acc == bd && j < bj)) {
+                bd = acc;
+                bj = j;
+            }
+        }
+    }
+    // merge the 4 groups (lanes 0, 8, 16, 24 hold distinct candidates) by (distance, id)
+#pragma unroll
+    for (int off = 8; off < 32; off <<= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, bd, off);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+        const int oc = __shfl_xor_sync(0xffffffffu, ncand, off);
+        ncand += oc;
+        if (oj >= 0 && (bj < 0 || od < bd || (od == bd && oj < bj))) {
+            bd = od;
+            bj = oj;
+        }
+    }
+    if (lane == 0) {
+        if (bj < 0) {   // every candidate distance was NaN: let the exact kernel decide (-> -1)
+            const int slot = atomicAdd(&counters[0], 1);
+            fb_list[slot] = (int32_t)qi;
+            list_out[qi] = -1;
+            if (dist_out) dist_out[qi] = RVCR_FLT_MAX;
+            atomicAdd(reinterpret_cast<unsigned long long*>(&counters[8]), 1ull);
+        } else {
+            list_out[qi] = (int32_t)(bj + list_begin);
+            if (dist_out) dist_out[qi] = bd;
+            atomicAdd(reinterpret_cast<unsigned long long*>(&counters[10]), (unsigned long long)ncand);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ host side ----
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// row-major bf16 matrix [rows][kdim] -> tensor map with a [box_rows][64] box, 128B swizzle
+int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int kdim, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return RVCR_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kdim * 2};
+    cuuint32_t box[2] = {(cuuint32_t)tc::BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for a %lld x %d bf16 matrix", (int)r, (long long)rows, kdim);
+        return RVCR_ERR_CUDA;
+    }
+    return RVCR_OK;
+}
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// centroid operands are built once per (centroid set, split mode)
+int ensure_centroid_operands(rvcr_index* h, int split, cudaStream_t s) {
+    if (h->cent_bf16 && h->cent_split == split) return RVCR_OK;
+    if (h->cent_bf16) cudaFree(h->cent_bf16);
+    if (h->cent_norm) cudaFree(h->cent_norm);
+    h->cent_bf16 = nullptr;
+    h->cent_norm = nullptr;
+    const int kdim = split ? 3 * h->d : h->d;
+    const int64_t npad = round_up(h->nlist, tc::BLOCK_N);
+    RVCR_CUDA(cudaMalloc(&h->cent_bf16, (size_t)npad * kdim * 2));
+    RVCR_CUDA(cudaMalloc(&h->cent_norm, (size_t)npad * 4));
+    const int64_t thr = npad * 32;
+    // pad centroids get ||c||^2 = +inf: v = +inf, never kept
+    tc_prep_rows_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(h->cent, h->nlist, npad, h->d, split, 1,
+                                                                       reinterpret_cast<__nv_bfloat16*>(h->cent_bf16),
+                                                                       h->cent_norm, INFINITY);
+    RVCR_CHECK_LAUNCH();
+    unsigned int* mx = h->ws_misc.as<unsigned int>() + 12;
+    RVCR_CUDA(cudaMemsetAsync(mx, 0, 4, s));
+    tc_max_kernel<<<(unsigned)((h->nlist + 255) / 256), 256, 0, s>>>(h->cent_norm, h->nlist, mx);
+    RVCR_CHECK_LAUNCH();
+    unsigned int bits = 0;
+    RVCR_CUDA(cudaMemcpyAsync(&bits, mx, 4, cudaMemcpyDeviceToHost, s));
+    RVCR_CUDA(cudaStreamSynchronize(s));
+    float m2;
+    memcpy(&m2, &bits, 4);
+    h->cent_norm_max = sqrtf(m2);
+    h->cent_pad = npad;
+    h->cent_kdim = kdim;
+    h->cent_split = split;
+    count_launch(h, 2);
+    return RVCR_OK;
+}
+
+template <int CLUSTER>
+int launch_tc(rvcr_index* h, const CUtensorMap& ta, const CUtensorMap& tb, int num_mblocks, int num_ntiles, int nsplit,
+              int tps, int nkb, float* topv, int* topj, cudaStream_t s) {
+    using C = tc::Cfg<CLUSTER>;
+    static bool attr = false;
+    if (!attr) {
+        RVCR_CUDA(cudaFuncSetAttribute(tc::coarse_tc_kernel<CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr = true;
+    }
+    const int nitems = num_mblocks * nsplit;
+    int nclusters = h->num_sms / CLUSTER;
+    if (nclusters > nitems) nclusters = nitems;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(nclusters * CLUSTER));
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CLUSTER;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    RVCR_CUDA(cudaLaunchKernelEx(&cfg, tc::coarse_tc_kernel<CLUSTER>, ta, tb, (const float*)h->cent_norm, num_mblocks,
+                                 num_ntiles, nsplit, tps, nkb, topv, topj));
+    return RVCR_OK;
+}
+
+}  // namespace
+
+bool coarse_tc_available() { return true; }
+
+int coarse_tc_invalidate(rvcr_index* h) {
+    if (h->cent_bf16) cudaFree(h->cent_bf16);
+    if (h->cent_norm) cudaFree(h->cent_norm);
+    h->cent_bf16 = nullptr;
+    h->cent_norm = nullptr;
+    h->cent_split = -1;
+    return RVCR_OK;
+}
+
+// Approximate top-8 nearest centroids per (query, split) on the tensor cores.
+// Outputs (device, owned by the handle scratch): topv/topj [n_pad][nsplit][8]; returns nsplit.
+int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int cluster, float** topv_out, int** topj_out,
+                   int* nsplit_out, float** qnorm_out, cudaStream_t s) {
+    if (h->d % tc::BLOCK_K != 0) {
+        set_error("d=%d unsupported by the tcgen05 path (must be a multiple of %d)", h->d, tc::BLOCK_K);
+        return RVCR_ERR_UNSUPPORTED;
+    }
+    const int kdim = split ? 3 * h->d : h->d;
+    const int mblk = tc::BLOCK_M * cluster;
+    const int64_t n_pad = round_up(n, mblk);
+    {
+        PhaseTimer pt(h, RVCR_PHASE_COARSE_PREP, s);
+        RVCR_TRY(ensure_centroid_operands(h, split, s));
+        RVCR_TRY(h->ws_tc0.reserve((size_t)n_pad * kdim * 2));   // bf16 queries
+        RVCR_TRY(h->ws_tc1.reserve((size_t)n_pad * 4));          // ||q||^2
+        const int64_t thr = n_pad * 32;
+        tc_prep_rows_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, n_pad, h->d, split, 0,
+                                                                           h->ws_tc0.as<__nv_bfloat16>(), h->ws_tc1.as<float>(), 0.f);
+        RVCR_CHECK_LAUNCH();
+        count_launch(h);
+    }
+    const int num_mblocks = (int)(n_pad / mblk);
+    const int num_ntiles = (int)(h->cent_pad / tc::BLOCK_N);
+    const int nclusters = h->num_sms / cluster;
+    int nsplit = 1;
+    if (num_mblocks < 4 * nclusters) {
+        nsplit = (3 * nclusters + num_mblocks - 1) / num_mblocks;
+        if (nsplit > num_ntiles) nsplit = num_ntiles;
+        if (nsplit < 1) nsplit = 1;
+    }
+    int tps = (num_ntiles + nsplit - 1) / nsplit;
+    nsplit = (num_ntiles + tps - 1) / tps;
+    RVCR_TRY(h->ws_tc2.reserve((size_t)n_pad * nsplit * tc::TOPT * 4));
+    RVCR_TRY(h->ws_tc3.reserve((size_t)n_pad * nsplit * tc::TOPT * 4));
+    CUtensorMap ta, tb;
+    RVCR_TRY(make_tmap(&ta, h->ws_tc0.p, n_pad, kdim, tc::BLOCK_M));
+    RVCR_TRY(make_tmap(&tb, h->cent_bf16, h->cent_pad, kdim, tc::BLOCK_N / cluster));
+    {
+        PhaseTimer pt(h, RVCR_PHASE_COARSE_MAIN, s);
+        if (cluster == 2)
+            RVCR_TRY(launch_tc<2>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, kdim / tc::BLOCK_K, h->ws_tc2.as<float>(),
+                                  h->ws_tc3.as<int>(), s));
+        else
+            RVCR_TRY(launch_tc<1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, kdim / tc::BLOCK_K, h->ws_tc2.as<float>(),
+                                  h->ws_tc3.as<int>(), s));
+        count_launch(h);
+    }
+    *topv_out = h->ws_tc2.as<float>();
+    *topj_out = h->ws_tc3.as<int>();
+    *nsplit_out = nsplit;
+    *qnorm_out = h->ws_tc1.as<float>();
+    return RVCR_OK;
+}
+
+int coarse_exact_selected(rvcr_index* h, const float* q, int64_t n, const int32_t* qsel, const int32_t* nsel_dev,
+                          int32_t* list_out, float* dist_out, cudaStream_t s);
+
+int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out, cudaStream_t s) {
+    const int split = h->opt.coarse_mode == 3 ? 1 : 0;
+    const int cluster = h->opt.tc_cluster == 1 ? 1 : 2;
+    float *topv, *qnorm;
+    int* topj;
+    int nsplit;
+    RVCR_TRY(coarse_tc_top8(h, q, n, split, cluster, &topv, &topj, &nsplit, &qnorm, s));
+    PhaseTimer pt(h, RVCR_PHASE_COARSE_RECHECK, s);
+    // error margin between two approximate values (see DESIGN.md "Numerics"):
+    //   bf16 rounding of both operands:  2 * 2 * 2^-8 |q||c|          (1-way)   /  2 * 2 * 3 * 2^-18 |q||c| (3-way split)
+    //   fp32 accumulation over kdim products and the final fma: kdim * 2^-21 |q||c| + 2^-20 (|q|^2 + |c|^2)
+    const int kdim = split ? 3 * h->d : h->d;
+    const float rel = (split ? 12.f * 1.01f / 262144.f : 1.01f / 64.f) + (float)kdim / 2097152.f;
+    const float absm = 1.f / 1048576.f;
+    RVCR_TRY(h->ws_stage.reserve((size_t)n * 4 + 64));
+    int32_t* fb_list = h->ws_stage.as<int32_t>();
+    int32_t* counters = h->ws_misc.as<int32_t>() + 16;   // [16] fallbacks of this call; [24..27] running totals
+    RVCR_CUDA(cudaMemsetAsync(counters, 0, 4, s));
+    const int64_t thr = n * 32;
+    tc_recheck_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, h->d, h->cent, h->nlist, qnorm, h->cent_norm_max, rel,
+                                                                     absm, topv, topj, nsplit, h->list_begin, list_out, dist_out,
+                                                                     fb_list, counters);
+    RVCR_CHECK_LAUNCH();
+    count_launch(h);
+    RVCR_TRY(coarse_exact_selected(h, q, n, fb_list, counters, list_out, dist_out, s));
+    h->stats.coarse_tc_queries += n;
+    h->tc_counters_dirty = true;
+    return RVCR_OK;
+}
+
 }  // namespace rvcr

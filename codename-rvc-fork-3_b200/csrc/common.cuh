@@ -61,6 +61,7 @@ struct Options {
     int64_t coarse_mode = 0;  // 0 auto, 1 exact FFMA, 2 tcgen05 bf16, 3 tcgen05 3-way split
     int64_t nan_on_zero_score = 1;
     int64_t profile = 0;      // record CUDA events around each phase's kernels
+    int64_t tc_cluster = 2;   // tcgen05 path: 1 = one CTA per SM, 2 = CTA pairs (cta_group::2)
 };
 
 }  // namespace rvcr
@@ -114,6 +115,7 @@ struct rvcr_index {
     cudaEvent_t pev[RVCR_NUM_PHASES][2] = {};
     bool pev_used[RVCR_NUM_PHASES] = {};
 
+    bool tc_counters_dirty = false;
     rvcr::Options opt;
     rvcr_stats stats{};
     std::mutex mu;
@@ -131,6 +133,8 @@ int coarse_exact(rvcr_index* h, const float* q, int64_t n, const int32_t* qsel /
 int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out,
               cudaStream_t s);
 bool coarse_tc_available();
+int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int cluster, float** topv_out, int** topj_out,
+                   int* nsplit_out, float** qnorm_out, cudaStream_t s);
 int coarse_tc_invalidate(rvcr_index* h);
 // scan_topk.cu
 int group_queries(rvcr_index* h, const int32_t* assign, int64_t n, bool only_local, cudaStream_t s);

@@ -20,6 +20,8 @@ ap.add_argument("--nq", type=int, default=180_000)
 ap.add_argument("--nlist", type=int, default=22_627)
 ap.add_argument("--mode", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--cluster", type=int, default=2)
+ap.add_argument("--addmode", type=int, default=2)
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -31,7 +33,8 @@ x = centres[which] + torch.randn((a.n, a.d), generator=g, device=dev) * 0.14
 cent = x[torch.randperm(a.n, generator=g, device=dev)[: a.nlist]].contiguous()
 index = rvcr.index_factory(a.d, f"IVF{a.nlist},Flat")
 index.set_centroids(cent.cpu().numpy())
-index.set_option("coarse_mode", a.mode)
+index.set_option("coarse_mode", a.addmode)
+index.set_option("tc_cluster", a.cluster)
 index.set_option("profile", 1)
 torch.cuda.synchronize()
 t0 = time.time()
@@ -43,6 +46,7 @@ torch.cuda.synchronize()
 t_add = time.time() - t0
 print(json.dumps({"add_s": t_add, "add_vec_per_s": a.n / t_add, "list_min": int(sizes.min()), "list_max": int(sizes.max()),
                   "list_mean": float(sizes.mean())}))
+index.set_option("coarse_mode", a.mode)
 rows = torch.randint(0, a.n, (a.nq,), generator=g, device=dev)
 q0 = (x[rows] + torch.randn((a.nq, a.d), generator=g, device=dev) * 0.05).contiguous()
 del x
