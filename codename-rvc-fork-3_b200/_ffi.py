@@ -48,6 +48,7 @@ SIGNATURES = {
     "rvcr_index_create": (C.c_int, [_I32, _I64, C.c_int, C.POINTER(_H)]),
     "rvcr_index_read": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_H)]),
     "rvcr_index_read_shard": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_H)]),
+    "rvcr_index_set_shard": (C.c_int, [_H, _I64, _I64]),
     "rvcr_index_write": (C.c_int, [_H, C.c_char_p]),
     "rvcr_index_free": (None, [_H]),
     "rvcr_index_info": (C.c_int, [_H, C.POINTER(Info)]),
@@ -67,6 +68,7 @@ SIGNATURES = {
     "rvcr_retrieve_blend": (C.c_int, [_H, _P, _I64, C.c_double, _P, _P, _P]),
     "rvcr_retrieve_blend_host": (C.c_int, [_H, _P, _I64, C.c_double]),
     "rvcr_retrieve_blend_assigned": (C.c_int, [_H, _P, _I64, _P, C.c_double, _P, _P, _P]),
+    "rvcr_search_assigned": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P]),
     "rvcr_reconstruct_n": (C.c_int, [_H, _I64, _I64, _P, C.c_int]),
     "rvcr_merge_coarse": (C.c_int, [_P, _P, _I32, _I64, _P, C.c_int, _P]),
     "rvcr_merge_topk": (C.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, C.c_int, _P]),

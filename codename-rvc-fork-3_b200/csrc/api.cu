@@ -316,6 +316,19 @@ int rvcr_index_set_nprobe(rvcr_index* h, int64_t nprobe) {
     return RVCR_OK;
 }
 
+int rvcr_index_set_shard(rvcr_index* h, int64_t list_begin, int64_t nlist_global) {
+    if (!h) return RVCR_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (list_begin < 0 || list_begin + h->nlist > nlist_global) {
+        set_error("set_shard: lists [%lld, %lld) do not fit an index of %lld lists", (long long)list_begin,
+                  (long long)(list_begin + h->nlist), (long long)nlist_global);
+        return RVCR_ERR_INVALID;
+    }
+    h->list_begin = list_begin;
+    h->nlist_global = nlist_global;
+    return RVCR_OK;
+}
+
 int rvcr_index_set_centroids(rvcr_index* h, const float* centroids_host, int64_t nlist) {
     RVCR_ENTER(h);
     if (!centroids_host || nlist != h->nlist) {
@@ -502,6 +515,13 @@ int rvcr_retrieve_blend_assigned(rvcr_index* h, float* feats_dev, int64_t n, con
     RVCR_ENTER(h);
     if (n > 0 && (!feats_dev || !assign_dev)) return RVCR_ERR_INVALID;
     return search_device(h, feats_dev, n, assign_dev, true, index_rate, D_dev, I_dev, (cudaStream_t)stream);
+}
+
+int rvcr_search_assigned(rvcr_index* h, const float* q_dev, int64_t n, const int32_t* assign_dev, float* D_dev, int64_t* I_dev,
+                         void* stream) {
+    RVCR_ENTER(h);
+    if (n > 0 && (!q_dev || !assign_dev || !D_dev || !I_dev)) return RVCR_ERR_INVALID;
+    return search_device(h, const_cast<float*>(q_dev), n, assign_dev, false, 0.0, D_dev, I_dev, (cudaStream_t)stream);
 }
 
 int rvcr_reconstruct_n(rvcr_index* h, int64_t i0, int64_t ni, float* out, int out_on_device) {

@@ -87,95 +87,97 @@ def _assign_blas(x, cent, block: int = 8192):
 
 
 # ---- on-device by-construction generator (bench, large configs) --------------------------------
+#
+# Every quantity is a pure function of (seed, global list id / query block id), so a shard built for
+# lists [lo, hi) is bit-identical to the same lists of the full index and the query set does not
+# depend on the number of GPUs.
 
-def device_index_by_construction(index, n_total: int, nlist: int, d: int, seed: int = 1234, sigma_c: float = 0.30,
-                                 sigma_s: float = 0.05, sigma_p: float = 0.14, rows_per_chunk: int = 1 << 20,
-                                 list_range: tuple[int, int] | None = None, skew: float = 0.35):
-    """Fill `index` (created with index_factory(d, f"IVF{nlist_local},Flat")) directly on its GPU.
+LIST_BLOCK = 256        # lists whose rows share one generator stream
+QUERY_BLOCK = 65536     # queries per generator stream
 
-    Structure: nlist // 4 blob centres ~ N(0, sigma_c^2); every centroid = its blob centre +
-    N(0, sigma_s^2) (4 sibling centroids per blob, a sibling gap comparable to the bf16 margin of the
-    tensor-core coarse path, so that path's exact re-check is exercised); list l holds size[l] points
-    = centroid_l + N(0, sigma_p^2).  List sizes are log-normal around n_total / nlist (sigma = `skew`).
-    ids are a fixed pseudo-random permutation-like map (id = row position: ids ascend within a list,
-    which is the only order property faiss guarantees).  Every quantity is derived from (seed, global
-    list id), so a shard built with list_range=(lo, hi) is bit-identical to the same lists of the
-    full index.  Returns (sizes_all int64[nlist] on host).
-    """
+
+def list_sizes(n_total: int, nlist: int, seed: int = 1234, skew: float = 0.35) -> np.ndarray:
+    """Log-normal list sizes (sigma = skew) rescaled to sum exactly to n_total; host, deterministic."""
+    rng = np.random.default_rng(seed + 77)
+    w = np.exp(skew * rng.standard_normal(nlist))
+    sizes = np.floor(w / w.sum() * n_total).astype(np.int64)
+    sizes[: int(n_total - sizes.sum())] += 1
+    return sizes
+
+
+def shard_ranges(sizes: np.ndarray, world: int):
+    """Contiguous list ranges balanced by vector count -- same rule as csrc/index_io.cu shard_range."""
+    nlist = len(sizes)
+    total = int(sizes.sum())
+    pre = np.concatenate([[0], np.cumsum(sizes)])
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        bounds.append(int(np.searchsorted(pre[:-1], target, side="left")) if total else nlist * r // world)
+    bounds.append(nlist)
+    return [(bounds[r], max(bounds[r], bounds[r + 1])) for r in range(world)]
+
+
+def all_centroids(nlist: int, d: int, device, seed: int = 1234, sigma_c: float = 0.30, sigma_s: float = 0.03):
+    """nlist // 4 blob centres ~ N(0, sigma_c^2); centroid l = centre[l // 4] + N(0, sigma_s^2): four
+    sibling centroids per blob whose mutual distance (~2 d sigma_s^2 = 1.4 at d = 768) is comparable to
+    the bf16 error margin of the tensor-core coarse path, so its exact re-check is exercised."""
     import torch
-    dev = torch.device(f"cuda:{index.device}")
-    g = torch.Generator(device="cpu").manual_seed(seed)
-    # list sizes (host, deterministic): log-normal, rescaled to sum exactly n_total
-    z = torch.randn(nlist, generator=g, dtype=torch.float64)
-    w = torch.exp(skew * z)
-    sizes = torch.floor(w / w.sum() * n_total).to(torch.int64)
-    sizes[: int(n_total - int(sizes.sum()))] += 1
-    sizes_np = sizes.numpy().copy()
+    g = torch.Generator(device=device).manual_seed(seed * 1000003 + 17)
+    nb = (nlist + 3) // 4
+    centres = torch.randn((nb, d), generator=g, device=device, dtype=torch.float32) * sigma_c
+    sib = torch.randn((nlist, d), generator=g, device=device, dtype=torch.float32) * sigma_s
+    return centres[torch.arange(nlist, device=device) // 4] + sib
+
+
+def fill_index_by_construction(index, cent_all, sizes: np.ndarray, n_total: int, list_range=None, seed: int = 1234,
+                               sigma_p: float = 0.14):
+    """`index` = index_factory(d, f"IVF{hi-lo},Flat") on its GPU.  List l holds sizes[l] points
+    = centroid_l + N(0, sigma_p^2); ids = global row position (ascending inside a list, the only order
+    property faiss guarantees)."""
+    import torch
+    dev = cent_all.device
+    nlist, d = cent_all.shape
     lo, hi = (0, nlist) if list_range is None else list_range
     offs_all = np.zeros(nlist + 1, np.int64)
-    np.cumsum(sizes_np, out=offs_all[1:])
-    local_sizes = sizes_np[lo:hi]
-    index.alloc_lists(local_sizes, int(n_total))
-
-    def centroids_for(l0: int, l1: int):
-        out = torch.empty((l1 - l0, d), dtype=torch.float32, device=dev)
-        gl = torch.Generator(device=dev)
-        for l in range(l0, l1, 4096):
-            m = min(4096, l1 - l)
-            ids = torch.arange(l, l + m, device=dev)
-            blob = ids // 4
-            # blob centre: seeded by blob id block so that it is independent of the chunking
-            b0, b1 = int(blob[0]), int(blob[-1]) + 1
-            gl.manual_seed(seed * 1000003 + 17 + b0 // 1024)
-            base_blob = (b0 // 1024) * 1024
-            nb = ((b1 - base_blob + 1023) // 1024) * 1024
-            centres = torch.randn((nb, d), generator=gl, device=dev, dtype=torch.float32) * sigma_c
-            if nb > 1024:  # crossing a 1024-blob block: regenerate per block for determinism
-                parts = []
-                for bb in range(base_blob, base_blob + nb, 1024):
-                    gl.manual_seed(seed * 1000003 + 17 + bb // 1024)
-                    parts.append(torch.randn((1024, d), generator=gl, device=dev, dtype=torch.float32) * sigma_c)
-                centres = torch.cat(parts)
-            gl.manual_seed(seed * 1000003 + 7_000_003 + l // 4096)
-            sib = torch.randn((4096, d), generator=gl, device=dev, dtype=torch.float32)[: m] * sigma_s
-            out[l - l0:l - l0 + m] = centres[blob - base_blob] + sib
-        return out
-
-    cent = centroids_for(lo, hi)
-    index.set_centroids(cent.cpu().numpy())
-    vecs, ids, offsets, _ = index.device_views()
-    gl = torch.Generator(device=dev)
-    local_off = np.zeros(hi - lo + 1, np.int64)
-    np.cumsum(local_sizes, out=local_off[1:])
-    # rows are generated per list block of 256 lists: deterministic regardless of sharding
-    LB = 256
-    for l in range((lo // LB) * LB, hi, LB):
-        l0, l1 = max(l, lo), min(l + LB, hi)
-        if l0 >= l1:
+    np.cumsum(sizes, out=offs_all[1:])
+    index.alloc_lists(sizes[lo:hi], int(n_total))
+    index.set_centroids(cent_all[lo:hi].cpu().numpy())
+    vecs, ids, _, _ = index.device_views()
+    g = torch.Generator(device=dev)
+    base = int(offs_all[lo])
+    for b0 in range((lo // LIST_BLOCK) * LIST_BLOCK, hi, LIST_BLOCK):
+        b1 = min(b0 + LIST_BLOCK, nlist)
+        rows = int(offs_all[b1] - offs_all[b0])
+        if rows == 0:
             continue
-        blk_sizes = sizes_np[l:min(l + LB, nlist)]
-        blk_rows = int(blk_sizes.sum())
-        gl.manual_seed(seed * 1000003 + 9_000_011 + l // LB)
-        noise = torch.randn((blk_rows, d), generator=gl, device=dev, dtype=torch.float32) * sigma_p
-        blk_off = np.zeros(len(blk_sizes) + 1, np.int64)
-        np.cumsum(blk_sizes, out=blk_off[1:])
-        r0, r1 = int(blk_off[l0 - l]), int(blk_off[l1 - l])
-        rep = torch.repeat_interleave(torch.arange(l0 - lo, l1 - lo, device=dev),
-                                      torch.as_tensor(sizes_np[l0:l1], device=dev))
-        dst0 = int(local_off[l0 - lo])
-        vecs[dst0:dst0 + (r1 - r0)] = cent[rep] + noise[r0:r1]
-        ids[dst0:dst0 + (r1 - r0)] = torch.arange(int(offs_all[l0]), int(offs_all[l0]) + (r1 - r0), device=dev)
-        del noise, rep
+        g.manual_seed(seed * 1000003 + 9_000_011 + b0 // LIST_BLOCK)
+        noise = torch.randn((rows, d), generator=g, device=dev, dtype=torch.float32) * sigma_p
+        l0, l1 = max(b0, lo), min(b1, hi)
+        r0, r1 = int(offs_all[l0] - offs_all[b0]), int(offs_all[l1] - offs_all[b0])
+        if r1 > r0:
+            rep = torch.repeat_interleave(torch.arange(l0, l1, device=dev), torch.as_tensor(sizes[l0:l1], device=dev))
+            dst = int(offs_all[l0]) - base
+            vecs[dst:dst + (r1 - r0)] = cent_all[rep] + noise[r0:r1]
+            ids[dst:dst + (r1 - r0)] = torch.arange(int(offs_all[l0]), int(offs_all[l1]), device=dev)
+            del rep
+        del noise
     index.commit()
-    return sizes_np
 
 
-def device_queries(index_vecs, nstored: int, nq: int, d: int, seed: int = 4321, sigma_q: float = 0.05,
-                   device=None):
-    """nq queries = random stored rows + N(0, sigma_q^2) noise, generated on the GPU."""
+def device_queries(cent_all, nq: int, q_range=None, seed: int = 4321, sigma_p: float = 0.14):
+    """Fresh mixture samples: query i = centroid[list_i] + N(0, sigma_p^2), list_i uniform; generated
+    per block of QUERY_BLOCK queries so any contiguous range reproduces the same rows."""
     import torch
-    dev = index_vecs.device if device is None else device
-    gl = torch.Generator(device=dev).manual_seed(seed)
-    rows = torch.randint(0, nstored, (nq,), generator=gl, device=dev)
-    q = index_vecs[rows] + torch.randn((nq, d), generator=gl, device=dev, dtype=torch.float32) * sigma_q
-    return q.contiguous()
+    dev = cent_all.device
+    nlist, d = cent_all.shape
+    q0, q1 = (0, nq) if q_range is None else q_range
+    out = torch.empty((q1 - q0, d), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev)
+    for b0 in range((q0 // QUERY_BLOCK) * QUERY_BLOCK, q1, QUERY_BLOCK):
+        g.manual_seed(seed * 1000003 + b0 // QUERY_BLOCK)
+        lists = torch.randint(0, nlist, (QUERY_BLOCK,), generator=g, device=dev)
+        qb = cent_all[lists] + torch.randn((QUERY_BLOCK, d), generator=g, device=dev, dtype=torch.float32) * sigma_p
+        a, b = max(b0, q0), min(b0 + QUERY_BLOCK, q1)
+        out[a - q0:b - q0] = qb[a - b0:b - b0]
+    return out

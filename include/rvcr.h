@@ -95,6 +95,10 @@ RVCR_API int rvcr_index_read(const char* path, int device, rvcr_index** out);
 /* Same file, but keeps only the lists of shard `rank` of `world` (contiguous centroid ranges
  * balanced by vector count).  List ids reported by this handle stay global. */
 RVCR_API int rvcr_index_read_shard(const char* path, int device, int rank, int world, rvcr_index** out);
+/* Declare a handle created with rvcr_index_create(d, nlist_local, ...) to be the shard holding global
+ * lists [list_begin, list_begin + nlist_local) of an index with nlist_global lists (what
+ * rvcr_index_read_shard sets up from a file). */
+RVCR_API int rvcr_index_set_shard(rvcr_index* h, int64_t list_begin, int64_t nlist_global);
 /* faiss.write_index(index, path)                        rvc/train/process/extract_index.py:71 */
 RVCR_API int rvcr_index_write(rvcr_index* h, const char* path);
 RVCR_API void rvcr_index_free(rvcr_index* h);
@@ -164,6 +168,9 @@ RVCR_API int rvcr_merge_coarse(const float* dist_all_dev, const int32_t* list_al
  * of other queries are left untouched and their D / I rows are set to (FLT_MAX, -1). */
 RVCR_API int rvcr_retrieve_blend_assigned(rvcr_index* h, float* feats_dev, int64_t n, const int32_t* assign_dev,
                                  double index_rate, float* D_dev, int64_t* I_dev, void* stream);
+/* The search half of the above: local top-8 (D, I) for owned queries, (FLT_MAX, -1) rows for the rest. */
+RVCR_API int rvcr_search_assigned(rvcr_index* h, const float* q_dev, int64_t n, const int32_t* assign_dev, float* D_dev,
+                                  int64_t* I_dev, void* stream);
 /* Merge G shards' top-8 candidate lists (G x n x 8, after an all-gather) into the global
  * top-8 by (distance, id). */
 RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, int32_t G, int64_t n, int32_t k,

@@ -1,0 +1,142 @@
+"""CPU, world_size 2 and 3, gloo: the host-side logic of the sharded path (partitioning, the small
+all-gather + merge, ownership, the all-to-all that returns rows to their home rank).  The compute
+backend injected here is the oracle (test infrastructure) -- on the GPU the same ShardedIndex code
+drives the C-ABI backend (tests/test_gpu_sharded.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleShardBackend:
+    device = "cpu"
+
+    def __init__(self, oracle, x, cent, lo, hi):
+        self.o = oracle
+        self.x = x
+        full = oracle.OracleIndex.from_vectors(x, cent)
+        self.list_begin, self.nlist = lo, hi - lo
+        self.cent = cent[lo:hi]
+        b, e = full.list_off[lo], full.list_off[hi]
+        self.off = (full.list_off[lo:hi + 1] - b).astype(np.int64)
+        self.vecs, self.ids = full.vecs[b:e], full.ids[b:e]
+
+    def assign(self, q):
+        a, d = self.o.coarse_assign(q.numpy(), self.cent)
+        a = np.where(a >= 0, a + self.list_begin, -1).astype(np.int32)
+        return torch.from_numpy(a), torch.from_numpy(d)
+
+    def merge_coarse(self, dist_all, list_all):
+        d, l = dist_all.numpy(), list_all.numpy().astype(np.int64)
+        l_key = np.where(l < 0, np.iinfo(np.int64).max, l)
+        d_key = np.where(l < 0, np.inf, d)
+        order = np.lexsort((l_key, d_key), axis=0)[0]
+        out = l[order, np.arange(l.shape[1])]
+        return torch.from_numpy(out.astype(np.int32))
+
+    def retrieve_blend_assigned(self, feats, assign, index_rate, blend=True):
+        q = feats.numpy()
+        a = assign.numpy().astype(np.int64) - self.list_begin
+        own = (a >= 0) & (a < self.nlist)
+        n = q.shape[0]
+        D = np.full((n, 8), np.float32(3.4028234663852886e38), np.float32)
+        I = np.full((n, 8), -1, np.int64)
+        if own.any():
+            Do, Io = self.o.scan_topk(q[own], a[own].astype(np.int32), self.off, self.vecs, self.ids)
+            D[own], I[own] = Do, Io
+            if blend:
+                with np.errstate(all="ignore"):
+                    q[own] = self.o.tail(Do, Io, self.x, index_rate, q[own])
+        return torch.from_numpy(D), torch.from_numpy(I)
+
+    def merge_topk(self, D_all, I_all):
+        D, I = D_all.numpy(), I_all.numpy()
+        G, n, k = D.shape
+        Dc = np.transpose(D, (1, 0, 2)).reshape(n, G * k)
+        Ic = np.transpose(I, (1, 0, 2)).reshape(n, G * k)
+        key_i = np.where(Ic < 0, np.iinfo(np.int64).max, Ic)
+        order = np.lexsort((key_i, Dc), axis=1)[:, :k]
+        return torch.from_numpy(np.take_along_axis(Dc, order, 1)), torch.from_numpy(np.take_along_axis(Ic, order, 1))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    import importlib
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sharded = importlib.import_module("codename-rvc-fork-3_b200.sharded")
+    synth = importlib.import_module("codename-rvc-fork-3_b200.synth")
+    pr = synth.make_host_problem(3000, 64, 0, 48, seed=5, dup_frac=0.01)
+    x, cent = pr.x, pr.centroids
+    full = oracle.OracleIndex.from_vectors(x, cent)
+    ranges = synth.shard_ranges(np.diff(full.list_off), world)
+    lo, hi = ranges[rank]
+    be = OracleShardBackend(oracle, x, cent, lo, hi)
+    sh = sharded.ShardedIndex(be)
+    assert sh.ranges == [tuple(r) for r in ranges]
+    # ragged home batches: rank r brings 40 + 13 r queries (one of them NaN on rank 0)
+    rng = np.random.default_rng(100 + rank)
+    n_r = 40 + 13 * rank
+    q = (x[rng.integers(0, len(x), n_r)] + rng.standard_normal((n_r, 64)).astype(np.float32) * 0.05).astype(np.float32)
+    if rank == 0:
+        q[3, 0] = np.nan
+    Dw, Iw = full.search(q)
+    with np.errstate(all="ignore"):
+        want = oracle.tail(Dw, Iw, x, 0.75, q)
+    feats = torch.from_numpy(q.copy())
+    out, D, I = sh.retrieve_blend_(feats, 0.75, want_neighbours=True)
+    assert out.data_ptr() == feats.data_ptr()
+    np.testing.assert_array_equal(D.numpy(), Dw)
+    np.testing.assert_array_equal(I.numpy(), Iw)
+    assert np.array_equal(out.numpy(), want, equal_nan=True)
+    Ds, Is = sh.search(torch.from_numpy(q.copy()))
+    np.testing.assert_array_equal(Ds.numpy(), Dw)
+    np.testing.assert_array_equal(Is.numpy(), Iw)
+    # an empty home batch on one rank
+    q2 = q[:0] if rank == world - 1 else q[:5]
+    f2 = torch.from_numpy(q2.copy())
+    sh.retrieve_blend_(f2, 0.3)
+    if len(q2):
+        with np.errstate(all="ignore"):
+            w2 = oracle.tail(*full.search(q2), x, 0.3, q2)
+        assert np.array_equal(f2.numpy(), w2, equal_nan=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_equals_single_on_gloo(world, tmp_path, oracle):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_shard_ranges_cover_and_balance():
+    import importlib
+    sys.path.insert(0, ROOT)
+    synth = importlib.import_module("codename-rvc-fork-3_b200.synth")
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(0, 500, 1000)
+    for world in (1, 2, 4, 8):
+        rs = synth.shard_ranges(sizes, world)
+        assert rs[0][0] == 0 and rs[-1][1] == 1000 and all(a[1] == b[0] for a, b in zip(rs[:-1], rs[1:]))
+        tot = [int(sizes[a:b].sum()) for a, b in rs]
+        assert max(tot) - min(tot) <= 2 * sizes.max()
