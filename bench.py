@@ -213,6 +213,7 @@ def main():
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- build this rank's shard (by construction, on the device) --------------------------------
@@ -221,10 +222,8 @@ def main():
     ranges = synth.shard_ranges(sizes, world)
     lo, hi = ranges[rank]
     cent_all = synth.all_centroids(nlist, d, dev)
-    index = rvcr.index_factory(d, f"IVF{hi - lo},Flat", device=local_rank)
+    index = rvcr.index_factory(d, f"IVF{nlist},Flat", device=local_rank)
     index.nprobe = 1
-    if world > 1:
-        index.set_shard(lo, nlist)            # shard handles report global list ids
     synth.fill_index_by_construction(index, cent_all, sizes, N, list_range=(lo, hi))
     index.set_option("coarse_mode", args.coarse_mode)
     index.set_option("profile", 1)
@@ -236,16 +235,14 @@ def main():
     setup_s = time.time() - t_setup
 
     sh = None
-    counts = None
     if world > 1:
         sh = sharded.ShardedIndex(sharded.CudaShardBackend(index))
-        counts = [nq * (r + 1) // world - nq * r // world for r in range(world)]
 
     def step(buf):
         if sh is None:
             index.retrieve_blend_(buf, INDEX_RATE)
         else:
-            sh.retrieve_blend_(buf, INDEX_RATE, counts=counts)
+            sh.retrieve_blend_(buf, INDEX_RATE)
 
     def barrier():
         if world > 1:
@@ -295,9 +292,8 @@ def main():
     st = index.stats()
     pk = peaks()
     nst = int(sizes[lo:hi].sum())
-    nq_rank = nq if sh is None else nq          # every rank runs the coarse step over all queries
-    owned_q = nq / world
-    coarse_flops = 2.0 * nq_rank * (hi - lo) * d
+    owned_q = nq / world                        # uniform queries: each shard owns ~1/world of them
+    coarse_flops = 2.0 * n_home * nlist * d     # home queries x all centroids (replicated quantizer)
     scan_bytes = nst * (4 * d + 8) + owned_q * 4 * d + owned_q * K * 12      # B_s: every list probed at these sizes
     blend_bytes = owned_q * (K * 4 * d + 8 * d) + owned_q * K * 12           # B_g
     roof = {}
@@ -345,7 +341,7 @@ def main():
                 index.retrieve_blend_host_(host.numpy(), INDEX_RATE)     # H2D, search+blend, D2H, sync
             else:
                 b = host.to(dev, non_blocking=True)
-                sh.retrieve_blend_(b, INDEX_RATE, counts=counts)
+                sh.retrieve_blend_(b, INDEX_RATE)
                 host.copy_(b, non_blocking=True)
                 torch.cuda.synchronize()
             barrier()
@@ -372,9 +368,9 @@ def main():
         a, _ = oracle.coarse_assign_blas(qs, cent_h)                 # untimed: which lists to stage on the host
         probed = np.unique(a[a >= 0])
         offs_h = offs_d.cpu().numpy()
-        sz = np.zeros(hi - lo, np.int64)
+        sz = np.zeros(nlist, np.int64)
         sz[probed] = offs_h[probed + 1] - offs_h[probed]
-        sub_off = np.zeros(hi - lo + 1, np.int64)
+        sub_off = np.zeros(nlist + 1, np.int64)
         np.cumsum(sz, out=sub_off[1:])
         sub_vecs = np.empty((int(sub_off[-1]), d), np.float32)
         for l in probed:
@@ -386,7 +382,7 @@ def main():
         sec = time.perf_counter() - t0
         import torch as _t
         cpu = {"value": sample / sec, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
-               "sample": f"first {sample} of {nq} query frames of this workload, all {hi - lo} centroids, the {len(probed)} lists "
+               "sample": f"first {sample} of {nq} query frames of this workload, all {nlist} centroids, the {len(probed)} lists "
                          f"they probe staged on the host; {sec:.2f} s of CPU work; oracle port of faiss 1.7.3 + numpy "
                          f"(omp_threads={oracle.num_threads()}, torch_threads={_t.get_num_threads()})"}
         del sub_vecs

@@ -25,8 +25,8 @@ class RvcrError(RuntimeError):
 
 class Info(C.Structure):
     _fields_ = [("d", C.c_int32), ("is_trained", C.c_int32), ("ntotal", C.c_int64), ("nlist", C.c_int64),
-                ("nprobe", C.c_int64), ("nstored", C.c_int64), ("list_begin", C.c_int64),
-                ("nlist_global", C.c_int64), ("device", C.c_int32), ("metric", C.c_int32)]
+                ("nprobe", C.c_int64), ("nstored", C.c_int64), ("owned_begin", C.c_int64),
+                ("owned_end", C.c_int64), ("device", C.c_int32), ("metric", C.c_int32)]
 
 
 class Stats(C.Structure):

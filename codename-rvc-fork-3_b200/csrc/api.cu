@@ -119,7 +119,8 @@ int search_device(rvcr_index* h, float* feats_or_q, int64_t n, const int32_t* as
     if (n == 0) return RVCR_OK;
     RVCR_TRY(finalize_pending(h, s));
     RVCR_TRY(stream_enter(h, s));
-    for (int i = 0; i < RVCR_NUM_PHASES; ++i) h->pev_used[i] = false;
+    // a caller-supplied assignment came from an earlier rvcr_assign call: keep its coarse phase timings
+    for (int i = assign_in ? RVCR_PHASE_GROUP : 0; i < RVCR_NUM_PHASES; ++i) h->pev_used[i] = false;
     const int32_t* assign = assign_in;
     if (!assign) {
         RVCR_TRY(h->ws_assign.reserve((size_t)n * 4));
@@ -230,7 +231,8 @@ int rvcr_index_create(int32_t d, int64_t nlist, int device, rvcr_index** out) {
     h->device = device;
     h->d = d;
     h->nlist = nlist;
-    h->nlist_global = nlist;
+    h->own_lo = 0;
+    h->own_hi = nlist;
     h->num_sms = prop.multiProcessorCount;
     h->offsets_host.assign((size_t)nlist + 1, 0);
     {
@@ -302,8 +304,8 @@ int rvcr_index_info(rvcr_index* h, rvcr_info* out) {
     out->nlist = h->nlist;
     out->nprobe = h->nprobe;
     out->nstored = h->nstored + h->npending;
-    out->list_begin = h->list_begin;
-    out->nlist_global = h->nlist_global;
+    out->owned_begin = h->own_lo;
+    out->owned_end = h->own_hi;
     out->device = h->device;
     out->metric = h->metric;
     return RVCR_OK;
@@ -316,16 +318,16 @@ int rvcr_index_set_nprobe(rvcr_index* h, int64_t nprobe) {
     return RVCR_OK;
 }
 
-int rvcr_index_set_shard(rvcr_index* h, int64_t list_begin, int64_t nlist_global) {
+int rvcr_index_set_shard(rvcr_index* h, int64_t owned_begin, int64_t owned_end) {
     if (!h) return RVCR_ERR_INVALID;
     std::lock_guard<std::mutex> lock(h->mu);
-    if (list_begin < 0 || list_begin + h->nlist > nlist_global) {
-        set_error("set_shard: lists [%lld, %lld) do not fit an index of %lld lists", (long long)list_begin,
-                  (long long)(list_begin + h->nlist), (long long)nlist_global);
+    if (owned_begin < 0 || owned_begin > owned_end || owned_end > h->nlist) {
+        set_error("set_shard: [%lld, %lld) is not a list range of an index with %lld lists", (long long)owned_begin,
+                  (long long)owned_end, (long long)h->nlist);
         return RVCR_ERR_INVALID;
     }
-    h->list_begin = list_begin;
-    h->nlist_global = nlist_global;
+    h->own_lo = owned_begin;
+    h->own_hi = owned_end;
     return RVCR_OK;
 }
 
@@ -461,6 +463,7 @@ int rvcr_assign(rvcr_index* h, const float* x_dev, int64_t n, int32_t* list_out_
     }
     if (n == 0) return RVCR_OK;
     RVCR_TRY(stream_enter(h, s));
+    for (int i = 0; i < RVCR_NUM_PHASES; ++i) h->pev_used[i] = false;
     RVCR_TRY(coarse_dispatch(h, x_dev, n, list_out_dev, dist_out_dev, s));
     return stream_leave(h, s);
 }

@@ -22,16 +22,16 @@ namespace rvcr {
 
 __global__ void __launch_bounds__(256)
 gather_blend_kernel(float* __restrict__ feats, int64_t n, int d, const float* __restrict__ D,
-                    const int32_t* __restrict__ P, const int32_t* __restrict__ assign, int64_t list_begin,
-                    int64_t nlist, const float* __restrict__ vecs, int64_t last_row_pos, float r32, float omr32) {
+                    const int32_t* __restrict__ P, const int32_t* __restrict__ assign, int64_t own_lo,
+                    int64_t own_hi, const float* __restrict__ vecs, int64_t last_row_pos, float r32, float omr32) {
     __shared__ float sw[RVCR_K];
     __shared__ int spos[RVCR_K];
     const int tid = threadIdx.x;
     const int nvec = d >> 2;
     for (int64_t qi = blockIdx.x; qi < n; qi += gridDim.x) {
         if (assign) {
-            const int64_t a = (int64_t)assign[qi] - list_begin;  // block-uniform
-            if (a < 0 || a >= nlist) continue;
+            const int64_t a = (int64_t)assign[qi];  // block-uniform
+            if (a >= 0 && (a < own_lo || a >= own_hi)) continue;  // another shard's query
         }
         if (tid < 32) {
             float w = 0.f;
@@ -101,7 +101,7 @@ int gather_blend(rvcr_index* h, float* feats, int64_t n, const float* D, const i
     if (threads < 32) threads = 32;
     int64_t grid = (int64_t)h->num_sms * (2048 / threads);
     if (grid > n) grid = n;
-    gather_blend_kernel<<<(unsigned)grid, threads, 0, s>>>(feats, n, h->d, D, P, assign, h->list_begin, h->nlist, h->vecs,
+    gather_blend_kernel<<<(unsigned)grid, threads, 0, s>>>(feats, n, h->d, D, P, assign, h->own_lo, h->own_hi, h->vecs,
                                                             h->last_row_pos, r32, omr32);
     RVCR_CHECK_LAUNCH();
     count_launch(h);

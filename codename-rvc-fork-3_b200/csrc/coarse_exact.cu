@@ -203,7 +203,7 @@ int coarse_exact(rvcr_index* h, const float* q, int64_t n, const int32_t* qsel, 
     dim3 grid((unsigned)qtiles, (unsigned)nsplit);
     coarse_exact_kernel<<<grid, PD_THREADS, smem, s>>>(q, qsel, nwork, nullptr, h->cent, h->nlist, h->d, bps, best);
     RVCR_CHECK_LAUNCH();
-    unpack_best_kernel<<<(unsigned)((nwork + 255) / 256), 256, 0, s>>>(best, qsel, nwork, nullptr, h->list_begin, list_out,
+    unpack_best_kernel<<<(unsigned)((nwork + 255) / 256), 256, 0, s>>>(best, qsel, nwork, nullptr, 0, list_out,
                                                                          dist_out);
     RVCR_CHECK_LAUNCH();
     count_launch(h, 3);
@@ -234,7 +234,7 @@ int coarse_exact_selected(rvcr_index* h, const float* q, int64_t n, const int32_
     dim3 grid((unsigned)gx, (unsigned)nsplit);
     coarse_exact_kernel<<<grid, PD_THREADS, smem, s>>>(q, qsel, n, nsel_dev, h->cent, h->nlist, h->d, bps, best);
     RVCR_CHECK_LAUNCH();
-    unpack_best_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(best, qsel, n, nsel_dev, h->list_begin, list_out, dist_out);
+    unpack_best_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(best, qsel, n, nsel_dev, 0, list_out, dist_out);
     RVCR_CHECK_LAUNCH();
     count_launch(h, 3);
     return RVCR_OK;

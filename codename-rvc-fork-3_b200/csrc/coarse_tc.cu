@@ -756,7 +756,7 @@ int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float
     RVCR_CUDA(cudaMemsetAsync(counters, 0, 4, s));
     const int64_t thr = n * 32;
     tc_recheck_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, h->d, h->cent, h->nlist, qnorm, h->cent_norm_max, rel,
-                                                                     absm, topv, topj, nsplit, h->list_begin, list_out, dist_out,
+                                                                     absm, topv, topj, nsplit, 0, list_out, dist_out,
                                                                      fb_list, counters);
     RVCR_CHECK_LAUNCH();
     count_launch(h);

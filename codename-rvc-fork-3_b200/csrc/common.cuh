@@ -72,9 +72,9 @@ struct rvcr_index {
     int d = 0;
     int metric = 1;
     bool trained = false;
-    int64_t nlist = 0;         // lists held by this handle
-    int64_t nlist_global = 0;  // lists of the whole index
-    int64_t list_begin = 0;    // first global list id held
+    int64_t nlist = 0;         // lists (== centroids) of the index; the quantizer is always complete
+    int64_t own_lo = 0;        // a shard stores only lists [own_lo, own_hi); the others are empty here
+    int64_t own_hi = 0;
     int64_t ntotal = 0;        // faiss ntotal of the whole index
     int64_t nstored = 0;       // rows in `vecs`
     int64_t nprobe = 1;

@@ -174,10 +174,11 @@ int read_index_file(const char* path, int device, int rank, int world, rvcr_inde
     int64_t lo = 0, hi = (int64_t)nlist;
     if (world > 1) shard_range(sizes, rank, world, lo, hi);
 
+    // the quantizer (all centroids) is replicated on every shard; only lists [lo, hi) are stored
     rvcr_index* h = nullptr;
-    RVCR_TRY(rvcr_index_create(ih.d, hi - lo, device, &h));
-    h->nlist_global = (int64_t)nlist;
-    h->list_begin = lo;
+    RVCR_TRY(rvcr_index_create(ih.d, (int64_t)nlist, device, &h));
+    h->own_lo = lo;
+    h->own_hi = hi;
     h->ntotal = ih.ntotal;
     h->nprobe = (int64_t)nprobe;
     auto fail = [&](int rc) {
@@ -185,11 +186,12 @@ int read_index_file(const char* path, int device, int rank, int world, rvcr_inde
         return rc;
     };
     {
-        int rc = rvcr_index_set_centroids(h, cent.data() + (size_t)lo * ih.d, hi - lo);
+        int rc = rvcr_index_set_centroids(h, cent.data(), (int64_t)nlist);
         if (rc != RVCR_OK) return fail(rc);
         h->trained = ih.trained != 0;
     }
-    std::vector<int64_t> local_sizes(sizes.begin() + lo, sizes.begin() + hi);
+    std::vector<int64_t> local_sizes((size_t)nlist, 0);
+    for (int64_t l = lo; l < hi; ++l) local_sizes[l] = sizes[l];
     {
         int64_t nst = 0;
         for (int64_t s : local_sizes) nst += s;
@@ -243,7 +245,7 @@ int read_index_file(const char* path, int device, int rank, int world, rvcr_inde
                 }
                 continue;
             }
-            const int64_t off = h->offsets_host[l - lo];
+            const int64_t off = h->offsets_host[l];
             if (!copy_piece(reinterpret_cast<char*>(h->vecs) + (size_t)off * rowb, (size_t)n * rowb) ||
                 !copy_piece(reinterpret_cast<char*>(h->ids) + (size_t)off * 8, (size_t)n * 8)) {
                 set_error("'%s': truncated list payload or copy failure (list %lld)", path, (long long)l);
@@ -268,7 +270,7 @@ int read_index_file(const char* path, int device, int rank, int world, rvcr_inde
 }
 
 int write_index_file(rvcr_index* h, const char* path) {
-    if (h->nlist != h->nlist_global || h->list_begin != 0) {
+    if (h->own_lo != 0 || h->own_hi != h->nlist) {
         set_error("write_index on a shard handle is unsupported");
         return RVCR_ERR_UNSUPPORTED;
     }

@@ -48,13 +48,13 @@ void DevBuf::release() {
 
 // ------------------------------------------------------------------------------ kernels ----
 
-__global__ void hist_lists_kernel(const int32_t* __restrict__ assign, int64_t n, int64_t list_begin, int64_t nlist,
+__global__ void hist_lists_kernel(const int32_t* __restrict__ assign, int64_t n, int64_t own_lo, int64_t own_hi, int64_t nlist,
                                   unsigned long long* __restrict__ counts, uint32_t* __restrict__ keys,
                                   int32_t* __restrict__ vals) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int64_t a = (int64_t)assign[i] - list_begin;
-    const bool ok = a >= 0 && a < nlist;
+    int64_t a = (int64_t)assign[i];
+    const bool ok = a >= own_lo && a < own_hi;  // a shard keeps only the rows of the lists it owns
     if (ok) atomicAdd(&counts[a], 1ull);
     keys[i] = ok ? (uint32_t)a : (uint32_t)nlist;  // dropped rows sort last
     vals[i] = (int32_t)i;
@@ -180,7 +180,7 @@ int finalize_pending(rvcr_index* h, cudaStream_t s) {
     FIN_TRY(keys2.reserve((size_t)nnew * 4));
     FIN_TRY(vals2.reserve((size_t)nnew * 4));
     FIN_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)(nlist + 1) * 8, s));
-    hist_lists_kernel<<<(unsigned)((nnew + 255) / 256), 256, 0, s>>>(stage_assign, nnew, h->list_begin, nlist,
+    hist_lists_kernel<<<(unsigned)((nnew + 255) / 256), 256, 0, s>>>(stage_assign, nnew, h->own_lo, h->own_hi, nlist,
                                                                       counts.as<unsigned long long>(), keys.as<uint32_t>(),
                                                                       vals.as<int32_t>());
     FIN_CUDA(cudaGetLastError());

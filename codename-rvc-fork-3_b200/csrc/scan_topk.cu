@@ -26,24 +26,25 @@ constexpr int SC_DSTRIDE = 33;
 
 // ------------------------------------------------------------------ grouping by list --------
 
-__global__ void make_keys_kernel(const int32_t* __restrict__ assign, int64_t n, int64_t list_begin,
+__global__ void make_keys_kernel(const int32_t* __restrict__ assign, int64_t n, int64_t own_lo, int64_t own_hi,
                                  int64_t nlist, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int64_t a = (int64_t)assign[i] - list_begin;
-    keys[i] = (a < 0 || a >= nlist) ? (uint32_t)nlist : (uint32_t)a;  // nlist = "not ours / invalid"
+    int64_t a = (int64_t)assign[i];
+    // nlist = invalid assignment (NaN query): answered with an all-pad row; nlist + 1 = another shard's list
+    keys[i] = a < 0 ? (uint32_t)nlist : (a < own_lo || a >= own_hi) ? (uint32_t)nlist + 1u : (uint32_t)a;
     vals[i] = (int32_t)i;
 }
 
 // flags[p] = 1 iff sorted position p starts a work item: first of its list segment, or a multiple
-// of SC_QT past the segment start.  Positions whose key == nlist (not owned) form no item when
-// skip_foreign is set.
+// of SC_QT past the segment start.  Positions whose key == nlist + 1 (a list another shard owns) form
+// no item.
 __global__ void flag_items_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t nlist, int skip_foreign,
                                   uint8_t* __restrict__ flags) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
     uint32_t k = keys[p];
-    if (skip_foreign && k == nlist) {
+    if (skip_foreign && k == nlist + 1u) {
         flags[p] = 0;
         return;
     }
@@ -240,10 +241,10 @@ int group_queries(rvcr_index* h, const int32_t* assign, int64_t n, bool only_loc
     RVCR_TRY(h->ws_misc.reserve(64));
     const int tb = 256;
     const unsigned nb = (unsigned)((n + tb - 1) / tb);
-    make_keys_kernel<<<nb, tb, 0, s>>>(assign, n, h->list_begin, h->nlist, h->ws_keys.as<uint32_t>(),
+    make_keys_kernel<<<nb, tb, 0, s>>>(assign, n, h->own_lo, h->own_hi, h->nlist, h->ws_keys.as<uint32_t>(),
                                        h->ws_vals.as<int32_t>());
     RVCR_CHECK_LAUNCH();
-    const int end_bit = ceil_log2((uint64_t)h->nlist + 1);
+    const int end_bit = ceil_log2((uint64_t)h->nlist + 2);
     size_t tmp = 0;
     RVCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->ws_keys.as<uint32_t>(), h->ws_keys2.as<uint32_t>(),
                                               h->ws_vals.as<int32_t>(), h->ws_vals2.as<int32_t>(), (int)n, 0, end_bit, s));

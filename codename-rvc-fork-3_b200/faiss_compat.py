@@ -121,9 +121,9 @@ class IndexIVFFlat:
         c = _as_f32_2d(centroids, inf.d, "set_centroids")
         check(lib().rvcr_index_set_centroids(self.handle, c.ctypes.data_as(C.c_void_p), c.shape[0]))
 
-    def set_shard(self, list_begin: int, nlist_global: int) -> None:
-        """This handle holds global lists [list_begin, list_begin + nlist) of a larger index."""
-        check(lib().rvcr_index_set_shard(self.handle, int(list_begin), int(nlist_global)))
+    def set_shard(self, owned_begin: int, owned_end: int) -> None:
+        """This handle stores only lists [owned_begin, owned_end); the quantizer stays complete."""
+        check(lib().rvcr_index_set_shard(self.handle, int(owned_begin), int(owned_end)))
 
     def get_centroids(self) -> np.ndarray:
         inf = self._info()

@@ -132,17 +132,22 @@ def all_centroids(nlist: int, d: int, device, seed: int = 1234, sigma_c: float =
 
 def fill_index_by_construction(index, cent_all, sizes: np.ndarray, n_total: int, list_range=None, seed: int = 1234,
                                sigma_p: float = 0.14):
-    """`index` = index_factory(d, f"IVF{hi-lo},Flat") on its GPU.  List l holds sizes[l] points
+    """`index` = index_factory(d, f"IVF{nlist},Flat") on its GPU.  List l holds sizes[l] points
     = centroid_l + N(0, sigma_p^2); ids = global row position (ascending inside a list, the only order
-    property faiss guarantees)."""
+    property faiss guarantees).  With list_range=(lo, hi) only those lists are stored (a shard); the
+    quantizer is always complete."""
     import torch
     dev = cent_all.device
     nlist, d = cent_all.shape
     lo, hi = (0, nlist) if list_range is None else list_range
     offs_all = np.zeros(nlist + 1, np.int64)
     np.cumsum(sizes, out=offs_all[1:])
-    index.alloc_lists(sizes[lo:hi], int(n_total))
-    index.set_centroids(cent_all[lo:hi].cpu().numpy())
+    local = np.zeros(nlist, np.int64)
+    local[lo:hi] = sizes[lo:hi]
+    index.alloc_lists(local, int(n_total))
+    index.set_centroids(cent_all.cpu().numpy())
+    if (lo, hi) != (0, nlist):
+        index.set_shard(lo, hi)
     vecs, ids, _, _ = index.device_views()
     g = torch.Generator(device=dev)
     base = int(offs_all[lo])

@@ -60,11 +60,11 @@ typedef struct rvcr_info {
     int32_t d;            /* vector dimension (768 for v2 / ContentVec, 256 for v1)             */
     int32_t is_trained;   /* quantizer holds centroids                                          */
     int64_t ntotal;       /* faiss Index::ntotal                                                */
-    int64_t nlist;        /* number of inverted lists == number of centroids held by this shard  */
+    int64_t nlist;        /* number of inverted lists == number of centroids (always the whole index) */
     int64_t nprobe;       /* value persisted in the file (extract_index.py:64 sets 1)           */
     int64_t nstored;      /* vectors stored in this handle's lists (== ntotal unless sharded)   */
-    int64_t list_begin;   /* first global list id held (0 unless sharded)                       */
-    int64_t nlist_global; /* number of lists of the whole index                                 */
+    int64_t owned_begin;  /* a shard stores lists [owned_begin, owned_end) only; 0 / nlist      */
+    int64_t owned_end;    /*   for a complete index                                             */
     int32_t device;
     int32_t metric;       /* 1 = METRIC_L2                                                      */
 } rvcr_info;
@@ -92,13 +92,14 @@ RVCR_API int rvcr_index_create(int32_t d, int64_t nlist, int device, rvcr_index*
 /* faiss.read_index(path)                                rvc/infer/pipeline.py:555
  * Streams the file straight into list-ordered device storage; no host copy of the vectors. */
 RVCR_API int rvcr_index_read(const char* path, int device, rvcr_index** out);
-/* Same file, but keeps only the lists of shard `rank` of `world` (contiguous centroid ranges
- * balanced by vector count).  List ids reported by this handle stay global. */
+/* Same file, but stores only the lists of shard `rank` of `world` (contiguous list-id ranges balanced
+ * by vector count).  The quantizer (all centroids, a few hundred MB at most) is replicated on every
+ * shard, so rvcr_assign on any shard gives the global assignment; list ids are global. */
 RVCR_API int rvcr_index_read_shard(const char* path, int device, int rank, int world, rvcr_index** out);
-/* Declare a handle created with rvcr_index_create(d, nlist_local, ...) to be the shard holding global
- * lists [list_begin, list_begin + nlist_local) of an index with nlist_global lists (what
- * rvcr_index_read_shard sets up from a file). */
-RVCR_API int rvcr_index_set_shard(rvcr_index* h, int64_t list_begin, int64_t nlist_global);
+/* Declare that this handle stores only lists [owned_begin, owned_end) of the index (what
+ * rvcr_index_read_shard sets up from a file): adds drop rows of other lists, the *_assigned entry
+ * points skip queries assigned to other lists. */
+RVCR_API int rvcr_index_set_shard(rvcr_index* h, int64_t owned_begin, int64_t owned_end);
 /* faiss.write_index(index, path)                        rvc/train/process/extract_index.py:71 */
 RVCR_API int rvcr_index_write(rvcr_index* h, const char* path);
 RVCR_API void rvcr_index_free(rvcr_index* h);
@@ -136,7 +137,7 @@ RVCR_API int rvcr_index_commit(rvcr_index* h, void* stream);
 
 /* ------------------------------------------------------------------------------- search --- */
 
-/* quantizer->assign(n, x): nearest centroid (global list id), lowest id on ties; optional
+/* quantizer->assign(n, x): nearest centroid (list id), lowest id on ties; optional
  * canonical distance to it.                  faiss IndexFlatL2::search(k=1), pipeline.py:499 */
 RVCR_API int rvcr_assign(rvcr_index* h, const float* x_dev, int64_t n, int32_t* list_out_dev,
                 float* dist_out_dev /* may be NULL */, void* stream);

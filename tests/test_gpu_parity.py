@@ -266,13 +266,25 @@ def test_sparse_file_and_shard_reader(rvcr, oracle, tmp_path):
     assert np.array_equal(If, Io) and np.array_equal(Df, Do)
     shards = [rvcr.read_index(path, shard=(r, 2)) for r in range(2)]
     infos = [s.info for s in shards]
-    assert infos[0]["list_begin"] == 0 and infos[0]["list_begin"] + infos[0]["nlist"] == infos[1]["list_begin"]
-    assert infos[1]["list_begin"] + infos[1]["nlist"] == nlist
+    assert infos[0]["owned_begin"] == 0 and infos[0]["owned_end"] == infos[1]["owned_begin"]
+    assert infos[1]["owned_end"] == nlist and infos[0]["nlist"] == infos[1]["nlist"] == nlist
     assert infos[0]["nstored"] + infos[1]["nstored"] == 900
     assert abs(infos[0]["nstored"] - 450) <= np.diff(oidx.list_off).max()
+    from importlib import import_module
+    synth = import_module("codename-rvc-fork-3_b200.synth")
+    assert [(i["owned_begin"], i["owned_end"]) for i in infos] == synth.shard_ranges(np.diff(oidx.list_off), 2)
+    # the quantizer is replicated: every shard gives the global assignment; each answers for its lists
     qd = torch.from_numpy(q).cuda()
-    la, da = zip(*[s.assign(qd) for s in shards])
-    ao, _ = oidx_assign = oracle.coarse_assign(q, cent)
-    la = np.stack([t.cpu().numpy() for t in la]); da = np.stack([t.cpu().numpy() for t in da])
-    best = np.where((da[0] < da[1]) | ((da[0] == da[1]) & (la[0] < la[1])), la[0], la[1])
-    assert np.array_equal(best, ao)
+    ao, _ = oracle.coarse_assign(q, cent)
+    D2 = np.full_like(Do, np.float32(3.4028234663852886e38)); I2 = np.full_like(Io, -1)
+    for s in shards:
+        la, _ = s.assign(qd)
+        assert np.array_equal(la.cpu().numpy(), ao)
+        Ds, Is = s.search(qd)                         # pads for queries whose list another shard stores
+        Ds, Is = Ds.cpu().numpy(), Is.cpu().numpy()
+        mine = (ao >= s.info["owned_begin"]) & (ao < s.info["owned_end"])
+        assert (Is[~mine] == -1).all()
+        D2[mine], I2[mine] = Ds[mine], Is[mine]
+    assert np.array_equal(I2, Io) and np.array_equal(D2, Do)
+    with pytest.raises(rvcr.RvcrError):
+        rvcr.write_index(shards[0], str(tmp_path / "no.index"))       # a shard cannot be serialised

@@ -1,0 +1,85 @@
+"""GPU, 2 ranks on one box (NCCL over NVLink): the sharded path through the C ABI equals the single-GPU
+path bit for bit -- assignments, neighbour ids, distances and blended rows.  Skipped with < 2 GPUs."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    import importlib
+
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    rvcr = importlib.import_module("codename-rvc-fork-3_b200")
+    sharded = importlib.import_module("codename-rvc-fork-3_b200.sharded")
+    synth = importlib.import_module("codename-rvc-fork-3_b200.synth")
+    path = os.path.join(tmp, "full.index")
+    z = np.load(os.path.join(tmp, "problem.npz"))
+    q_all = z["q"]
+    shard = rvcr.read_index(path, device=rank, shard=(rank, world))
+    full = rvcr.read_index(path, device=rank)
+    sizes = full.list_sizes()
+    assert (shard.info["owned_begin"], shard.info["owned_end"]) == synth.shard_ranges(sizes, world)[rank]
+    sh = sharded.ShardedIndex(sharded.CudaShardBackend(shard))
+    n = len(q_all)
+    lo = n * rank // world + (3 if rank else 0)                              # ragged home batches
+    hi = n * (rank + 1) // world + (3 if rank + 1 < world else 0)
+    q = q_all[lo:hi]
+    for mode in (1, 2):
+        shard.set_option("coarse_mode", mode)
+        full.set_option("coarse_mode", mode)
+        ref = torch.from_numpy(q.copy()).cuda()
+        _, Dr, Ir = full.retrieve_blend_(ref, 0.75, want_neighbours=True)
+        got = torch.from_numpy(q.copy()).cuda()
+        _, Dg, Ig = sh.retrieve_blend_(got, 0.75, want_neighbours=True)
+        torch.cuda.synchronize()
+        assert torch.equal(Ig, Ir) and torch.equal(Dg, Dr)
+        assert np.array_equal(got.cpu().numpy(), ref.cpu().numpy(), equal_nan=True)
+        Ds, Is = sh.search(torch.from_numpy(q.copy()).cuda())
+        assert torch.equal(Is, Ir) and torch.equal(Ds, Dr)
+    # an empty home batch on one rank
+    q2 = q[:0] if rank == world - 1 else q[:7]
+    f2 = torch.from_numpy(q2.copy()).cuda()
+    sh.retrieve_blend_(f2, 0.3)
+    if len(q2):
+        r2 = torch.from_numpy(q2.copy()).cuda()
+        full.retrieve_blend_(r2, 0.3)
+        assert np.array_equal(f2.cpu().numpy(), r2.cpu().numpy(), equal_nan=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+
+
+def test_two_shards_equal_one_gpu(rvcr, oracle, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from importlib import import_module
+    synth = import_module("codename-rvc-fork-3_b200.synth")
+    pr = synth.make_host_problem(40_000, 768, 2000, 512, seed=9, dup_frac=0.005)
+    pr.q[17, 5] = np.nan
+    oidx = oracle.OracleIndex.from_vectors(pr.x, pr.centroids)
+    oracle.write_index(oidx.to_data(), str(tmp_path / "full.index"))
+    np.savez(tmp_path / "problem.npz", q=pr.q)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(2))

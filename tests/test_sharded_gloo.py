@@ -16,35 +16,33 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class OracleShardBackend:
+    """The oracle standing in for the C-ABI backend: full quantizer, lists [lo, hi) only."""
     device = "cpu"
 
     def __init__(self, oracle, x, cent, lo, hi):
         self.o = oracle
         self.x = x
+        self.cent = cent
         full = oracle.OracleIndex.from_vectors(x, cent)
-        self.list_begin, self.nlist = lo, hi - lo
-        self.cent = cent[lo:hi]
+        self.nlist = len(cent)
+        self.owned = (lo, hi)
+        sizes = np.diff(full.list_off)
+        local = np.zeros_like(sizes)
+        local[lo:hi] = sizes[lo:hi]
+        self.off = np.zeros(self.nlist + 1, np.int64)
+        np.cumsum(local, out=self.off[1:])
         b, e = full.list_off[lo], full.list_off[hi]
-        self.off = (full.list_off[lo:hi + 1] - b).astype(np.int64)
         self.vecs, self.ids = full.vecs[b:e], full.ids[b:e]
 
     def assign(self, q):
         a, d = self.o.coarse_assign(q.numpy(), self.cent)
-        a = np.where(a >= 0, a + self.list_begin, -1).astype(np.int32)
         return torch.from_numpy(a), torch.from_numpy(d)
 
-    def merge_coarse(self, dist_all, list_all):
-        d, l = dist_all.numpy(), list_all.numpy().astype(np.int64)
-        l_key = np.where(l < 0, np.iinfo(np.int64).max, l)
-        d_key = np.where(l < 0, np.inf, d)
-        order = np.lexsort((l_key, d_key), axis=0)[0]
-        out = l[order, np.arange(l.shape[1])]
-        return torch.from_numpy(out.astype(np.int32))
-
-    def retrieve_blend_assigned(self, feats, assign, index_rate, blend=True):
+    def scan_assigned(self, feats, assign, index_rate, blend=True):
         q = feats.numpy()
-        a = assign.numpy().astype(np.int64) - self.list_begin
-        own = (a >= 0) & (a < self.nlist)
+        a = assign.numpy().astype(np.int64)
+        lo, hi = self.owned
+        own = (a < 0) | ((a >= lo) & (a < hi))          # invalid assignments are answered with pads / NaN
         n = q.shape[0]
         D = np.full((n, 8), np.float32(3.4028234663852886e38), np.float32)
         I = np.full((n, 8), -1, np.int64)
