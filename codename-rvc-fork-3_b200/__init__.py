@@ -10,6 +10,7 @@ Host side only: every number is computed by librvcr.so (hand-written sm_100a CUD
 from ._ffi import RvcrError, device_count, lib  # noqa: F401
 from .faiss_compat import (METRIC_L2, IndexIVFFlat, extract_index_ivf, index_factory, read_index,  # noqa: F401
                            write_index)
+from . import sharded, synth  # noqa: F401
 from .retrieve import patch_pipeline, retrieve_speaker_embeddings  # noqa: F401
 
 __all__ = ["IndexIVFFlat", "read_index", "write_index", "index_factory", "extract_index_ivf", "METRIC_L2",

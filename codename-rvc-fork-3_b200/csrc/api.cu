@@ -6,6 +6,7 @@
 //   rvcr_index_create / _set_nprobe / _add / _write <- rvc/train/process/extract_index.py:59-71
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -288,6 +289,9 @@ void rvcr_index_free(rvcr_index* h) {
                           &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_stage};
         for (DevBuf* b : bufs) b->release();
         if (h->last_done) cudaEventDestroy(h->last_done);
+        if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+        if (h->out_stream) cudaStreamDestroy(h->out_stream);
+        for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);
         for (int i = 0; i < RVCR_NUM_PHASES; ++i)
             for (int k = 0; k < 2; ++k)
                 if (h->pev[i][k]) cudaEventDestroy(h->pev[i][k]);
@@ -503,13 +507,109 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     RVCR_ENTER(h);
     if (n > 0 && !feats_host) return RVCR_ERR_INVALID;
     if (n <= 0) return n < 0 ? RVCR_ERR_INVALID : RVCR_OK;
+    RVCR_TRY(check_searchable(h, RVCR_K));
+    // Host -> device copies are pipelined against the coarse quantizer: the queries go up in chunks on a
+    // copy stream while the tensor cores already assign the previous chunk (the coarse step is per-query
+    // independent).  The list scan needs the whole batch grouped by list, so it starts after the last
+    // chunk; the blended rows come back with one device -> host copy.
     cudaStream_t s = nullptr;
-    const size_t bytes = (size_t)n * h->d * sizeof(float);
-    RVCR_TRY(h->ws_q.reserve(bytes));
-    RVCR_CUDA(cudaMemcpyAsync(h->ws_q.p, feats_host, bytes, cudaMemcpyHostToDevice, s));
-    RVCR_TRY(search_device(h, h->ws_q.as<float>(), n, nullptr, true, index_rate, nullptr, nullptr, s));
-    RVCR_CUDA(cudaMemcpyAsync(feats_host, h->ws_q.p, bytes, cudaMemcpyDeviceToHost, s));
+    const size_t rowb = (size_t)h->d * sizeof(float);
+    RVCR_TRY(h->ws_q.reserve((size_t)n * rowb));
+    RVCR_TRY(h->ws_assign.reserve((size_t)n * 4));
+    RVCR_TRY(finalize_pending(h, s));
+    if (!h->copy_stream) RVCR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    const int64_t chunk = 131072;
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    while ((int64_t)h->copy_events.size() < nchunks) {
+        cudaEvent_t e;
+        RVCR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->copy_events.push_back(e);
+    }
+    RVCR_TRY(stream_enter(h, s));
+    for (int i = 0; i < RVCR_NUM_PHASES; ++i) h->pev_used[i] = false;
+    char* dq = reinterpret_cast<char*>(h->ws_q.p);
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t off = c * chunk, m = std::min(chunk, n - off);
+        RVCR_CUDA(cudaMemcpyAsync(dq + (size_t)off * rowb, reinterpret_cast<const char*>(feats_host) + (size_t)off * rowb,
+                                  (size_t)m * rowb, cudaMemcpyHostToDevice, h->copy_stream));
+        RVCR_CUDA(cudaEventRecord(h->copy_events[c], h->copy_stream));
+    }
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t off = c * chunk, m = std::min(chunk, n - off);
+        RVCR_CUDA(cudaStreamWaitEvent(s, h->copy_events[c], 0));
+        RVCR_TRY(coarse_dispatch(h, h->ws_q.as<float>() + (size_t)off * h->d, m, h->ws_assign.as<int32_t>() + off, nullptr, s));
+    }
+    // Device -> host: when the caller's buffer is pinned (device-mapped), the lists are scanned in waves of
+    // work items and each wave's blended rows are written by the blend kernel straight into the host buffer
+    // on a second stream, so the PCIe write-back of wave k overlaps the scan of wave k+1.
+    cudaPointerAttributes pat;
+    const bool mapped = cudaPointerGetAttributes(&pat, feats_host) == cudaSuccess && pat.type == cudaMemoryTypeHost &&
+                        pat.devicePointer != nullptr && h->opt.scan_impl == 4;
+    cudaGetLastError();
+    if (!mapped) {
+        RVCR_TRY(search_device(h, h->ws_q.as<float>(), n, h->ws_assign.as<int32_t>(), true, index_rate, nullptr, nullptr, s));
+        RVCR_CUDA(cudaMemcpyAsync(feats_host, h->ws_q.p, (size_t)n * rowb, cudaMemcpyDeviceToHost, s));
+        RVCR_CUDA(cudaStreamSynchronize(s));
+        return RVCR_OK;
+    }
+    if (!h->out_stream) RVCR_CUDA(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+    RVCR_TRY(group_queries(h, h->ws_assign.as<int32_t>(), n, false, s));
+    RVCR_TRY(h->ws_P.reserve((size_t)n * RVCR_K * 4));
+    RVCR_TRY(h->ws_D.reserve((size_t)n * RVCR_K * 4));
+    int nitems = 0;
+    RVCR_CUDA(cudaMemcpyAsync(&nitems, h->ws_misc.p, 4, cudaMemcpyDeviceToHost, s));
     RVCR_CUDA(cudaStreamSynchronize(s));
+    int waves = nitems / 512;
+    int max_waves = 16;
+    if (const char* e = getenv("RVCR_HOST_WAVES")) max_waves = atoi(e);   // tuning knob (1 = no overlap)
+    if (max_waves > 16) max_waves = 16;
+    if (waves > max_waves) waves = max_waves;
+    if (waves < 1) waves = 1;
+    while ((int)h->copy_events.size() < waves) {
+        cudaEvent_t e;
+        RVCR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->copy_events.push_back(e);
+    }
+    RVCR_CUDA(cudaMemsetAsync(h->ws_misc.as<int32_t>() + 32, 0, 4 * 16, s));   // per-wave tickets
+    float* out_dev = reinterpret_cast<float*>(pat.devicePointer);
+    const bool trace = getenv("RVCR_HOST_TRACE") != nullptr;
+    int blend_ctas = 128;  // enough CTAs to keep PCIe busy; more of them slow the concurrent scan (LSU back-pressure)
+    if (const char* e = getenv("RVCR_HOST_BLEND_CTAS")) blend_ctas = atoi(e);
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(2 + 3 * (size_t)waves);
+        for (auto& e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[0], s);
+    }
+    for (int k = 0; k < waves; ++k) {
+        const int ib = (int)((int64_t)nitems * k / waves), ie = (int)((int64_t)nitems * (k + 1) / waves);
+        RVCR_TRY(scan_topk_range(h, h->ws_q.as<float>(), n, h->ws_D.as<float>(), h->ws_P.as<int32_t>(), nullptr, ib, ie, 32 + k,
+                                 k == 0, s));
+        RVCR_CUDA(cudaEventRecord(h->copy_events[k], s));
+        if (trace) cudaEventRecord(tev[1 + 3 * k], s);
+        RVCR_CUDA(cudaStreamWaitEvent(h->out_stream, h->copy_events[k], 0));
+        if (trace) cudaEventRecord(tev[2 + 3 * k], h->out_stream);
+        RVCR_TRY(gather_blend_range(h, h->ws_q.as<float>(), n, h->ws_D.as<float>(), h->ws_P.as<int32_t>(), index_rate, ib, ie,
+                                    out_dev, blend_ctas, h->out_stream));
+        if (trace) cudaEventRecord(tev[3 + 3 * k], h->out_stream);
+    }
+    if (trace) {
+        cudaStreamSynchronize(h->out_stream);
+        cudaStreamSynchronize(s);
+        for (int k = 0; k < waves; ++k) {
+            float a, b, c;
+            cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * k]);
+            cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * k]);
+            cudaEventElapsedTime(&c, tev[0], tev[3 + 3 * k]);
+            fprintf(stderr, "[rvcr trace] wave %d: scan done %.2f ms, blend start %.2f, blend done %.2f\n", k, a, b, c);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
+    h->stats.calls_search += 1;
+    h->stats.queries += n;
+    RVCR_CUDA(cudaStreamSynchronize(h->out_stream));
+    RVCR_CUDA(cudaStreamSynchronize(s));
+    RVCR_TRY(stream_leave(h, s));
     return RVCR_OK;
 }
 
@@ -579,6 +679,9 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
         h->opt.coarse_mode = value;
     } else if (!strcmp(key, "profile")) {
         h->opt.profile = value ? 1 : 0;
+    } else if (!strcmp(key, "scan_impl")) {
+        if (value < 1 || value > 4) return RVCR_ERR_INVALID;
+        h->opt.scan_impl = value;
     } else if (!strcmp(key, "tc_cluster")) {
         if (value != 1 && value != 2) return RVCR_ERR_INVALID;
         h->opt.tc_cluster = value;
@@ -602,6 +705,7 @@ int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out) {
     else if (!strcmp(key, "nan_on_zero_score")) *value_out = h->opt.nan_on_zero_score;
     else if (!strcmp(key, "profile")) *value_out = h->opt.profile;
     else if (!strcmp(key, "tc_cluster")) *value_out = h->opt.tc_cluster;
+    else if (!strcmp(key, "scan_impl")) *value_out = h->opt.scan_impl;
     else if (!strcmp(key, "coarse_tc_available")) *value_out = coarse_tc_available() ? 1 : 0;
     else {
         set_error("unknown option '%s'", key);

@@ -20,15 +20,28 @@
 
 namespace rvcr {
 
+// Default: every query qi < n, in place.  With `qorder` the kernel instead walks the sorted positions of
+// work items [item_begin, item_end) (a contiguous range: items are ordered by sorted position) and writes
+// the blended row of query qorder[p] to out + qorder[p]*d -- `out` may be mapped pinned host memory, in
+// which case the rows go straight over PCIe while the next wave of lists is being scanned.
 __global__ void __launch_bounds__(256)
 gather_blend_kernel(float* __restrict__ feats, int64_t n, int d, const float* __restrict__ D,
                     const int32_t* __restrict__ P, const int32_t* __restrict__ assign, int64_t own_lo,
-                    int64_t own_hi, const float* __restrict__ vecs, int64_t last_row_pos, float r32, float omr32) {
+                    int64_t own_hi, const float* __restrict__ vecs, int64_t last_row_pos, float r32, float omr32,
+                    const int32_t* __restrict__ qorder, const int32_t* __restrict__ items,
+                    const int32_t* __restrict__ nitems_ptr, int item_begin, int item_end, float* __restrict__ out) {
     __shared__ float sw[RVCR_K];
     __shared__ int spos[RVCR_K];
     const int tid = threadIdx.x;
     const int nvec = d >> 2;
-    for (int64_t qi = blockIdx.x; qi < n; qi += gridDim.x) {
+    int64_t first = 0, last = n;
+    if (qorder) {
+        const int nit = *nitems_ptr;
+        first = item_begin < nit ? (int64_t)items[item_begin] : n;
+        last = item_end < nit ? (int64_t)items[item_end] : n;
+    }
+    for (int64_t it = first + blockIdx.x; it < last; it += gridDim.x) {
+        const int64_t qi = qorder ? (int64_t)qorder[it] : it;
         if (assign) {
             const int64_t a = (int64_t)assign[qi];  // block-uniform
             if (a >= 0 && (a < own_lo || a >= own_hi)) continue;  // another shard's query
@@ -58,7 +71,8 @@ gather_blend_kernel(float* __restrict__ feats, int64_t n, int d, const float* __
             wk[k] = sw[k];
             rows[k] = spos[k] >= 0 ? reinterpret_cast<const float4*>(vecs + (int64_t)spos[k] * d) : nullptr;
         }
-        float4* f4 = reinterpret_cast<float4*>(feats + qi * d);
+        const float4* f4 = reinterpret_cast<const float4*>(feats + qi * d);
+        float4* o4 = reinterpret_cast<float4*>((out ? out : feats) + qi * d);
         for (int c = tid; c < nvec; c += blockDim.x) {
             float4 v[RVCR_K];
 #pragma unroll
@@ -81,7 +95,7 @@ gather_blend_kernel(float* __restrict__ feats, int64_t n, int d, const float* __
             o.y = __fadd_rn(__fmul_rn(acc.y, r32), __fmul_rn(omr32, f.y));
             o.z = __fadd_rn(__fmul_rn(acc.z, r32), __fmul_rn(omr32, f.z));
             o.w = __fadd_rn(__fmul_rn(acc.w, r32), __fmul_rn(omr32, f.w));
-            f4[c] = o;
+            o4[c] = o;
         }
         __syncthreads();
     }
@@ -102,7 +116,27 @@ int gather_blend(rvcr_index* h, float* feats, int64_t n, const float* D, const i
     int64_t grid = (int64_t)h->num_sms * (2048 / threads);
     if (grid > n) grid = n;
     gather_blend_kernel<<<(unsigned)grid, threads, 0, s>>>(feats, n, h->d, D, P, assign, h->own_lo, h->own_hi, h->vecs,
-                                                            h->last_row_pos, r32, omr32);
+                                                            h->last_row_pos, r32, omr32, nullptr, nullptr, nullptr, 0, 0,
+                                                            nullptr);
+    RVCR_CHECK_LAUNCH();
+    count_launch(h);
+    return RVCR_OK;
+}
+
+// Blend the queries of work items [item_begin, item_end) (after their scan wave) into `out` rows.
+int gather_blend_range(rvcr_index* h, const float* feats, int64_t n, const float* D, const int32_t* P, double index_rate,
+                       int item_begin, int item_end, float* out, int max_ctas, cudaStream_t s) {
+    if (n <= 0) return RVCR_OK;
+    const float r32 = (float)index_rate;
+    const float omr32 = (float)(1.0 - index_rate);
+    int threads = ((h->d / 4 + 31) / 32) * 32;
+    if (threads > 256) threads = 256;
+    if (threads < 32) threads = 32;
+    int64_t grid = max_ctas > 0 ? max_ctas : (int64_t)h->num_sms * (2048 / threads);
+    gather_blend_kernel<<<(unsigned)grid, threads, 0, s>>>(const_cast<float*>(feats), n, h->d, D, P, nullptr, h->own_lo, h->own_hi,
+                                                            h->vecs, h->last_row_pos, r32, omr32, h->ws_vals2.as<int32_t>(),
+                                                            h->ws_items.as<int32_t>(), h->ws_misc.as<int32_t>(), item_begin,
+                                                            item_end, out);
     RVCR_CHECK_LAUNCH();
     count_launch(h);
     return RVCR_OK;

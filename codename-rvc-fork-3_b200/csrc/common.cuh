@@ -61,6 +61,7 @@ struct Options {
     int64_t coarse_mode = 0;  // 0 auto, 1 exact FFMA, 2 tcgen05 bf16, 3 tcgen05 3-way split
     int64_t nan_on_zero_score = 1;
     int64_t profile = 0;      // record CUDA events around each phase's kernels
+    int64_t scan_impl = 4;    // 1 scalar 8-lane, 2 packed f32x2 TQx4, 3 same with 16 warps, 4 packed TQx8 tile (default)
     int64_t tc_cluster = 2;   // tcgen05 path: 1 = one CTA per SM, 2 = CTA pairs (cta_group::2)
 };
 
@@ -107,6 +108,9 @@ struct rvcr_index {
     // per-call scratch
     rvcr::DevBuf ws_assign, ws_keys, ws_vals, ws_keys2, ws_vals2, ws_cub, ws_items, ws_flags, ws_misc,
         ws_D, ws_P, ws_I, ws_best, ws_q, ws_tc0, ws_tc1, ws_tc2, ws_tc3, ws_stage;
+    cudaStream_t copy_stream = nullptr;          // host-buffer entry points: H2D chunks overlap the coarse step
+    cudaStream_t out_stream = nullptr;           // ... and blended rows stream out while later lists are scanned
+    std::vector<cudaEvent_t> copy_events;
     cudaEvent_t last_done = nullptr;
     cudaStream_t last_stream = nullptr;
     bool have_last = false;
@@ -140,6 +144,10 @@ int coarse_tc_invalidate(rvcr_index* h);
 int group_queries(rvcr_index* h, const int32_t* assign, int64_t n, bool only_local, cudaStream_t s);
 int scan_topk(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, int64_t* I,
               cudaStream_t s);
+int scan_topk_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, int64_t* I, int item_begin, int item_end,
+                    int ticket_slot, bool fill, cudaStream_t s);
+int gather_blend_range(rvcr_index* h, const float* feats, int64_t n, const float* D, const int32_t* P, double index_rate,
+                       int item_begin, int item_end, float* out, int max_ctas, cudaStream_t s);
 // blend.cu
 int gather_blend(rvcr_index* h, float* feats, int64_t n, const float* D, const int32_t* P,
                  const int32_t* assign /*nullable: restrict to owned*/, double index_rate,

@@ -54,10 +54,14 @@ def test_golden_search_and_blend(rvcr, oracle, golden, tmp_path, name):
     got = out[0].cpu().numpy()
     assert_blend_close(got, g["out"])
     assert np.array_equal(got, g["out"], equal_nan=True)          # in fact bit-exact
-    # host-buffer variant (the e2e path of bench.py)
+    # host-buffer variant (the e2e path of bench.py): pageable buffer, then pinned buffer (rows are written
+    # straight into the mapped host buffer by the blend kernel, wave by wave)
     h = g["q"].copy()
     index.retrieve_blend_host_(h, float(g["index_rate"]))
     assert np.array_equal(h, g["out"], equal_nan=True)
+    hp = torch.from_numpy(g["q"].copy()).pin_memory()
+    index.retrieve_blend_host_(hp.numpy(), float(g["index_rate"]))
+    assert np.array_equal(hp.numpy(), g["out"], equal_nan=True)
     # the unfused, faiss-shaped call sequence the unmodified reference would run gives the same numbers
     with np.errstate(all="ignore"):
         ref = oracle.tail_numpy_verbatim(D, I, index.reconstruct_n(0, index.ntotal), float(g["index_rate"]), g["q"])
@@ -137,6 +141,14 @@ def test_config_parity_with_oracle(rvcr, oracle, tmp_path, cfg):
         got = f.cpu().numpy()
         assert_blend_close(got, want)
         assert np.array_equal(got, want, equal_nan=True)
+        hp = torch.from_numpy(q.copy()).pin_memory()                  # pinned host path: multi-wave write-back
+        index.retrieve_blend_host_(hp.numpy(), rate)
+        assert np.array_equal(hp.numpy(), want, equal_nan=True)
+    for impl in (1, 2, 3):                                            # older scan kernels stay bit-identical
+        index.set_option("scan_impl", impl)
+        Dk, Ik = index.search(q, k=8)
+        assert np.array_equal(Ik, Io) and np.array_equal(Dk, Do)
+    index.set_option("scan_impl", 4)
 
 
 def test_coarse_splits_and_ties(rvcr, oracle):

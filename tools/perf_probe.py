@@ -21,6 +21,7 @@ ap.add_argument("--nlist", type=int, default=22_627)
 ap.add_argument("--mode", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--cluster", type=int, default=2)
+ap.add_argument("--scan", type=int, default=3)
 ap.add_argument("--addmode", type=int, default=2)
 a = ap.parse_args()
 
@@ -35,6 +36,7 @@ index = rvcr.index_factory(a.d, f"IVF{a.nlist},Flat")
 index.set_centroids(cent.cpu().numpy())
 index.set_option("coarse_mode", a.addmode)
 index.set_option("tc_cluster", a.cluster)
+index.set_option("scan_impl", a.scan)
 index.set_option("profile", 1)
 torch.cuda.synchronize()
 t0 = time.time()
