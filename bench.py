@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--workload", default="C5", choices=["C1", "C2", "C3", "C5"])
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--coarse-mode", type=int, default=0)
-    ap.add_argument("--scan-impl", type=int, default=4)
+    ap.add_argument("--scan-impl", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -311,7 +311,8 @@ def main():
     if "scan" in phase_acc:
         gb = scan_bytes / (phase_acc["scan"] * 1e-3) / 1e9
         roof["scan"] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / pk["hbm_gbs"],
-                        "traffic": None, "kernel": f"scan_topk_kernel_v{args.scan_impl}", "ms": phase_acc["scan"], "bytes_per_launch": scan_bytes,
+                        "traffic": None, "kernel": "scan_tc_kernel (tcgen05 tf32 + TMA) + scan_recheck_kernel (exact fp32)" if args.scan_impl == 5
+                        else f"scan_topk_kernel_v{args.scan_impl}", "ms": phase_acc["scan"], "bytes_per_launch": scan_bytes,
                         "peak_source": pk["source"]}
     if "blend" in phase_acc:
         gb = blend_bytes / (phase_acc["blend"] * 1e-3) / 1e9

@@ -32,7 +32,8 @@ class Info(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("calls_search", C.c_int64), ("queries", C.c_int64), ("kernels_launched", C.c_int64),
                 ("coarse_tc_queries", C.c_int64), ("coarse_candidates", C.c_int64),
-                ("coarse_fallback", C.c_int64), ("scan_items", C.c_int64), ("reserved", C.c_int64 * 8)]
+                ("coarse_fallback", C.c_int64), ("scan_items", C.c_int64), ("scan_tc_candidates", C.c_int64),
+                ("scan_tc_fallback", C.c_int64), ("reserved", C.c_int64 * 6)]
 
 
 _H = C.c_void_p          # rvcr_index*

@@ -286,7 +286,8 @@ void rvcr_index_free(rvcr_index* h) {
         if (h->stage_assign) cudaFree(h->stage_assign);
         DevBuf* bufs[] = {&h->ws_assign, &h->ws_keys, &h->ws_vals, &h->ws_keys2, &h->ws_vals2, &h->ws_cub, &h->ws_items,
                           &h->ws_flags, &h->ws_misc, &h->ws_D, &h->ws_P, &h->ws_I, &h->ws_best, &h->ws_q, &h->ws_tc0,
-                          &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_stage};
+                          &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_stage, &h->row_norm, &h->ws_cand, &h->ws_candcnt,
+                          &h->ws_fb};
         for (DevBuf* b : bufs) b->release();
         if (h->last_done) cudaEventDestroy(h->last_done);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -438,6 +439,7 @@ int rvcr_index_alloc_lists(rvcr_index* h, const int64_t* sizes_host, int64_t nto
     h->nstored = nst;
     h->ntotal = ntotal;
     h->last_row_pos = -1;
+    scan_tc_invalidate(h);
     return RVCR_OK;
 }
 
@@ -544,7 +546,7 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     // on a second stream, so the PCIe write-back of wave k overlaps the scan of wave k+1.
     cudaPointerAttributes pat;
     const bool mapped = cudaPointerGetAttributes(&pat, feats_host) == cudaSuccess && pat.type == cudaMemoryTypeHost &&
-                        pat.devicePointer != nullptr && h->opt.scan_impl == 4;
+                        pat.devicePointer != nullptr && (h->opt.scan_impl == 4 || h->opt.scan_impl == 5);
     cudaGetLastError();
     if (!mapped) {
         RVCR_TRY(search_device(h, h->ws_q.as<float>(), n, h->ws_assign.as<int32_t>(), true, index_rate, nullptr, nullptr, s));
@@ -680,7 +682,7 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "profile")) {
         h->opt.profile = value ? 1 : 0;
     } else if (!strcmp(key, "scan_impl")) {
-        if (value < 1 || value > 4) return RVCR_ERR_INVALID;
+        if (value < 1 || value > 5) return RVCR_ERR_INVALID;
         h->opt.scan_impl = value;
     } else if (!strcmp(key, "tc_cluster")) {
         if (value != 1 && value != 2) return RVCR_ERR_INVALID;
@@ -737,6 +739,14 @@ int rvcr_get_stats(rvcr_index* h, rvcr_stats* out) {
         h->stats.coarse_fallback = (int64_t)tot[0];
         h->stats.coarse_candidates = (int64_t)tot[1];
         h->tc_counters_dirty = false;
+    }
+    if (h->scan_fb_dirty) {
+        unsigned long long tot[2] = {0, 0};
+        RVCR_CUDA(cudaDeviceSynchronize());
+        RVCR_CUDA(cudaMemcpy(tot, h->ws_misc.as<int32_t>() + 48, sizeof(tot), cudaMemcpyDeviceToHost));
+        h->stats.scan_tc_fallback = (int64_t)tot[0];
+        h->stats.scan_tc_candidates = (int64_t)tot[1];
+        h->scan_fb_dirty = false;
     }
     *out = h->stats;
     return RVCR_OK;

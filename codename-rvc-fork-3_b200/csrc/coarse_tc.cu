@@ -31,7 +31,7 @@
 #include <math.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace rvcr {
 
@@ -44,168 +44,6 @@ constexpr int UMMA_K = 16;
 constexpr int TOPT = 8;        // approximate nearest centroids kept per (query, split)
 constexpr int THREADS = 256;
 constexpr int EPI_WARP0 = 4;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
-// ---- mbarrier ------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a mis-programmed pipeline traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
-        if (it > (1u << 24)) __trap();
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(
-            smem_u32(bar)),
-        "r"(cta)
-        : "memory");
-}
-
-// ---- TMA -----------------------------------------------------------------------------------
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
-}
-template <int CLUSTER>
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int crd0, int crd1) {
-    if constexpr (CLUSTER == 1) {
-        asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                smem_u32(dst)),
-            "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1)
-            : "memory");
-    } else {
-        // both CTAs of the pair issue this; clearing the peer bit routes complete_tx to the
-        // leader CTA's barrier
-        asm volatile(
-            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                smem_u32(dst)),
-            "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(crd0), "r"(crd1)
-            : "memory");
-    }
-}
-
-// ---- tcgen05 -------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <int CLUSTER>
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    if constexpr (CLUSTER == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    } else {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-}
-template <int CLUSTER>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    if constexpr (CLUSTER == 1)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-    else
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
-template <int CLUSTER>
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (CLUSTER == 1) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(
-                tmem_d),
-            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(
-                tmem_d),
-            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-            : "memory");
-    }
-}
-// all previously issued MMAs of this thread arrive on `bar` when they complete
-template <int CLUSTER>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    if constexpr (CLUSTER == 1) {
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-    } else {
-        const uint16_t mask = 3;  // both CTAs of the pair
-        asm volatile(
-            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                smem_u32(bar)),
-            "h"(mask)
-            : "memory");
-    }
-}
-
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);       // start address, 16-byte units
-    d |= (uint64_t)0 << 16;                        // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
-    return d;
-}
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    return (1u << 4)                    // D format: fp32
-           | (1u << 7)                  // A format: bf16
-           | (1u << 10)                 // B format: bf16
-           | ((uint32_t)(N >> 3) << 17) // N / 8
-           | ((uint32_t)(M >> 4) << 24);// M / 16    (A, B K-major; no negate; dense)
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // sorted (ascending) top-T insertion, fully unrolled, registers only
 __device__ __forceinline__ void top_insert(float (&tv)[TOPT], int (&tj)[TOPT], float x, int j) {
@@ -559,12 +397,7 @@ __global__ void tc_recheck_kernel(const float* __restrict__ q, int64_t n, int d,
 
 // ------------------------------------------------------------------------------ host side ----
 
-namespace {
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
+namespace tc {
 EncodeTiledFn get_encode_fn() {
     static EncodeTiledFn fn = nullptr;
     static bool tried = false;
@@ -578,10 +411,14 @@ EncodeTiledFn get_encode_fn() {
     }
     return fn;
 }
+}  // namespace tc
+
+
+namespace {
 
 // row-major bf16 matrix [rows][kdim] -> tensor map with a [box_rows][64] box, 128B swizzle
 int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int kdim, int box_rows) {
-    EncodeTiledFn fn = get_encode_fn();
+    tc::EncodeTiledFn fn = tc::get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
         return RVCR_ERR_CUDA;

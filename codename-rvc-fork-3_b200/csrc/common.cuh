@@ -61,7 +61,8 @@ struct Options {
     int64_t coarse_mode = 0;  // 0 auto, 1 exact FFMA, 2 tcgen05 bf16, 3 tcgen05 3-way split
     int64_t nan_on_zero_score = 1;
     int64_t profile = 0;      // record CUDA events around each phase's kernels
-    int64_t scan_impl = 4;    // 1 scalar 8-lane, 2 packed f32x2 TQx4, 3 same with 16 warps, 4 packed TQx8 tile (default)
+    int64_t scan_impl = 5;    // 5 tcgen05 tf32 + exact re-check (default); exact FFMA scans: 1 scalar 8-lane, 2 packed f32x2
+                              // TQx4, 3 same with 16 warps, 4 packed TQx8 tile
     int64_t tc_cluster = 2;   // tcgen05 path: 1 = one CTA per SM, 2 = CTA pairs (cta_group::2)
 };
 
@@ -106,6 +107,16 @@ struct rvcr_index {
     int64_t npending = 0;
 
     // per-call scratch
+    // tensor-core scan (scan_tc.cu): ||y||^2 per stored row, TMA descriptors of the list storage, candidate lists
+    rvcr::DevBuf row_norm, ws_cand, ws_candcnt, ws_fb;
+    bool row_norm_valid = false;
+    float row_norm_max = 0.f;
+    alignas(64) unsigned char scan_tmaps[4][128];
+    bool scan_tmap_valid = false;
+    const void* scan_tmap_base = nullptr;
+    int64_t scan_tmap_rows = -1;
+    bool scan_fb_dirty = false;
+
     rvcr::DevBuf ws_assign, ws_keys, ws_vals, ws_keys2, ws_vals2, ws_cub, ws_items, ws_flags, ws_misc,
         ws_D, ws_P, ws_I, ws_best, ws_q, ws_tc0, ws_tc1, ws_tc2, ws_tc3, ws_stage;
     cudaStream_t copy_stream = nullptr;          // host-buffer entry points: H2D chunks overlap the coarse step
@@ -146,6 +157,12 @@ int scan_topk(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, in
               cudaStream_t s);
 int scan_topk_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, int64_t* I, int item_begin, int item_end,
                     int ticket_slot, bool fill, cudaStream_t s);
+int fill_pad(float* D, int32_t* P, int64_t* I, int64_t nk, cudaStream_t s);
+// scan_tc.cu : tcgen05 tf32 list scan + exact re-check
+bool scan_tc_supported(const rvcr_index* h);
+int scan_tc_invalidate(rvcr_index* h);
+int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, int64_t* I, int item_begin, int item_end,
+                  int ticket_slot, bool fill, cudaStream_t s);
 int gather_blend_range(rvcr_index* h, const float* feats, int64_t n, const float* D, const int32_t* P, double index_rate,
                        int item_begin, int item_end, float* out, int max_ctas, cudaStream_t s);
 // blend.cu
@@ -213,6 +230,33 @@ __device__ __forceinline__ float reduce8_canonical(float a) {
     a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 1));
     a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 2));
     return a;
+}
+
+// warp-level insertion of the candidates (cd, cpos) of the 32 lanes into the sorted top-8 held in
+// lanes 0..7 (td, tp); same code as v1's inner loop
+__device__ __forceinline__ void top8_update(float& td, int& tp, float cd, int cpos, bool valid, int lane) {
+    const float thr_d = __shfl_sync(0xffffffffu, td, 7);
+    const int thr_p = __shfl_sync(0xffffffffu, tp, 7);
+    unsigned m = __ballot_sync(0xffffffffu, valid && cand_less(cd, cpos, thr_d, thr_p));
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const float xd = __shfl_sync(0xffffffffu, cd, src);
+        const int xp = __shfl_sync(0xffffffffu, cpos, src);
+        const bool lt = cand_less(td, tp, xd, xp);
+        const int rank = __popc(__ballot_sync(0xffffffffu, lt) & 0xffu);
+        const float ud = __shfl_up_sync(0xffffffffu, td, 1);
+        const int up = __shfl_up_sync(0xffffffffu, tp, 1);
+        if (lane < 8) {
+            if (lane == rank) {
+                td = xd;
+                tp = xp;
+            } else if (lane > rank) {
+                td = ud;
+                tp = up;
+            }
+        }
+    }
 }
 
 }  // namespace rvcr

@@ -131,6 +131,7 @@ static int ceil_log2(uint64_t v) {
 
 int refresh_derived(rvcr_index* h, cudaStream_t s) {
     h->last_row_pos = -1;
+    scan_tc_invalidate(h);
     if (h->nstored > 0 && h->ntotal > 0) {
         RVCR_TRY(h->ws_misc.reserve(64));
         long long* dpos = h->ws_misc.as<long long>() + 4;

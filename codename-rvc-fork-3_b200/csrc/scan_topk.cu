@@ -253,33 +253,6 @@ __device__ __forceinline__ void s2_load_stage(float* sStage, const float* __rest
     }
 }
 
-// warp-level insertion of the candidates (cd, cpos) of the 32 lanes into the sorted top-8 held in
-// lanes 0..7 (td, tp); same code as v1's inner loop
-__device__ __forceinline__ void top8_update(float& td, int& tp, float cd, int cpos, bool valid, int lane) {
-    const float thr_d = __shfl_sync(0xffffffffu, td, 7);
-    const int thr_p = __shfl_sync(0xffffffffu, tp, 7);
-    unsigned m = __ballot_sync(0xffffffffu, valid && cand_less(cd, cpos, thr_d, thr_p));
-    while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const float xd = __shfl_sync(0xffffffffu, cd, src);
-        const int xp = __shfl_sync(0xffffffffu, cpos, src);
-        const bool lt = cand_less(td, tp, xd, xp);
-        const int rank = __popc(__ballot_sync(0xffffffffu, lt) & 0xffu);
-        const float ud = __shfl_up_sync(0xffffffffu, td, 1);
-        const int up = __shfl_up_sync(0xffffffffu, tp, 1);
-        if (lane < 8) {
-            if (lane == rank) {
-                td = xd;
-                tp = xp;
-            } else if (lane > rank) {
-                td = ud;
-                tp = up;
-            }
-        }
-    }
-}
-
 template <int TQ>
 __device__ __forceinline__ void s2_run_item(const float* __restrict__ q, const int32_t* __restrict__ qorder, int64_t p0,
                                             int cnt, const float* __restrict__ lbase, int64_t lb, int64_t len, int d,
@@ -866,6 +839,13 @@ __global__ void fill_pad_kernel(float* __restrict__ D, int32_t* __restrict__ P, 
 
 // ----------------------------------------------------------------------------- host side ----
 
+int fill_pad(float* D, int32_t* P, int64_t* I, int64_t nk, cudaStream_t s) {
+    if (nk <= 0) return RVCR_OK;
+    fill_pad_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, s>>>(D, P, I, nk);
+    RVCR_CHECK_LAUNCH();
+    return RVCR_OK;
+}
+
 static int ceil_log2(uint64_t v) {
     int b = 0;
     while ((1ull << b) < v) ++b;
@@ -936,6 +916,8 @@ int scan_topk(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, in
 // dynamic-scheduling ticket (slot 1 is zeroed by group_queries; slots 32.. by the caller).
 int scan_topk_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, int64_t* I, int item_begin, int item_end,
                     int ticket_slot, bool fill, cudaStream_t s) {
+    if ((h->opt.scan_impl == 5 || h->opt.scan_impl == 0) && scan_tc_supported(h))
+        return scan_tc_range(h, q, n, D, P, I, item_begin, item_end, ticket_slot, fill, s);
     if (h->d % PD_KC != 0) {
         set_error("d=%d unsupported (must be a multiple of %d)", h->d, PD_KC);
         return RVCR_ERR_UNSUPPORTED;
@@ -967,7 +949,7 @@ int scan_topk_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t*
         fill_pad_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, s>>>(D, P, I, nk);
         RVCR_CHECK_LAUNCH();
     }
-    if ((item_begin != 0 || item_end != 0x7fffffff) && h->opt.scan_impl != 4 && h->opt.scan_impl != 0) {
+    if ((item_begin != 0 || item_end != 0x7fffffff) && h->opt.scan_impl != 4 && h->opt.scan_impl != 5 && h->opt.scan_impl != 0) {
         set_error("work-item ranges need scan_impl 4");
         return RVCR_ERR_UNSUPPORTED;
     }

@@ -77,7 +77,9 @@ typedef struct rvcr_stats {
     int64_t coarse_candidates;  /* candidates exactly re-checked after the tcgen05 path           */
     int64_t coarse_fallback;    /* queries re-done by the exact FFMA kernel (margin overflow)     */
     int64_t scan_items;         /* (list, query-block) work items of the last scan               */
-    int64_t reserved[8];
+    int64_t scan_tc_candidates; /* rows exactly re-checked after the tcgen05 tf32 list scan       */
+    int64_t scan_tc_fallback;   /* queries re-done by the brute-force exact scan (margin overflow) */
+    int64_t reserved[6];
 } rvcr_stats;
 
 RVCR_API const char* rvcr_last_error(void);

@@ -144,11 +144,12 @@ def test_config_parity_with_oracle(rvcr, oracle, tmp_path, cfg):
         hp = torch.from_numpy(q.copy()).pin_memory()                  # pinned host path: multi-wave write-back
         index.retrieve_blend_host_(hp.numpy(), rate)
         assert np.array_equal(hp.numpy(), want, equal_nan=True)
-    for impl in (1, 2, 3):                                            # older scan kernels stay bit-identical
+    assert index.get_option("scan_impl") == 5                         # default: tcgen05 tf32 scan + exact re-check
+    for impl in (1, 2, 3, 4):                                         # the exact FFMA scan kernels stay bit-identical
         index.set_option("scan_impl", impl)
         Dk, Ik = index.search(q, k=8)
         assert np.array_equal(Ik, Io) and np.array_equal(Dk, Do)
-    index.set_option("scan_impl", 4)
+    index.set_option("scan_impl", 5)
 
 
 def test_coarse_splits_and_ties(rvcr, oracle):

@@ -21,7 +21,7 @@ ap.add_argument("--nlist", type=int, default=22_627)
 ap.add_argument("--mode", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--cluster", type=int, default=2)
-ap.add_argument("--scan", type=int, default=3)
+ap.add_argument("--scan", type=int, default=5)
 ap.add_argument("--addmode", type=int, default=2)
 a = ap.parse_args()
 
