@@ -405,6 +405,8 @@ def main():
                 "clocks": clocks,
                 "coarse_stats": {"tc_queries": st["coarse_tc_queries"], "rechecked_candidates": st["coarse_candidates"],
                                  "exact_fallback_queries": st["coarse_fallback"]},
+                "scan_stats": {"tc_candidates_rechecked": st.get("scan_tc_candidates", 0), "exact_fallback_queries": st.get("scan_tc_fallback", 0),
+                               "queries": st["queries"]},
                 "sanity": {"finite_first_rows": bool(np.isfinite(result_check).all())}}
         print(json.dumps(line), flush=True)
     if world > 1:

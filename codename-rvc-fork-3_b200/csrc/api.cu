@@ -287,7 +287,7 @@ void rvcr_index_free(rvcr_index* h) {
         DevBuf* bufs[] = {&h->ws_assign, &h->ws_keys, &h->ws_vals, &h->ws_keys2, &h->ws_vals2, &h->ws_cub, &h->ws_items,
                           &h->ws_flags, &h->ws_misc, &h->ws_D, &h->ws_P, &h->ws_I, &h->ws_best, &h->ws_q, &h->ws_tc0,
                           &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_stage, &h->row_norm, &h->ws_cand, &h->ws_candcnt,
-                          &h->ws_fb};
+                          &h->ws_fb, &h->ws_cstage};
         for (DevBuf* b : bufs) b->release();
         if (h->last_done) cudaEventDestroy(h->last_done);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);

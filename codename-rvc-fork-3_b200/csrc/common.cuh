@@ -108,7 +108,7 @@ struct rvcr_index {
 
     // per-call scratch
     // tensor-core scan (scan_tc.cu): ||y||^2 per stored row, TMA descriptors of the list storage, candidate lists
-    rvcr::DevBuf row_norm, ws_cand, ws_candcnt, ws_fb;
+    rvcr::DevBuf row_norm, ws_cand, ws_candcnt, ws_fb, ws_cstage;
     bool row_norm_valid = false;
     float row_norm_max = 0.f;
     alignas(64) unsigned char scan_tmaps[4][128];

@@ -12,16 +12,20 @@
 //   tcgen05  kind::tf32 MMA  acc[row, query] = <y_row, q>  (A = the staged rows, B = the item's <= 16 queries,
 //            both read from shared memory as K-major fp32; the tensor core uses the top 19 bits of each
 //            operand), fp32 accumulation in TMEM
-//   epilogue v = ||y||^2 - 2 acc  (||y||^2 precomputed per stored row), per query a sorted list of the 32
-//            smallest v per TMEM lane quarter, kept in registers across the warp
-//   merge    per query: v8 = 8th smallest v overall; every row with v <= v8 + margin(q) is a candidate
+//   epilogue v = ||y||^2 - 2 acc  (||y||^2 precomputed per stored row) -> shared memory, [query][row] per chunk
+//            of 512 rows
+//   select   per query: U = 8th smallest of the 32 lane minima (an upper bound of the 8th smallest v, and
+//            within a row or two of it); every row with v <= U + margin(q) is a candidate (ballot-compacted)
 //   recheck  canonical fp32 distance (fvec_L2sqr order, pairdist.cuh) of each candidate, top-8 by
 //            (distance, position): bit-identical to the exact scan
 //
 // margin(q) bounds twice the worst-case |v - v_true| (tf32 truncation of both operands, Cauchy-Schwarz;
 // fp32 accumulation of d products; norm roundings), so the true top-8 are always among the candidates
-// (DESIGN.md "Numerics").  If a quarter's 32-entry list might have been truncated inside the margin, or more
-// than 64 rows qualify, the query is re-done by the brute-force exact kernel below.
+// (DESIGN.md "Numerics").  If more than 64 rows qualify, the query is re-done by the brute-force exact
+// kernel below.
+#include <stddef.h>
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace rvcr {
@@ -35,14 +39,22 @@ constexpr int UMMA_K = 8;                   // tf32: 32 B per MMA
 constexpr int STAGE_BYTES = TILE_M * 128;   // 16 KB
 constexpr int QKB_BYTES = QT * 128;         // 2 KB: one k-block of the query operand
 constexpr int NACC = 4;                     // TMEM accumulator stages (QT columns each)
-constexpr int TMEM_COLS = 64;
+constexpr int A_COL0 = NACC * QT;           // TMEM columns [64, 512): ring of split row blocks (the MMA A operands),
+constexpr int NTS = 7;                      //   7 stages x (32 columns hi | 32 columns lo)
+constexpr int A_STAGE_COLS = 2 * KB;
+constexpr int TMEM_COLS = 512;
 constexpr int IRING = 4;                    // work-item descriptor ring
-constexpr int THREADS = 256;                // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 item scheduler, 4-7 epilogue
+constexpr int THREADS = 512;                // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 item scheduler, 4-7 epilogue, 8-15 row splitters
+constexpr int CONV_GROUPS = 2;              // two groups of 4 splitter warps take alternate stages (two stages in flight)
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 128;
-constexpr int TOPT = 32;                    // approximate candidates kept per (query, lane quarter)
+constexpr int CONV_WARP0 = 8;
+constexpr int CONV_THREADS = 128;
 constexpr int CCAP = 64;                    // candidates handed to the re-check per query
-constexpr int MERGE_BYTES = 4 * QT * TOPT * 8;
+constexpr int SCAP = 256;                   // (v, position) pairs staged per query while a multi-chunk list streams
+constexpr int CHUNK_TILES = 4;              // the epilogue selects candidates per chunk of 4 tiles = 512 list rows
+constexpr int CHUNK_ROWS = CHUNK_TILES * TILE_M;
+constexpr int SV_BYTES = QT * CHUNK_ROWS * 4;   // v of one chunk: [16 queries][512 rows] fp32 = 32 KB
 
 struct Item {
     int idx;   // ticket; >= nitems: stop
@@ -51,13 +63,28 @@ struct Item {
 };
 
 struct Smem {
-    uint64_t full[8], empty[8];
+    uint64_t full[8], empty[8];            // shared-memory row ring: TMA -> splitters -> TMA
+    uint64_t conv[NTS], aempty[NTS];       // TMEM operand ring: splitters -> MMA -> splitters
     uint64_t tfull[NACC], tempty[NACC];
     uint64_t ifull[IRING], iempty[IRING];
     uint64_t qfull[2];
     Item items[IRING];
+    float2 qnorm[2][QT];      // (||q||^2, ||q - tf32(q)||^2) of the queries staged in sQ[buf]
     uint32_t tmem_ptr;
 };
+
+// Warp-collective barrier wait: one lane polls (32x less shared-memory polling traffic), then every lane
+// performs its own (immediately successful) wait so that each thread has acquire semantics of its own.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+    if (lane == 0) tc::mbar_wait(bar, parity);
+    __syncwarp();
+    tc::mbar_wait(bar, parity);
+}
+// Warp-collective arrive (barrier counts are per warp): all lanes' prior writes are ordered before lane 0's arrive.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive_local(bar);
+}
 
 __device__ __forceinline__ void fetch_item(Item* out, int32_t* ticket, int item_begin, int nitems,
                                            const int32_t* __restrict__ items, const uint32_t* __restrict__ keys,
@@ -84,62 +111,43 @@ __device__ __forceinline__ void fetch_item(Item* out, int32_t* ticket, int item_
     *out = it;
 }
 
-// insert the warp's 32 values (v, pos) into the sorted (ascending across lanes) list (td, tp)
-__device__ __forceinline__ void top32_insert(float& td, int& tp, float v, int pos, int lane) {
-    const float thr = __shfl_sync(0xffffffffu, td, 31);
-    unsigned m = __ballot_sync(0xffffffffu, v < thr);
-    while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const float x = __shfl_sync(0xffffffffu, v, src);
-        const int xp = __shfl_sync(0xffffffffu, pos, src);
-        const int rank = __popc(__ballot_sync(0xffffffffu, td <= x));
-        const float ud = __shfl_up_sync(0xffffffffu, td, 1);
-        const int up = __shfl_up_sync(0xffffffffu, tp, 1);
-        if (lane == rank) {
-            td = x;
-            tp = xp;
-        } else if (lane > rank) {
-            td = ud;
-            tp = up;
-        }
-    }
-}
-
-// bitonic sort of one value per lane, ascending across lanes (first fill of an empty list)
-__device__ __forceinline__ void warp_sort32(float& v, int& p, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, v, j);
-            const int op = __shfl_xor_sync(0xffffffffu, p, j);
-            const bool up = ((lane & k) == 0);          // ascending block
-            const bool lower = ((lane & j) == 0);       // this lane keeps the smaller of the pair when ascending
-            const bool take_min = (up == lower);
-            const bool other_smaller = (ov < v) || (ov == v && op < p);
-            if (take_min ? other_smaller : !other_smaller) {
-                v = ov;
-                p = op;
-            }
-        }
-    }
-}
-
-// queries of an item -> K-major, 128B-swizzled tf32 operand tile [kb][16 rows][32 floats]; rows >= cnt
+// queries of an item -> K-major, 128B-swizzled operand tile [kb][16 rows][32 floats]; 8 threads per query, thread
+// (j, c) copies 16-byte chunk c of every k-block of query j (a 128 B contiguous read per 8 threads); rows >= cnt
 // replicate the last query (finite values; their accumulator columns are never read)
 __device__ __forceinline__ void load_queries(uint8_t* sQ, const float* __restrict__ q, const int32_t* __restrict__ qorder,
                                              const Item& it, int d, int nkb, int et) {
-    const int per_row = nkb * 8;                 // 16-byte chunks per query row
-    const int total = QT * per_row;
-    for (int c = et; c < total; c += EPI_THREADS) {
-        const int j = c / per_row, rem = c - j * per_row;
-        const int kb = rem >> 3, c16 = rem & 7;
-        const int jj = j < it.cnt ? j : it.cnt - 1;
-        const float* src = q + (int64_t)qorder[it.p0 + jj] * d + kb * KB + c16 * 4;
-        uint8_t* dst = sQ + kb * QKB_BYTES + (j >> 3) * 1024 + (j & 7) * 128 + ((c16 ^ (j & 7)) << 4);
-        cp_async16(dst, src);
+    const int j = et >> 3, c16 = et & 7;
+    const int jj = j < it.cnt ? j : it.cnt - 1;
+    const float* src = q + (int64_t)qorder[it.p0 + jj] * d + c16 * 4;
+    uint8_t* dst = sQ + (j >> 3) * 1024 + (j & 7) * 128 + ((c16 ^ (j & 7)) << 4);
+    for (int kb = 0; kb < nkb; ++kb) cp_async16(dst + kb * QKB_BYTES, src + kb * KB);
+}
+
+// After the copies landed: round the staged queries to tf32 in place (round to nearest, so the tensor core reads
+// them exactly) and record ||q||^2 and ||q - tf32(q)||^2 -- the part of <q, y> the MMA cannot see, bounded in the
+// margin by Cauchy-Schwarz with its exact norm.
+__device__ __forceinline__ void convert_queries(uint8_t* sQ, float2* qnorm, int nkb, int et) {
+    const int j = et >> 3, c16 = et & 7;
+    uint8_t* p = sQ + (j >> 3) * 1024 + (j & 7) * 128 + ((c16 ^ (j & 7)) << 4);
+    float n2 = 0.f, l2 = 0.f;
+    for (int kb = 0; kb < nkb; ++kb) {
+        float4 f = *reinterpret_cast<float4*>(p + kb * QKB_BYTES);
+        float4 h;
+        h.x = tc::to_tf32_rna(f.x);
+        h.y = tc::to_tf32_rna(f.y);
+        h.z = tc::to_tf32_rna(f.z);
+        h.w = tc::to_tf32_rna(f.w);
+        *reinterpret_cast<float4*>(p + kb * QKB_BYTES) = h;
+        n2 = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, n2))));
+        const float e0 = f.x - h.x, e1 = f.y - h.y, e2 = f.z - h.z, e3 = f.w - h.w;   // exact
+        l2 = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, l2))));
     }
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+        n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+        l2 += __shfl_xor_sync(0xffffffffu, l2, off);
+    }
+    if (c16 == 0) qnorm[j] = make_float2(n2, l2);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -148,18 +156,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                const float* __restrict__ q, const int32_t* __restrict__ qorder, const uint32_t* __restrict__ keys,
                const int32_t* __restrict__ items, const int32_t* __restrict__ nitems_ptr, int32_t* __restrict__ ticket,
                const int64_t* __restrict__ offsets, const float* __restrict__ ynorm, uint32_t nlist, int64_t n, int d,
-               int nstage, float ymax, float rel_margin, float abs_margin, int item_begin, int item_end,
+               int nstage, float ymax, float acc_rel, float abs_margin, int item_begin, int item_end,
                int32_t* __restrict__ cand, int32_t* __restrict__ candcnt, int32_t* __restrict__ fb_list,
-               int32_t* __restrict__ fb_count, unsigned long long* __restrict__ totals /*[0] fallbacks, [1] candidates*/) {
+               int32_t* __restrict__ fb_count, unsigned long long* __restrict__ totals /*[0] fallbacks, [1] candidates*/,
+               float2* __restrict__ stage_buf /*[grid][16][SCAP]*/, int dbg_flags) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nkb = d / KB;
     uint8_t* sR = smem;                                         // nstage x 16 KB
     uint8_t* sQ = sR + (size_t)nstage * STAGE_BYTES;            // 2 x nkb x 2 KB
     const int qbuf_bytes = nkb * QKB_BYTES;
-    float* sMv = reinterpret_cast<float*>(sQ + 2 * (size_t)qbuf_bytes);   // [4][16][32]
-    int* sMp = reinterpret_cast<int*>(sMv + 4 * QT * TOPT);               // [4][16][32]
-    Smem* S = reinterpret_cast<Smem*>(reinterpret_cast<uint8_t*>(sMp) + 4 * QT * TOPT * 4);
+    float* sV = reinterpret_cast<float*>(sQ + 2 * (size_t)qbuf_bytes);    // [16][CHUNK_ROWS]
+    Smem* S = reinterpret_cast<Smem*>(reinterpret_cast<uint8_t*>(sV) + SV_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nitems = min(*nitems_ptr, item_end);
@@ -173,18 +181,22 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < nstage; ++i) {
             tc::mbar_init(&S->full[i], 1);
-            tc::mbar_init(&S->empty[i], 1);
+            tc::mbar_init(&S->empty[i], CONV_THREADS / 32);
+        }
+        for (int i = 0; i < NTS; ++i) {
+            tc::mbar_init(&S->conv[i], CONV_THREADS / 32);
+            tc::mbar_init(&S->aempty[i], 1);
         }
         for (int i = 0; i < NACC; ++i) {
             tc::mbar_init(&S->tfull[i], 1);
-            tc::mbar_init(&S->tempty[i], EPI_THREADS);
+            tc::mbar_init(&S->tempty[i], EPI_THREADS / 32);
         }
         for (int i = 0; i < IRING; ++i) {
             tc::mbar_init(&S->ifull[i], 1);
-            tc::mbar_init(&S->iempty[i], 2 + 4);     // TMA thread + MMA thread + one lane per epilogue warp
+            tc::mbar_init(&S->iempty[i], 2 + 4 + 4 * CONV_GROUPS); // TMA thread + MMA thread + one lane per epilogue / splitter warp
         }
-        tc::mbar_init(&S->qfull[0], EPI_THREADS);
-        tc::mbar_init(&S->qfull[1], EPI_THREADS);
+        tc::mbar_init(&S->qfull[0], EPI_THREADS / 32);
+        tc::mbar_init(&S->qfull[1], EPI_THREADS / 32);
         tc::fence_mbar_init();
     } else if (warp == 2) {
         tc::tmem_alloc<1>(&S->tmem_ptr, TMEM_COLS);
@@ -211,60 +223,133 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
         }
     } else if (warp == 0) {
         // ================================ TMA producer ==================================================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (uint32_t it = 0;; ++it) {
-                const uint32_t slot = it % IRING, use = it / IRING;
-                tc::mbar_wait(&S->ifull[slot], use & 1);
-                const Item cur = S->items[slot];
-                tc::mbar_arrive_local(&S->iempty[slot]);
-                if (cur.idx >= nitems) break;
-                const int ntiles = (int)((cur.len + TILE_M - 1) / TILE_M);
-                for (int t = 0; t < ntiles; ++t) {
-                    const int64_t left = cur.len - (int64_t)t * TILE_M;
-                    const int rows = left >= 97 ? 128 : left >= 65 ? 96 : left >= 33 ? 64 : 32;
-                    const CUtensorMap* tm = rows == 128 ? &tm128 : rows == 96 ? &tm96 : rows == 64 ? &tm64 : &tm32;
-                    const int row0 = (int)(cur.lb + (int64_t)t * TILE_M);
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        tc::mbar_wait(&S->empty[stage], phase ^ 1);
-                        tc::mbar_arrive_expect_tx(&S->full[stage], (uint32_t)rows * 128u);
-                        tc::tma_load_2d<1>(tm, &S->full[stage], sR + (size_t)stage * STAGE_BYTES, kb * KB, row0);
-                        if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+        // converged warp, uniformized coordinates (see the MMA issuer), one elected lane issues the copies
+        const uint32_t sR_addr = tc::warp_uniform(tc::smem_u32(sR));
+        const uint32_t bar_addr = tc::warp_uniform(tc::smem_u32(S));
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t slot = it % IRING, use = it / IRING;
+            mbar_wait_warp(&S->ifull[slot], use & 1, lane);
+            const Item cur = S->items[slot];
+            mbar_arrive_warp(&S->iempty[slot], lane);
+            if (!tc::warp_uniform(cur.idx < nitems ? 1 : 0)) break;
+            const int len = tc::warp_uniform((int)cur.len);       // < 2^31 rows per shard
+            const int lb = tc::warp_uniform((int)cur.lb);
+            const int ntiles = (len + TILE_M - 1) / TILE_M;
+            for (int t = 0; t < ntiles; ++t) {
+                const int left = len - t * TILE_M;
+                const int rows = left >= 97 ? 128 : left >= 65 ? 96 : left >= 33 ? 64 : 32;
+                const CUtensorMap* tm = rows == 128 ? &tm128 : rows == 96 ? &tm96 : rows == 64 ? &tm64 : &tm32;
+                const int row0 = lb + t * TILE_M;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait_warp(&S->empty[stage], phase ^ 1, lane);
+                    if (tc::elect_one()) {
+                        const uint32_t fb = bar_addr + (uint32_t)offsetof(Smem, full) + stage * 8;
+                        tc::mbar_arrive_expect_tx_addr(fb, (uint32_t)rows * 128u);
+                        tc::tma_load_2d_addr(tm, fb, sR_addr + stage * STAGE_BYTES, kb * KB, row0);
                     }
+                    __syncwarp();
+                    if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ===================================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::make_idesc_tf32(TILE_M, QT);
-            uint32_t stage = 0, phase = 0, tile_cnt = 0;
-            for (uint32_t it = 0;; ++it) {
-                const uint32_t slot = it % IRING, use = it / IRING;
-                tc::mbar_wait(&S->ifull[slot], use & 1);
-                const Item cur = S->items[slot];
-                tc::mbar_arrive_local(&S->iempty[slot]);
-                if (cur.idx >= nitems) break;
-                tc::mbar_wait(&S->qfull[it & 1], (it >> 1) & 1);        // this item's queries are in sQ[it & 1]
-                const uint32_t qaddr = tc::smem_u32(sQ + (size_t)(it & 1) * qbuf_bytes);
-                const int ntiles = (int)((cur.len + TILE_M - 1) / TILE_M);
-                for (int t = 0; t < ntiles; ++t, ++tile_cnt) {
-                    const uint32_t as = tile_cnt % NACC, ause = tile_cnt / NACC;
-                    tc::mbar_wait(&S->tempty[as], (ause & 1) ^ 1);      // epilogue drained this accumulator
+        // The whole warp runs this loop converged; loop bounds and addresses are REDUX-uniformized so they live in
+        // uniform registers, and one elected lane issues the tcgen05 instructions.
+        constexpr uint32_t idesc = tc::make_idesc_tf32(TILE_M, QT);
+        const uint32_t tbase = tc::warp_uniform(tmem_base);
+        const uint32_t sQ_addr = tc::warp_uniform(tc::smem_u32(sQ));
+        const uint32_t bar_addr = tc::warp_uniform(tc::smem_u32(S));
+        uint32_t ts = 0, tphase = 0, tile_cnt = 0;
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t slot = it % IRING, use = it / IRING;
+            mbar_wait_warp(&S->ifull[slot], use & 1, lane);
+            const Item cur = S->items[slot];
+            mbar_arrive_warp(&S->iempty[slot], lane);
+            if (!tc::warp_uniform(cur.idx < nitems ? 1 : 0)) break;
+            const int ntiles = tc::warp_uniform((int)((cur.len + TILE_M - 1) / TILE_M));
+            mbar_wait_warp(&S->qfull[it & 1], (it >> 1) & 1, lane);        // this item's queries are in sQ[it & 1]
+            const uint32_t qaddr = sQ_addr + (it & 1) * (uint32_t)qbuf_bytes;
+            for (int t = 0; t < ntiles; ++t, ++tile_cnt) {
+                const uint32_t as = tile_cnt % NACC, ause = tile_cnt / NACC;
+                mbar_wait_warp(&S->tempty[as], (ause & 1) ^ 1, lane);      // epilogue drained this accumulator
+                tc::tc_fence_after();
+                const uint32_t tmem_d = tbase + as * QT;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait_warp(&S->conv[ts], tphase, lane);            // the split row block is in TMEM stage ts
                     tc::tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + as * QT;
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        tc::mbar_wait(&S->full[stage], phase);
-                        tc::tc_fence_after();
-                        const uint64_t da = tc::make_smem_desc(tc::smem_u32(sR + (size_t)stage * STAGE_BYTES));
-                        const uint64_t db = tc::make_smem_desc(qaddr + kb * QKB_BYTES);
+                    const uint64_t db = tc::make_smem_desc(qaddr + kb * QKB_BYTES);
+                    const uint32_t ta = tbase + A_COL0 + ts * A_STAGE_COLS;
+                    if (tc::elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < KB / UMMA_K; ++k)   // +32 B inside the 128 B swizzle row = +2 (16-byte units)
-                            tc::umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        tc::umma_commit<1>(&S->empty[stage]);
-                        if (kb == nkb - 1) tc::umma_commit<1>(&S->tfull[as]);
-                        if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+                        for (int k = 0; k < KB / UMMA_K; ++k) {   // B: +32 B inside the 128 B swizzle row = +2 (16-byte units)
+                            tc::umma_tf32_ts(tmem_d, ta + UMMA_K * k, db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            tc::umma_tf32_ts(tmem_d, ta + KB + UMMA_K * k, db + (uint64_t)(2 * k), idesc, 1u);
+                        }
+                        tc::umma_commit_addr(bar_addr + (uint32_t)offsetof(Smem, aempty) + ts * 8);
+                        if (kb == nkb - 1) tc::umma_commit_addr(bar_addr + (uint32_t)offsetof(Smem, tfull) + as * 8);
                     }
+                    __syncwarp();
+                    if (++ts == NTS) { ts = 0; tphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= CONV_WARP0) {
+        // ================================ row splitters ================================================
+        // thread t owns row t of every staged [128 rows][32 floats] block: y = hi + lo with hi = y's top 19 bits
+        // (exactly representable in tf32, so the result does not depend on how the tensor core would cut a raw fp32
+        // operand) and lo = y - hi (exact).  Both go to TMEM as A operands (columns [0,32) hi, [32,64) lo of the
+        // stage); the shared-memory stage is handed back to the TMA producer as soon as it has been read.
+        const int cw = (warp - CONV_WARP0) & 3;      // == warp % 4: TMEM lane quarter
+        const int cg = (warp - CONV_WARP0) >> 2;     // splitter group: handles stage sequence numbers = cg (mod CONV_GROUPS)
+        const int t = cw * 32 + lane;
+        uint32_t stage = 0, phase = 0, ts = 0, tphase = 0, seq = 0;
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t slot = it % IRING, use = it / IRING;
+            mbar_wait_warp(&S->ifull[slot], use & 1, lane);
+            const Item cur = S->items[slot];
+            mbar_arrive_warp(&S->iempty[slot], lane);
+            if (cur.idx >= nitems) break;
+            const int ntiles = (int)((cur.len + TILE_M - 1) / TILE_M);
+            for (int tl = 0; tl < ntiles; ++tl) {
+                const int64_t left = cur.len - (int64_t)tl * TILE_M;
+                const bool active = (int64_t)cw * 32 < left;     // warp-uniform: this quarter holds list rows
+                for (int kb = 0; kb < nkb; ++kb, ++seq) {
+                    if ((int)(seq % CONV_GROUPS) == cg) {
+                        mbar_wait_warp(&S->full[stage], phase, lane);
+                        mbar_wait_warp(&S->aempty[ts], tphase ^ 1, lane);
+                        tc::tc_fence_after();
+                        const uint32_t taddr = tmem_base + ((uint32_t)(cw * 32) << 16) + A_COL0 + ts * A_STAGE_COLS;
+                        if (active && !(dbg_flags & 4)) {
+                            const uint8_t* row = sR + (size_t)stage * STAGE_BYTES + t * 128;
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {
+                                uint32_t hi[16], lo[16];
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    const float4 f = *reinterpret_cast<const float4*>(row + (((4 * hf + c) ^ (t & 7)) << 4));
+                                    const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const uint32_t hb = __float_as_uint(fv[e]) & 0xffffe000u;
+                                        hi[4 * c + e] = hb;
+                                        lo[4 * c + e] = __float_as_uint(fv[e] - __uint_as_float(hb));
+                                    }
+                                }
+                                if (hf == 1) mbar_arrive_warp(&S->empty[stage], lane);   // the row block is in registers
+                                tc::tmem_st16(taddr + 16 * hf, hi);
+                                tc::tmem_st16(taddr + KB + 16 * hf, lo);
+                            }
+                            tc::tmem_st_wait();
+                        } else {
+                            mbar_arrive_warp(&S->empty[stage], lane);
+                        }
+                        tc::tc_fence_before();
+                        mbar_arrive_warp(&S->conv[ts], lane);
+                    }
+                    if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+                    if (++ts == NTS) { ts = 0; tphase ^= 1; }
                 }
             }
         }
@@ -274,143 +359,172 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
         const int et = threadIdx.x - EPI_WARP0 * 32;
         uint32_t tile_cnt = 0;
         unsigned long long n_fb = 0, n_cand = 0;    // lane 0: running totals for rvcr_get_stats
-        tc::mbar_wait(&S->ifull[0], 0);
+        mbar_wait_warp(&S->ifull[0], 0, lane);
         Item cur = S->items[0];
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive_local(&S->iempty[0]);
+        mbar_arrive_warp(&S->iempty[0], lane);
         if (cur.idx < nitems) {
             load_queries(sQ, q, qorder, cur, d, nkb, et);
             cp_async_commit();
             cp_async_wait<0>();
+            convert_queries(sQ, S->qnorm[0], nkb, et);
             tc::fence_proxy_async_smem();
-            tc::mbar_arrive_local(&S->qfull[0]);
+            mbar_arrive_warp(&S->qfull[0], lane);
         }
         for (uint32_t it = 0;; ++it) {
             if (cur.idx >= nitems) break;
             Item nxt;
             {
                 const uint32_t sn = it + 1, slot = sn % IRING, use = sn / IRING;
-                tc::mbar_wait(&S->ifull[slot], use & 1);
+                mbar_wait_warp(&S->ifull[slot], use & 1, lane);
                 nxt = S->items[slot];
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive_local(&S->iempty[slot]);
+                mbar_arrive_warp(&S->iempty[slot], lane);
             }
             const bool have_next = nxt.idx < nitems;
-            // buffer (it+1)&1 was last read by item it-1, whose MMAs and merge are complete
+            // buffer (it+1)&1 was last read by item it-1, whose MMAs and selection are complete
             if (have_next) load_queries(sQ + (size_t)((it + 1) & 1) * qbuf_bytes, q, qorder, nxt, d, nkb, et);
             cp_async_commit();
             bool next_published = !have_next;
 
-            float td[QT];
-            int tp[QT];
-#pragma unroll
-            for (int j = 0; j < QT; ++j) {
-                td[j] = __int_as_float(0x7f800000);
-                tp[j] = -1;
-            }
             const int cnt = cur.cnt;
             const int ntiles = (int)((cur.len + TILE_M - 1) / TILE_M);
-            for (int t = 0; t < ntiles; ++t, ++tile_cnt) {
-                const uint32_t as = tile_cnt % NACC, ause = tile_cnt / NACC;
-                const int64_t row = (int64_t)t * TILE_M + ew * 32 + lane;
-                const bool valid = row < cur.len;
-                const int pos = (int)(cur.lb + row);
-                const float yn = valid ? __ldg(ynorm + pos) : 0.f;
-                tc::mbar_wait(&S->tfull[as], ause & 1);
-                tc::tc_fence_after();
-                uint32_t r[16];
-                tc::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + as * QT, r);
-                tc::tmem_ld_wait();
-                tc::tc_fence_before();
-                tc::mbar_arrive_local(&S->tempty[as]);
-                const bool first = (t == 0);
+            // this warp selects for queries ew, ew+4, ew+8, ew+12 of the item (slot u <-> query ew + 4u)
+            float ub[4], mg[4], lmin[4];
+            int ncand[4];
 #pragma unroll
-                for (int j = 0; j < QT; ++j) {
-                    if (j < cnt) {   // warp-uniform
-                        float v = valid ? fmaf(-2.f, __uint_as_float(r[j]), yn) : __int_as_float(0x7f800000);
-                        if (!(v == v)) v = __int_as_float(0x7f800000);   // NaN rows are never candidates
-                        if (first) {
-                            int p = v < __int_as_float(0x7f800000) ? pos : -1;
-                            warp_sort32(v, p, lane);
-                            td[j] = v;
-                            tp[j] = p;
-                        } else {
-                            top32_insert(td[j], tp[j], v, pos, lane);
-                        }
+            for (int u = 0; u < 4; ++u) {
+                ub[u] = __int_as_float(0x7f800000);
+                lmin[u] = __int_as_float(0x7f800000);   // this lane's minimum over rows = lane (mod 32), all chunks so far
+                mg[u] = 0.f;
+                ncand[u] = 0;
+            }
+            // lists longer than one chunk: candidates are staged with their v (the cutoff only tightens from chunk
+            // to chunk) and filtered once more against the final cutoff
+            const bool multi = ntiles > CHUNK_TILES;
+            float2* stage = stage_buf + ((size_t)blockIdx.x * QT) * SCAP;
+            for (int t0 = 0; t0 < ntiles || t0 == 0; t0 += CHUNK_TILES) {
+                const int t1 = min(t0 + CHUNK_TILES, ntiles);
+                // ---- pass 1: v = ||y||^2 - 2 <y, q> of this chunk's tiles -> sV[query][row in chunk] ----
+                for (int t = t0; t < t1; ++t, ++tile_cnt) {
+                    const uint32_t as = tile_cnt % NACC, ause = tile_cnt / NACC;
+                    const int64_t row = (int64_t)t * TILE_M + ew * 32 + lane;
+                    const bool valid = row < cur.len;
+                    const float yn = valid ? __ldg(ynorm + cur.lb + row) : 0.f;
+                    mbar_wait_warp(&S->tfull[as], ause & 1, lane);
+                    tc::tc_fence_after();
+                    uint32_t r[16];
+                    tc::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + as * QT, r);
+                    tc::tmem_ld_wait();
+                    tc::tc_fence_before();
+                    mbar_arrive_warp(&S->tempty[as], lane);
+                    float* dst = sV + (t - t0) * TILE_M + ew * 32 + lane;
+#pragma unroll
+                    for (int j = 0; j < QT; ++j)
+                        if (j < cnt)   // warp-uniform
+                            dst[j * CHUNK_ROWS] = valid ? fmaf(-2.f, __uint_as_float(r[j]), yn) : __int_as_float(0x7f800000);
+                    if (!next_published) {
+                        cp_async_wait<0>();
+                        convert_queries(sQ + (size_t)((it + 1) & 1) * qbuf_bytes, S->qnorm[(it + 1) & 1], nkb, et);
+                        tc::fence_proxy_async_smem();
+                        mbar_arrive_warp(&S->qfull[(it + 1) & 1], lane);
+                        next_published = true;
                     }
                 }
                 if (!next_published) {
                     cp_async_wait<0>();
+                    convert_queries(sQ + (size_t)((it + 1) & 1) * qbuf_bytes, S->qnorm[(it + 1) & 1], nkb, et);
                     tc::fence_proxy_async_smem();
-                    tc::mbar_arrive_local(&S->qfull[(it + 1) & 1]);
+                    mbar_arrive_warp(&S->qfull[(it + 1) & 1], lane);
                     next_published = true;
                 }
+                tc::named_bar_sync(1, EPI_THREADS);      // the chunk's v are in sV
+                // ---- pass 2: per query, every row with v <= U + margin(q) is a candidate, where U >= the 8th
+                // smallest v of the list: the 8th smallest of the 32 lane minima (8 distinct rows are <= it) ----
+                const int rows = (int)min((long long)CHUNK_ROWS, cur.len - (long long)t0 * TILE_M);
+                const int pos0 = (int)(cur.lb + (int64_t)t0 * TILE_M);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = ew + 4 * u;
+                    if (j < cnt && rows > 0) {   // warp-uniform
+                        const int64_t qi = qorder[cur.p0 + j];
+                        const float* vj = sV + j * CHUNK_ROWS;
+                        if (t0 == 0) {
+                            // |v - v_true| <= 2 |acc - <q, y>| + roundings, |acc - <q, y>| <= ||q_lo|| ||y|| (the part of q
+                            // the tf32 operand drops) + acc_rel ||q|| ||y|| (lo-part truncation, fp32 accumulation);
+                            // two approximate values are compared, hence the factor 4 (DESIGN.md "Numerics")
+                            const float2 nn = S->qnorm[it & 1][j];
+                            mg[u] = 4.04f * ymax * (sqrtf(nn.y) + acc_rel * sqrtf(nn.x)) + abs_margin * (nn.x + ymax * ymax);
+                        }
+                        float lm = lmin[u];
+                        for (int r0 = lane; r0 < rows; r0 += 32) lm = fminf(lm, vj[r0]);
+                        lmin[u] = lm;
+                        int rk = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float xi = __shfl_sync(0xffffffffu, lm, i);
+                            rk += (xi < lm || (xi == lm && i < lane)) ? 1 : 0;
+                        }
+                        const unsigned b7 = __ballot_sync(0xffffffffu, rk == 7);
+                        ub[u] = __shfl_sync(0xffffffffu, lm, __ffs(b7) - 1);   // non-increasing from chunk to chunk
+                        const float cutoff = ub[u] + mg[u];
+                        for (int r0 = 0; r0 < rows; r0 += 32) {
+                            const int rr = r0 + lane;
+                            const float v = rr < rows ? vj[rr] : __int_as_float(0x7f800000);
+                            const bool pass = rr < rows && v <= cutoff;
+                            const unsigned bm = __ballot_sync(0xffffffffu, pass);
+                            const int idx = ncand[u] + __popc(bm & ((1u << lane) - 1u));
+                            if (pass) {
+                                if (!multi) {
+                                    if (idx < CCAP) cand[qi * CCAP + idx] = pos0 + rr;
+                                } else if (idx < SCAP) {
+                                    stage[(size_t)j * SCAP + idx] = make_float2(v, __int_as_float(pos0 + rr));
+                                }
+                            }
+                            ncand[u] += __popc(bm);
+                        }
+                    }
+                }
+                tc::named_bar_sync(1, EPI_THREADS);      // selection done: sV may be overwritten
             }
-            if (!next_published) {
-                cp_async_wait<0>();
-                tc::fence_proxy_async_smem();
-                tc::mbar_arrive_local(&S->qfull[(it + 1) & 1]);
-            }
-
-            // ---- merge the four quarter lists, select the candidates of every query of the item ----
-            tc::named_bar_sync(1, EPI_THREADS);      // previous item's merge reads of sM are done
+            if (multi) {
 #pragma unroll
-            for (int j = 0; j < QT; ++j) {
-                if (j < cnt) {
-                    sMv[(ew * QT + j) * TOPT + lane] = td[j];
-                    sMp[(ew * QT + j) * TOPT + lane] = tp[j];
+                for (int u = 0; u < 4; ++u) {
+                    const int j = ew + 4 * u;
+                    if (j < cnt) {   // warp-uniform
+                        const int64_t qi = qorder[cur.p0 + j];
+                        const int staged = ncand[u];
+                        if (staged > SCAP) {
+                            ncand[u] = CCAP + 1;       // staging overflowed: exact fallback
+                        } else {
+                            __syncwarp();              // this warp's staged entries are visible to all its lanes
+                            const float cutoff = ub[u] + mg[u];
+                            int kept = 0;
+                            for (int e0 = 0; e0 < staged; e0 += 32) {
+                                const int e = e0 + lane;
+                                float2 ent = make_float2(0.f, 0.f);
+                                if (e < staged) ent = stage[(size_t)j * SCAP + e];
+                                const bool pass = e < staged && ent.x <= cutoff;
+                                const unsigned bm = __ballot_sync(0xffffffffu, pass);
+                                const int idx = kept + __popc(bm & ((1u << lane) - 1u));
+                                if (pass && idx < CCAP) cand[qi * CCAP + idx] = __float_as_int(ent.y);
+                                kept += __popc(bm);
+                            }
+                            ncand[u] = kept;
+                        }
+                    }
                 }
             }
-            tc::named_bar_sync(1, EPI_THREADS);
-            const uint8_t* sQc = sQ + (size_t)(it & 1) * qbuf_bytes;
-            for (int j = ew; j < cnt; j += 4) {
-                const int64_t qi = qorder[cur.p0 + j];
-                // 8th smallest v overall: it is among the 8 smallest of each quarter
-                const float x = sMv[((lane >> 3) * QT + j) * TOPT + (lane & 7)];
-                int rk = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float xi = __shfl_sync(0xffffffffu, x, i);
-                    rk += (xi < x || (xi == x && i < lane)) ? 1 : 0;
-                }
-                const unsigned b7 = __ballot_sync(0xffffffffu, rk == 7);
-                const float v8 = __shfl_sync(0xffffffffu, x, __ffs(b7) - 1);
-                // ||q||^2 from the staged query row (any order; rounding is covered by the margin slack)
-                float qn2 = 0.f;
-                for (int c = lane; c < nkb * 8; c += 32) {
-                    const int kb = c >> 3, c16 = c & 7;
-                    const float4 f = *reinterpret_cast<const float4*>(sQc + kb * QKB_BYTES + (j >> 3) * 1024 + (j & 7) * 128 +
-                                                                      ((c16 ^ (j & 7)) << 4));
-                    qn2 = fmaf(f.x, f.x, qn2);
-                    qn2 = fmaf(f.y, f.y, qn2);
-                    qn2 = fmaf(f.z, f.z, qn2);
-                    qn2 = fmaf(f.w, f.w, qn2);
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) qn2 += __shfl_xor_sync(0xffffffffu, qn2, off);
-                const float margin = rel_margin * sqrtf(qn2) * ymax + abs_margin * (qn2 + ymax * ymax);
-                const float cutoff = v8 + margin;
-                int total = 0;
-                bool ovf = false;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const float v = sMv[(w * QT + j) * TOPT + lane];
-                    const int p = sMp[(w * QT + j) * TOPT + lane];
-                    const bool pass = p >= 0 && v <= cutoff;
-                    const unsigned bm = __ballot_sync(0xffffffffu, pass);
-                    if (bm >> 31) ovf = true;     // the quarter's 32nd entry qualifies: its list may be truncated
-                    const int idx = total + __popc(bm & ((1u << lane) - 1u));
-                    if (pass && idx < CCAP) cand[qi * CCAP + idx] = p;
-                    total += __popc(bm);
-                }
-                if (lane == 0) {
-                    if (ovf || total > CCAP) {
+            for (int u = 0; u < 4; ++u) {
+                const int j = ew + 4 * u;
+                if (j < cnt && lane == 0) {
+                    const int64_t qi = qorder[cur.p0 + j];
+                    if (ncand[u] > CCAP) {
                         candcnt[qi] = -1;
                         fb_list[atomicAdd(fb_count, 1)] = (int32_t)(cur.p0 + j);   // sorted position
                         ++n_fb;
                     } else {
-                        candcnt[qi] = total;
-                        n_cand += (unsigned long long)total;
+                        candcnt[qi] = ncand[u];
+                        n_cand += (unsigned long long)ncand[u];
                     }
                 }
             }
@@ -643,7 +757,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     RVCR_TRY(ensure_row_norms(h, s));
     RVCR_TRY(ensure_scan_tmaps(h));
     const int d = h->d, nkb = d / stc::KB;
-    const size_t fixed = 2 * (size_t)nkb * stc::QKB_BYTES + stc::MERGE_BYTES + sizeof(stc::Smem) + 1024;
+    const size_t fixed = 2 * (size_t)nkb * stc::QKB_BYTES + stc::SV_BYTES + sizeof(stc::Smem) + 1024;
     int nstage = (int)((226 * 1024 - fixed) / stc::STAGE_BYTES);
     if (nstage > 8) nstage = 8;
     if (nstage < 2) {
@@ -659,14 +773,15 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     RVCR_TRY(h->ws_cand.reserve((size_t)n * stc::CCAP * 4));
     RVCR_TRY(h->ws_candcnt.reserve((size_t)n * 4));
     RVCR_TRY(h->ws_fb.reserve((size_t)n * 4 + 64));
+    RVCR_TRY(h->ws_cstage.reserve((size_t)h->num_sms * stc::QT * stc::SCAP * sizeof(float2)));
     int32_t* fb_count = h->ws_misc.as<int32_t>() + 14;
     RVCR_CUDA(cudaMemsetAsync(fb_count, 0, 4, s));
     if (fill) {
         RVCR_TRY(fill_pad(D, P, I, n * RVCR_K, s));
     }
-    // margin between two approximate values: 2 x |v - v_true|, |v - v_true| <= 2 |acc - <q,y>| + norm roundings;
-    // |acc - <q,y>| <= (2^-9 (tf32 truncation of both operands) + d 2^-21 (fp32 accumulation)) |q||y|
-    const float rel = 4.f * (1.01f / 512.f + (float)d / 2097152.f);
+    // relative error of one accumulated dot product beyond the dropped query low part: truncation of the row
+    // low part to tf32 (2^-20) and fp32 accumulation of 2 d products in the tensor core (d 2^-21)
+    const float rel = 1.f / 1048576.f + (float)d / 2097152.f;
     const float absm = 1.f / 524288.f;
     int grid = h->num_sms;
     const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(h->scan_tmaps);
@@ -674,9 +789,11 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
         tm[0], tm[1], tm[2], tm[3], q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), h->ws_items.as<int32_t>(),
         h->ws_misc.as<int32_t>(), h->ws_misc.as<int32_t>() + ticket_slot, h->offsets, h->row_norm.as<float>(), (uint32_t)h->nlist, n, d,
         nstage, h->row_norm_max, rel, absm, item_begin, item_end, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
-        h->ws_fb.as<int32_t>(), fb_count, reinterpret_cast<unsigned long long*>(h->ws_misc.as<int32_t>() + 48));
+        h->ws_fb.as<int32_t>(), fb_count, reinterpret_cast<unsigned long long*>(h->ws_misc.as<int32_t>() + 48),
+        h->ws_cstage.as<float2>(), getenv("RVCR_STC_FLAGS") ? atoi(getenv("RVCR_STC_FLAGS")) : 0);
     RVCR_CHECK_LAUNCH();
     {
+        PhaseTimer pt(h, RVCR_PHASE_SCAN_RECHECK, s);
         const size_t rsm = (size_t)RC_WARPS * d * 4;
         int64_t rgrid = (int64_t)h->num_sms * 8;
         if (rgrid * RC_WARPS > n) rgrid = (n + RC_WARPS - 1) / RC_WARPS;
@@ -687,6 +804,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
         RVCR_CHECK_LAUNCH();
     }
     {
+        PhaseTimer pt(h, RVCR_PHASE_SCAN_FALLBACK, s);
         const size_t fsm = (size_t)(d + 32) * 4;
         scan_exact_fallback_kernel<<<h->num_sms * 2, 256, fsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(),
                                                                     h->ws_fb.as<int32_t>(), fb_count, (uint32_t)h->nlist, d, h->vecs,

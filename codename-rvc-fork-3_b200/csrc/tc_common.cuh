@@ -83,6 +83,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
     }
 }
 
+// address-based forms (shared-memory addresses kept in uniform registers by the caller)
+__device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t bar_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_addr(const CUtensorMap* m, uint32_t bar_addr, uint32_t dst_addr, int crd0, int crd1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_addr),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(crd0), "r"(crd1)
+        : "memory");
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -139,6 +150,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     }
 }
 
+// single-CTA commit on a barrier given by its shared-memory address (keeps the address on the uniform datapath)
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_smem_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem_addr) : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -180,6 +196,40 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, A operand read from tensor memory (lane = row, one 32-bit column per k element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(
+            tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// fp32 -> tf32 (round to nearest, ties away), returned as an fp32 bit pattern with the low 13 bits clear
+__device__ __forceinline__ float to_tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4)                    // D format: fp32
            | (2u << 7)                  // A format: tf32
@@ -196,6 +246,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// A value every lane of the warp already agrees on, made PROVABLY uniform for the compiler: REDUX writes a
+// uniform register, so descriptors / coordinates derived from it stay on the uniform datapath and the tcgen05 / TMA
+// instructions that need uniform-register operands are not wrapped in ELECT + R2UR.BROADCAST waterfall loops.
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_uniform(int v) { return __reduce_max_sync(0xffffffffu, v); }
+
 // generic-proxy writes to shared memory (st.shared / cp.async) -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -258,7 +258,7 @@ class IndexIVFFlat:
         return (v.reshape(-1)[: n * P].reshape(n, P).copy(), j.reshape(-1)[: n * P].reshape(n, P).copy(), qn,
                 float(cmax.value))
 
-    PHASES = ("coarse_prep", "coarse_main", "coarse_recheck", "group", "scan", "blend")
+    PHASES = ("coarse_prep", "coarse_main", "coarse_recheck", "group", "scan", "blend", "scan_recheck", "scan_fallback")
 
     def phase_ms(self) -> dict:
         """Per-phase device time (ms) of the last search-type call; needs set_option("profile", 1)."""

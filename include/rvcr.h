@@ -46,6 +46,8 @@ extern "C" {
 #define RVCR_PHASE_GROUP 3          /* sort queries by probed list, build work items        */
 #define RVCR_PHASE_SCAN 4           /* inverted-list scan + top-8                           */
 #define RVCR_PHASE_BLEND 5          /* gather + 1/score^2 weights + index_rate blend        */
+#define RVCR_PHASE_SCAN_RECHECK 6  /* (inside SCAN) exact fp32 re-check of the tensor-core scan's candidates */
+#define RVCR_PHASE_SCAN_FALLBACK 7 /* (inside SCAN) brute-force exact scan of overflowed queries            */
 #define RVCR_NUM_PHASES 8
 
 #if defined(__GNUC__)
