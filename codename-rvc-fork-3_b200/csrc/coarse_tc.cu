@@ -120,32 +120,43 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
+    // The issuing warps run their loops converged (all loop bounds are kernel parameters / special registers, hence
+    // uniform); only the tcgen05 / TMA instructions themselves are predicated on one elected lane.  Issuing from inside
+    // an `if (elect)` region instead makes the compiler treat every descriptor as divergent and wrap each instruction in
+    // an ELECT + R2UR.BROADCAST waterfall (~15 slow instructions per MMA).
     if (warp == 0) {
         // ================================ TMA producer =================================
-        if (elect_one()) {
-            uint32_t stage = 0, phase = 0;
-            for (int item = cluster_id; item < nitems; item += nclusters) {
-                const int mb = item / nsplit, sp = item - mb * nsplit;
-                const int m0 = mb * (BLOCK_M * CLUSTER) + (int)cta_rank * BLOCK_M;
-                const int t0 = sp * tiles_per_split;
-                const int t1 = min(t0 + tiles_per_split, num_ntiles);
-                for (int t = t0; t < t1; ++t) {
-                    const int n0 = t * BLOCK_N + (int)cta_rank * C::LOAD_N;
-                    for (int kb = 0; kb < num_kblocks; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        tma_load_2d<CLUSTER>(&tmap_a, &full_bar[stage], sA + stage * C::A_BYTES, kb * BLOCK_K, m0);
-                        tma_load_2d<CLUSTER>(&tmap_b, &full_bar[stage], sB + stage * C::B_BYTES, kb * BLOCK_K, n0);
-                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * CLUSTER);
-                        else mbar_arrive_cluster(&full_bar[stage], 0);
-                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        const uint32_t sA_addr = tc::warp_uniform(smem_u32(sA)), sB_addr = tc::warp_uniform(smem_u32(sB));
+        const uint32_t full_addr = tc::warp_uniform(smem_u32(full_bar));
+        uint32_t stage = 0, phase = 0;
+        for (int item = cluster_id; item < nitems; item += nclusters) {
+            const int mb = item / nsplit, sp = item - mb * nsplit;
+            const int m0 = mb * (BLOCK_M * CLUSTER) + (int)cta_rank * BLOCK_M;
+            const int t0 = sp * tiles_per_split;
+            const int t1 = min(t0 + tiles_per_split, num_ntiles);
+            for (int t = t0; t < t1; ++t) {
+                const int n0 = t * BLOCK_N + (int)cta_rank * C::LOAD_N;
+                for (int kb = 0; kb < num_kblocks; ++kb) {
+                    mbar_wait_warp(&empty_bar[stage], phase ^ 1, lane);
+                    if (elect_one()) {
+                        const uint32_t fb = full_addr + stage * 8;
+                        tma_load_2d_a<CLUSTER>(&tmap_a, fb, sA_addr + stage * C::A_BYTES, kb * BLOCK_K, m0);
+                        tma_load_2d_a<CLUSTER>(&tmap_b, fb, sB_addr + stage * C::B_BYTES, kb * BLOCK_K, n0);
+                        if (leader) mbar_arrive_expect_tx_addr(fb, C::STAGE_BYTES * CLUSTER);
+                        else mbar_arrive_cluster_addr(fb, 0);
                     }
+                    __syncwarp();
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ===================================
-        if (leader && elect_one()) {
+        if (leader) {
             constexpr uint32_t idesc = make_idesc(C::UMMA_M, BLOCK_N);
+            const uint32_t sA_addr = tc::warp_uniform(smem_u32(sA)), sB_addr = tc::warp_uniform(smem_u32(sB));
+            const uint32_t empty_addr = tc::warp_uniform(smem_u32(empty_bar)), tfull_addr = tc::warp_uniform(smem_u32(tmem_full_bar));
+            const uint32_t tbase = tc::warp_uniform(tmem_base);
             uint32_t stage = 0, phase = 0, tile_cnt = 0;
             for (int item = cluster_id; item < nitems; item += nclusters) {
                 const int sp = item % nsplit;
@@ -153,22 +164,25 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int t1 = min(t0 + tiles_per_split, num_ntiles);
                 for (int t = t0; t < t1; ++t, ++tile_cnt) {
                     const uint32_t as = tile_cnt & 1, aphase = (tile_cnt >> 1) & 1;
-                    mbar_wait(&tmem_empty_bar[as], aphase ^ 1);   // epilogue drained this accumulator
+                    mbar_wait_warp(&tmem_empty_bar[as], aphase ^ 1, lane);   // epilogue drained this accumulator
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                    const uint32_t tmem_d = tbase + as * BLOCK_N;
                     for (int kb = 0; kb < num_kblocks; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);
+                        mbar_wait_warp(&full_bar[stage], phase, lane);
                         tc_fence_after();
-                        const uint64_t da = make_smem_desc(smem_u32(sA + stage * C::A_BYTES));
-                        const uint64_t db = make_smem_desc(smem_u32(sB + stage * C::B_BYTES));
+                        const uint64_t da = make_smem_desc(sA_addr + stage * C::A_BYTES);
+                        const uint64_t db = make_smem_desc(sB_addr + stage * C::B_BYTES);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte units
-                            umma_bf16<CLUSTER>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                               (kb > 0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte units
+                                umma_bf16<CLUSTER>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                                   (kb > 0 || k > 0) ? 1u : 0u);
+                            }
+                            umma_commit_a<CLUSTER>(empty_addr + stage * 8);   // frees the smem stage when the MMAs retire
+                            if (kb == num_kblocks - 1) umma_commit_a<CLUSTER>(tfull_addr + as * 8);
                         }
-                        umma_commit<CLUSTER>(&empty_bar[stage]);   // frees the smem stage when the MMAs retire
-                        if (kb == num_kblocks - 1) umma_commit<CLUSTER>(&tmem_full_bar[as]);
+                        __syncwarp();
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -189,7 +203,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int i = 0; i < TOPT; ++i) { tv[i] = __int_as_float(0x7f800000); tj[i] = -1; }
             for (int t = t0; t < t1; ++t, ++tile_cnt) {
                 const uint32_t as = tile_cnt & 1, aphase = (tile_cnt >> 1) & 1;
-                mbar_wait(&tmem_full_bar[as], aphase);
+                mbar_wait_warp(&tmem_full_bar[as], aphase, lane);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N;
                 const int n0 = t * BLOCK_N;

@@ -73,18 +73,8 @@ struct Smem {
     uint32_t tmem_ptr;
 };
 
-// Warp-collective barrier wait: one lane polls (32x less shared-memory polling traffic), then every lane
-// performs its own (immediately successful) wait so that each thread has acquire semantics of its own.
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
-    if (lane == 0) tc::mbar_wait(bar, parity);
-    __syncwarp();
-    tc::mbar_wait(bar, parity);
-}
-// Warp-collective arrive (barrier counts are per warp): all lanes' prior writes are ordered before lane 0's arrive.
-__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, int lane) {
-    __syncwarp();
-    if (lane == 0) tc::mbar_arrive_local(bar);
-}
+using tc::mbar_arrive_warp;
+using tc::mbar_wait_warp;
 
 __device__ __forceinline__ void fetch_item(Item* out, int32_t* ticket, int item_begin, int nitems,
                                            const int32_t* __restrict__ items, const uint32_t* __restrict__ keys,

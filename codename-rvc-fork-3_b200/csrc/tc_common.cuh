@@ -83,6 +83,19 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
     }
 }
 
+// Warp-collective barrier wait: one lane polls (32x less shared-memory polling traffic), then every lane
+// performs its own (immediately successful) wait so that each thread has acquire semantics of its own.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+    mbar_wait(bar, parity);
+}
+// Warp-collective arrive (barrier counts are per warp): all lanes' prior writes are ordered before lane 0's arrive.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive_local(bar);
+}
+
 // address-based forms (shared-memory addresses kept in uniform registers by the caller)
 __device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t bar_addr, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
@@ -92,6 +105,39 @@ __device__ __forceinline__ void tma_load_2d_addr(const CUtensorMap* m, uint32_t 
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_addr),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(crd0), "r"(crd1)
         : "memory");
+}
+
+template <int CLUSTER>
+__device__ __forceinline__ void tma_load_2d_a(const CUtensorMap* m, uint32_t bar_addr, uint32_t dst_addr, int crd0, int crd1) {
+    if constexpr (CLUSTER == 1) {
+        tma_load_2d_addr(m, bar_addr, dst_addr, crd0, crd1);
+    } else {
+        // both CTAs of the pair issue this; clearing the peer bit routes complete_tx to the leader CTA's barrier
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                dst_addr),
+            "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr & 0xFEFFFFFFu), "r"(crd0), "r"(crd1)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t bar_addr, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(
+            bar_addr),
+        "r"(cta)
+        : "memory");
+}
+template <int CLUSTER>
+__device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {
+    if constexpr (CLUSTER == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+    } else {
+        const uint16_t mask = 3;  // both CTAs of the pair
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         bar_addr),
+                     "h"(mask)
+                     : "memory");
+    }
 }
 
 // ---- tcgen05 -------------------------------------------------------------------------------
