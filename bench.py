@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--coarse-mode", type=int, default=0)
     ap.add_argument("--scan-impl", type=int, default=5)
+    ap.add_argument("--tc-resident", type=int, default=-1, help="coarse kernel: resident query k-blocks (0/8/9/10; -1 = library default)")
+    ap.add_argument("--fused-blend", type=int, default=-1, help="1 = re-check kernel also blends (default), 0 = separate gather_blend kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -228,6 +230,10 @@ def main():
     synth.fill_index_by_construction(index, cent_all, sizes, N, list_range=(lo, hi))
     index.set_option("coarse_mode", args.coarse_mode)
     index.set_option("scan_impl", args.scan_impl)
+    if args.tc_resident >= 0:
+        index.set_option("tc_resident", args.tc_resident)
+    if args.fused_blend >= 0:
+        index.set_option("fused_blend", args.fused_blend)
     index.set_option("profile", 1)
     nq_lo, nq_hi = nq * rank // world, nq * (rank + 1) // world
     q_home = synth.device_queries(cent_all, nq, q_range=(nq_lo, nq_hi))
@@ -308,11 +314,15 @@ def main():
                           "kernel": "coarse_tc_kernel<2> (tcgen05 bf16, fp32 accumulate)" if tc else "coarse_exact_kernel",
                           "ms": phase_acc["coarse_main"], "flops_per_launch": coarse_flops,
                           "peak_source": pk["source"] + " cuBLAS bf16 burst" if tc else "measured FFMA micro-peak (profiles/)"}
+    fused = "scan" in phase_acc and "blend" not in phase_acc      # the re-check kernel also gathered + blended
     if "scan" in phase_acc:
-        gb = scan_bytes / (phase_acc["scan"] * 1e-3) / 1e9
+        sb = scan_bytes + (blend_bytes if fused else 0)
+        gb = sb / (phase_acc["scan"] * 1e-3) / 1e9
         roof["scan"] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / pk["hbm_gbs"],
-                        "traffic": None, "kernel": "scan_tc_kernel (tcgen05 tf32 + TMA) + scan_recheck_kernel (exact fp32)" if args.scan_impl == 5
-                        else f"scan_topk_kernel_v{args.scan_impl}", "ms": phase_acc["scan"], "bytes_per_launch": scan_bytes,
+                        "traffic": None, "kernel": ("scan_tc_kernel (tcgen05 tf32 + TMA) + scan_recheck_kernel (exact fp32"
+                                                    + (" + gather/weights/blend)" if fused else ")")) if args.scan_impl == 5
+                        else f"scan_topk_kernel_v{args.scan_impl}", "ms": phase_acc["scan"], "bytes_per_launch": sb,
+                        "bytes_note": "B_s + B_g (SURVEY 8d): scan and fused tail" if fused else "B_s (SURVEY 8d)",
                         "peak_source": pk["source"]}
     if "blend" in phase_acc:
         gb = blend_bytes / (phase_acc["blend"] * 1e-3) / 1e9

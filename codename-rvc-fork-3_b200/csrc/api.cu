@@ -138,11 +138,18 @@ int search_device(rvcr_index* h, float* feats_or_q, int64_t n, const int32_t* as
         RVCR_TRY(h->ws_D.reserve((size_t)n * RVCR_K * 4));
         D = h->ws_D.as<float>();
     }
+    h->fuse.active = blend && h->opt.fused_blend != 0;
+    h->fuse.done = false;
+    h->fuse.out = feats_or_q;
+    h->fuse.r32 = (float)index_rate;
+    h->fuse.omr32 = (float)(1.0 - index_rate);
     {
         PhaseTimer pt(h, RVCR_PHASE_SCAN, s);
-        RVCR_TRY(scan_topk(h, feats_or_q, n, D, h->ws_P.as<int32_t>(), I_dev, s));
+        const int rc = scan_topk(h, feats_or_q, n, D, h->ws_P.as<int32_t>(), I_dev, s);
+        h->fuse.active = false;
+        RVCR_TRY(rc);
     }
-    if (blend) {
+    if (blend && !h->fuse.done) {
         PhaseTimer pt(h, RVCR_PHASE_BLEND, s);
         RVCR_TRY(gather_blend(h, feats_or_q, n, D, h->ws_P.as<int32_t>(), assign_in, index_rate, s));
     }
@@ -520,8 +527,18 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     RVCR_TRY(h->ws_assign.reserve((size_t)n * 4));
     RVCR_TRY(finalize_pending(h, s));
     if (!h->copy_stream) RVCR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    const int64_t chunk = 131072;
-    const int64_t nchunks = (n + chunk - 1) / chunk;
+    // chunk sizes ramp up (32 Ki, 64 Ki, then 128 Ki rows) so that only a small first copy is exposed
+    std::vector<int64_t> coff;
+    {
+        int64_t off = 0, c = 32768;
+        while (off < n) {
+            coff.push_back(off);
+            off += c;
+            if (c < 131072) c *= 2;
+        }
+        coff.push_back(n);
+    }
+    const int64_t nchunks = (int64_t)coff.size() - 1;
     while ((int64_t)h->copy_events.size() < nchunks) {
         cudaEvent_t e;
         RVCR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -531,13 +548,13 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     for (int i = 0; i < RVCR_NUM_PHASES; ++i) h->pev_used[i] = false;
     char* dq = reinterpret_cast<char*>(h->ws_q.p);
     for (int64_t c = 0; c < nchunks; ++c) {
-        const int64_t off = c * chunk, m = std::min(chunk, n - off);
+        const int64_t off = coff[c], m = coff[c + 1] - off;
         RVCR_CUDA(cudaMemcpyAsync(dq + (size_t)off * rowb, reinterpret_cast<const char*>(feats_host) + (size_t)off * rowb,
                                   (size_t)m * rowb, cudaMemcpyHostToDevice, h->copy_stream));
         RVCR_CUDA(cudaEventRecord(h->copy_events[c], h->copy_stream));
     }
     for (int64_t c = 0; c < nchunks; ++c) {
-        const int64_t off = c * chunk, m = std::min(chunk, n - off);
+        const int64_t off = coff[c], m = coff[c + 1] - off;
         RVCR_CUDA(cudaStreamWaitEvent(s, h->copy_events[c], 0));
         RVCR_TRY(coarse_dispatch(h, h->ws_q.as<float>() + (size_t)off * h->d, m, h->ws_assign.as<int32_t>() + off, nullptr, s));
     }
@@ -575,7 +592,10 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     RVCR_CUDA(cudaMemsetAsync(h->ws_misc.as<int32_t>() + 32, 0, 4 * 16, s));   // per-wave tickets
     float* out_dev = reinterpret_cast<float*>(pat.devicePointer);
     const bool trace = getenv("RVCR_HOST_TRACE") != nullptr;
-    int blend_ctas = 128;  // enough CTAs to keep PCIe busy; more of them slow the concurrent scan (LSU back-pressure)
+    // Enough CTAs to keep PCIe busy; more of them slow the concurrent scan (LSU back-pressure).  SM-issued writes to the
+    // mapped buffer top out at ~46-48 GB/s (cudaMemcpy D2H: 57 GB/s); a cp.async.bulk (TMA store) variant of the write-back
+    // was measured at the same rate (r01, 187-193 ms e2e for every CTA count / buffer depth tried) and was dropped.
+    int blend_ctas = 128;
     if (const char* e = getenv("RVCR_HOST_BLEND_CTAS")) blend_ctas = atoi(e);
     std::vector<cudaEvent_t> tev;
     if (trace) {
@@ -687,6 +707,11 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "tc_cluster")) {
         if (value != 1 && value != 2) return RVCR_ERR_INVALID;
         h->opt.tc_cluster = value;
+    } else if (!strcmp(key, "tc_resident")) {
+        if (value != 0 && value != 6 && value != 8 && value != 9 && value != 10) return RVCR_ERR_INVALID;
+        h->opt.tc_resident = value;
+    } else if (!strcmp(key, "fused_blend")) {
+        h->opt.fused_blend = value ? 1 : 0;
     } else if (!strcmp(key, "nan_on_zero_score")) {
         if (value != 1) {
             set_error("only the reference behaviour (NaN row on a zero score) is implemented");
@@ -708,6 +733,8 @@ int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out) {
     else if (!strcmp(key, "profile")) *value_out = h->opt.profile;
     else if (!strcmp(key, "tc_cluster")) *value_out = h->opt.tc_cluster;
     else if (!strcmp(key, "scan_impl")) *value_out = h->opt.scan_impl;
+    else if (!strcmp(key, "tc_resident")) *value_out = h->opt.tc_resident;
+    else if (!strcmp(key, "fused_blend")) *value_out = h->opt.fused_blend;
     else if (!strcmp(key, "coarse_tc_available")) *value_out = coarse_tc_available() ? 1 : 0;
     else {
         set_error("unknown option '%s'", key);

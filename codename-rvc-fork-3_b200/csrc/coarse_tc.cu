@@ -59,34 +59,50 @@ __device__ __forceinline__ void top_insert(float (&tv)[TOPT], int (&tj)[TOPT], f
     }
 }
 
-template <int CLUSTER>
+// NRES = k-blocks of the query operand (A) kept resident in shared memory for a whole work item (one m-block
+// against every centroid tile of its split); SB = stages of the centroid (B) ring; SA = slots for the A k-blocks
+// that are still streamed.  NRES = 0 streams everything (SA == SB, A and B of a k-block share a stage).  The streamed
+// k-blocks are spread evenly -- every P-th one (kb % P == P - 1), plus whatever exceeds the NRES resident slots --
+// so that a freed A slot is reused about P k-blocks later and its TMA load never waits for the tensor pipe.
+//
+// Why: with both operands streamed, each CTA pair pulls 64 KB through the L2 per 512 tensor cycles -- 9.5 KB/clk
+// chip-wide at full tensor rate, above the ~6.3 KB/clk the L2 slices deliver (ncu r01: lts 6.39 KB/clk, tensor pipe
+// 68 % active).  The A block of an item is reused by all of its ~354 centroid tiles, so pinning most of it in shared
+// memory cuts the L2 traffic to (NKB + streamed)/(2 NKB) of that and leaves the tensor pipe as the limiter.
+template <int CLUSTER, int NRES, int SB, int SA, int P>
 struct Cfg {
     static constexpr int LOAD_N = BLOCK_N / CLUSTER;                      // B rows loaded per CTA
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;                 // 16 KB
     static constexpr int B_BYTES = LOAD_N * BLOCK_K * 2;                  // 32 KB / 16 KB
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = CLUSTER == 1 ? 4 : 6;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
+    static constexpr int RES_BYTES = NRES * A_BYTES;
+    static constexpr int RING_BYTES = SB * B_BYTES + SA * A_BYTES;
+    static constexpr int SMEM_BYTES = RES_BYTES + RING_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
     static constexpr int UMMA_M = BLOCK_M * CLUSTER;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(NRES > 0 || SA == SB, "fully streamed: one A slot per B stage");
 };
 
 // grid = persistent CTAs (multiple of CLUSTER); work item = (m-block of 128*CLUSTER queries, split
 // of the centroid tiles); item i is taken by cluster (i mod nclusters).
-template <int CLUSTER>
+template <int CLUSTER, int NRES, int SB, int SA, int P>
 __global__ void __launch_bounds__(THREADS, 1)
 coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const float* __restrict__ cn, int num_mblocks, int num_ntiles, int nsplit, int tiles_per_split,
                  int num_kblocks, float* __restrict__ topv, int* __restrict__ topj) {
-    using C = Cfg<CLUSTER>;
+    using C = Cfg<CLUSTER, NRES, SB, SA, P>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-    uint64_t* full_bar = bars;                      // [STAGES]  TMA -> MMA       (leader CTA's are used)
-    uint64_t* empty_bar = bars + C::STAGES;         // [STAGES]  MMA -> TMA       (each CTA its own)
-    uint64_t* tmem_full_bar = bars + 2 * C::STAGES; // [2]       MMA -> epilogue  (each CTA its own)
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]       epilogue -> MMA  (leader CTA's are used)
+    uint8_t* sAres = smem;                               // NRES resident A k-blocks
+    uint8_t* sB = smem + C::RES_BYTES;                   // SB stages
+    uint8_t* sA = sB + SB * C::B_BYTES;                  // SA slots (streamed A k-blocks)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RES_BYTES + C::RING_BYTES);
+    uint64_t* full_bar = bars;                      // [SB]  TMA -> MMA       (leader CTA's are used)
+    uint64_t* empty_bar = full_bar + SB;            // [SB]  MMA -> TMA       (each CTA its own)
+    uint64_t* aempty_bar = empty_bar + SB;          // [SA]  MMA -> TMA: streamed A slot free (each CTA its own)
+    uint64_t* ares_full_bar = aempty_bar + SA;      // [1]   TMA -> MMA: resident A loaded (leader CTA's is used)
+    uint64_t* ares_empty_bar = ares_full_bar + 1;   // [1]   MMA -> TMA: the item's MMAs are complete (each CTA its own)
+    uint64_t* tmem_full_bar = ares_empty_bar + 1;   // [2]   MMA -> epilogue  (each CTA its own)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]   epilogue -> MMA  (leader CTA's are used)
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
@@ -96,6 +112,8 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int cluster_id = blockIdx.x / CLUSTER;
     const int nclusters = gridDim.x / CLUSTER;
     const int nitems = num_mblocks * nsplit;
+    // k-block kb is streamed when it is every P-th one or the resident slots are used up; else it lives in slot kb - kb / P
+    auto is_streamed = [](int kb) { return NRES == 0 || kb % P == P - 1 || kb - kb / P >= NRES; };
 
     if constexpr (CLUSTER > 1) cluster_sync_all();
     if (warp == 0 && lane == 0) {
@@ -103,10 +121,13 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         prefetch_tmap(&tmap_b);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < C::STAGES; ++i) {
+        for (int i = 0; i < SB; ++i) {
             mbar_init(&full_bar[i], CLUSTER);   // one arrive per CTA's producer (+ tx bytes)
             mbar_init(&empty_bar[i], 1);        // one tcgen05.commit
         }
+        for (int i = 0; i < SA; ++i) mbar_init(&aempty_bar[i], 1);
+        mbar_init(ares_full_bar, CLUSTER);
+        mbar_init(ares_empty_bar, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);                // one tcgen05.commit
             mbar_init(&tmem_empty_bar[i], CLUSTER * 128);   // every epilogue thread of the pair
@@ -126,27 +147,50 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // an ELECT + R2UR.BROADCAST waterfall (~15 slow instructions per MMA).
     if (warp == 0) {
         // ================================ TMA producer =================================
+        const uint32_t sAres_addr = tc::warp_uniform(smem_u32(sAres));
         const uint32_t sA_addr = tc::warp_uniform(smem_u32(sA)), sB_addr = tc::warp_uniform(smem_u32(sB));
         const uint32_t full_addr = tc::warp_uniform(smem_u32(full_bar));
-        uint32_t stage = 0, phase = 0;
-        for (int item = cluster_id; item < nitems; item += nclusters) {
+        const uint32_t ares_full_addr = tc::warp_uniform(smem_u32(ares_full_bar));
+        uint32_t stage = 0, phase = 0, astage = 0, aphase = 0, item_cnt = 0;
+        for (int item = cluster_id; item < nitems; item += nclusters, ++item_cnt) {
             const int mb = item / nsplit, sp = item - mb * nsplit;
             const int m0 = mb * (BLOCK_M * CLUSTER) + (int)cta_rank * BLOCK_M;
             const int t0 = sp * tiles_per_split;
             const int t1 = min(t0 + tiles_per_split, num_ntiles);
+            if (NRES > 0) {
+                // the previous item's MMAs no longer read the resident block
+                mbar_wait_warp(ares_empty_bar, (item_cnt & 1) ^ 1, lane);
+                if (elect_one()) {
+                    int nres = 0;
+                    for (int kb = 0; kb < num_kblocks; ++kb)
+                        if (!is_streamed(kb)) {
+                            tma_load_2d_a<CLUSTER>(&tmap_a, ares_full_addr, sAres_addr + (kb - kb / P) * C::A_BYTES, kb * BLOCK_K, m0);
+                            ++nres;
+                        }
+                    if (leader) mbar_arrive_expect_tx_addr(ares_full_addr, (uint32_t)nres * C::A_BYTES * CLUSTER);
+                    else mbar_arrive_cluster_addr(ares_full_addr, 0);
+                }
+                __syncwarp();
+            }
             for (int t = t0; t < t1; ++t) {
                 const int n0 = t * BLOCK_N + (int)cta_rank * C::LOAD_N;
                 for (int kb = 0; kb < num_kblocks; ++kb) {
+                    const bool streamed = is_streamed(kb);     // uniform
                     mbar_wait_warp(&empty_bar[stage], phase ^ 1, lane);
+                    if (NRES > 0 && streamed) mbar_wait_warp(&aempty_bar[astage], aphase ^ 1, lane);
                     if (elect_one()) {
                         const uint32_t fb = full_addr + stage * 8;
-                        tma_load_2d_a<CLUSTER>(&tmap_a, fb, sA_addr + stage * C::A_BYTES, kb * BLOCK_K, m0);
+                        const uint32_t aslot = NRES > 0 ? astage : stage;
+                        if (streamed) tma_load_2d_a<CLUSTER>(&tmap_a, fb, sA_addr + aslot * C::A_BYTES, kb * BLOCK_K, m0);
                         tma_load_2d_a<CLUSTER>(&tmap_b, fb, sB_addr + stage * C::B_BYTES, kb * BLOCK_K, n0);
-                        if (leader) mbar_arrive_expect_tx_addr(fb, C::STAGE_BYTES * CLUSTER);
+                        if (leader) mbar_arrive_expect_tx_addr(fb, (uint32_t)(C::B_BYTES + (streamed ? C::A_BYTES : 0)) * CLUSTER);
                         else mbar_arrive_cluster_addr(fb, 0);
                     }
                     __syncwarp();
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == SB) { stage = 0; phase ^= 1; }
+                    if (NRES > 0 && streamed) {
+                        if (++astage == SA) { astage = 0; aphase ^= 1; }
+                    }
                 }
             }
         }
@@ -154,23 +198,32 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // ================================ MMA issuer ===================================
         if (leader) {
             constexpr uint32_t idesc = make_idesc(C::UMMA_M, BLOCK_N);
+            const uint32_t sAres_addr = tc::warp_uniform(smem_u32(sAres));
             const uint32_t sA_addr = tc::warp_uniform(smem_u32(sA)), sB_addr = tc::warp_uniform(smem_u32(sB));
             const uint32_t empty_addr = tc::warp_uniform(smem_u32(empty_bar)), tfull_addr = tc::warp_uniform(smem_u32(tmem_full_bar));
+            const uint32_t aempty_addr = tc::warp_uniform(smem_u32(aempty_bar));
+            const uint32_t ares_empty_addr = tc::warp_uniform(smem_u32(ares_empty_bar));
             const uint32_t tbase = tc::warp_uniform(tmem_base);
-            uint32_t stage = 0, phase = 0, tile_cnt = 0;
-            for (int item = cluster_id; item < nitems; item += nclusters) {
+            uint32_t stage = 0, phase = 0, astage = 0, tile_cnt = 0, item_cnt = 0;
+            for (int item = cluster_id; item < nitems; item += nclusters, ++item_cnt) {
                 const int sp = item % nsplit;
                 const int t0 = sp * tiles_per_split;
                 const int t1 = min(t0 + tiles_per_split, num_ntiles);
+                if (NRES > 0) {
+                    mbar_wait_warp(ares_full_bar, item_cnt & 1, lane);     // this item's resident A block landed
+                    tc_fence_after();
+                }
                 for (int t = t0; t < t1; ++t, ++tile_cnt) {
                     const uint32_t as = tile_cnt & 1, aphase = (tile_cnt >> 1) & 1;
                     mbar_wait_warp(&tmem_empty_bar[as], aphase ^ 1, lane);   // epilogue drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tbase + as * BLOCK_N;
                     for (int kb = 0; kb < num_kblocks; ++kb) {
+                        const bool streamed = is_streamed(kb);     // uniform
                         mbar_wait_warp(&full_bar[stage], phase, lane);
                         tc_fence_after();
-                        const uint64_t da = make_smem_desc(sA_addr + stage * C::A_BYTES);
+                        const uint32_t aslot = NRES > 0 ? astage : stage;
+                        const uint64_t da = make_smem_desc(streamed ? sA_addr + aslot * C::A_BYTES : sAres_addr + (kb - kb / P) * C::A_BYTES);
                         const uint64_t db = make_smem_desc(sB_addr + stage * C::B_BYTES);
                         if (elect_one()) {
 #pragma unroll
@@ -180,11 +233,19 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                                    (kb > 0 || k > 0) ? 1u : 0u);
                             }
                             umma_commit_a<CLUSTER>(empty_addr + stage * 8);   // frees the smem stage when the MMAs retire
+                            if (NRES > 0 && streamed) umma_commit_a<CLUSTER>(aempty_addr + astage * 8);
                             if (kb == num_kblocks - 1) umma_commit_a<CLUSTER>(tfull_addr + as * 8);
                         }
                         __syncwarp();
-                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == SB) { stage = 0; phase ^= 1; }
+                        if (NRES > 0 && streamed) {
+                            if (++astage == SA) astage = 0;
+                        }
                     }
+                }
+                if (NRES > 0) {
+                    if (elect_one()) umma_commit_a<CLUSTER>(ares_empty_addr);   // resident block may be overwritten
+                    __syncwarp();
                 }
             }
         }
@@ -487,13 +548,14 @@ int ensure_centroid_operands(rvcr_index* h, int split, cudaStream_t s) {
     return RVCR_OK;
 }
 
-template <int CLUSTER>
+template <int CLUSTER, int NRES, int SB, int SA, int P>
 int launch_tc(rvcr_index* h, const CUtensorMap& ta, const CUtensorMap& tb, int num_mblocks, int num_ntiles, int nsplit,
               int tps, int nkb, float* topv, int* topj, cudaStream_t s) {
-    using C = tc::Cfg<CLUSTER>;
+    using C = tc::Cfg<CLUSTER, NRES, SB, SA, P>;
     static bool attr = false;
     if (!attr) {
-        RVCR_CUDA(cudaFuncSetAttribute(tc::coarse_tc_kernel<CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        RVCR_CUDA(cudaFuncSetAttribute(tc::coarse_tc_kernel<CLUSTER, NRES, SB, SA, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       C::SMEM_BYTES));
         attr = true;
     }
     const int nitems = num_mblocks * nsplit;
@@ -511,8 +573,8 @@ int launch_tc(rvcr_index* h, const CUtensorMap& ta, const CUtensorMap& tb, int n
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    RVCR_CUDA(cudaLaunchKernelEx(&cfg, tc::coarse_tc_kernel<CLUSTER>, ta, tb, (const float*)h->cent_norm, num_mblocks,
-                                 num_ntiles, nsplit, tps, nkb, topv, topj));
+    RVCR_CUDA(cudaLaunchKernelEx(&cfg, tc::coarse_tc_kernel<CLUSTER, NRES, SB, SA, P>, ta, tb, (const float*)h->cent_norm,
+                                 num_mblocks, num_ntiles, nsplit, tps, nkb, topv, topj));
     return RVCR_OK;
 }
 
@@ -569,12 +631,21 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
     RVCR_TRY(make_tmap(&tb, h->cent_bf16, h->cent_pad, kdim, tc::BLOCK_N / cluster));
     {
         PhaseTimer pt(h, RVCR_PHASE_COARSE_MAIN, s);
-        if (cluster == 2)
-            RVCR_TRY(launch_tc<2>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, kdim / tc::BLOCK_K, h->ws_tc2.as<float>(),
-                                  h->ws_tc3.as<int>(), s));
-        else
-            RVCR_TRY(launch_tc<1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, kdim / tc::BLOCK_K, h->ws_tc2.as<float>(),
-                                  h->ws_tc3.as<int>(), s));
+        float* tv = h->ws_tc2.as<float>();
+        int* tj = h->ws_tc3.as<int>();
+        const int nkb = kdim / tc::BLOCK_K;
+        // option "tc_resident": A k-blocks pinned in shared memory (0 = stream both operands, the r01 v1 kernel)
+        const int64_t res = h->opt.tc_resident;
+        if (cluster == 2) {
+            if (res == 0) RVCR_TRY((launch_tc<2, 0, 6, 6, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            else if (res == 6) RVCR_TRY((launch_tc<2, 6, 5, 3, 2>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            else if (res == 8) RVCR_TRY((launch_tc<2, 8, 4, 2, 3>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            else if (res == 9) RVCR_TRY((launch_tc<2, 9, 4, 1, 4>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            else RVCR_TRY((launch_tc<2, 10, 3, 1, 6>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+        } else {
+            if (res == 0) RVCR_TRY((launch_tc<1, 0, 4, 4, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            else RVCR_TRY((launch_tc<1, 8, 2, 2, 3>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+        }
         count_launch(h);
     }
     *topv_out = h->ws_tc2.as<float>();

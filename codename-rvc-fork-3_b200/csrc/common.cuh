@@ -64,6 +64,8 @@ struct Options {
     int64_t scan_impl = 5;    // 5 tcgen05 tf32 + exact re-check (default); exact FFMA scans: 1 scalar 8-lane, 2 packed f32x2
                               // TQx4, 3 same with 16 warps, 4 packed TQx8 tile
     int64_t tc_cluster = 2;   // tcgen05 path: 1 = one CTA per SM, 2 = CTA pairs (cta_group::2)
+    int64_t fused_blend = 1;  // scan_impl 5: re-check kernel also does the gather + weights + blend
+    int64_t tc_resident = 9;  // coarse tcgen05 kernel: query-operand k-blocks pinned in shared memory per work item (0, 6, 8, 9, 10)
 };
 
 }  // namespace rvcr
@@ -129,6 +131,14 @@ struct rvcr_index {
     // optional per-phase CUDA-event timing (option "profile"), read back by rvcr_get_phase_ms
     cudaEvent_t pev[RVCR_NUM_PHASES][2] = {};
     bool pev_used[RVCR_NUM_PHASES] = {};
+
+    // set by search_device around the scan when the caller wants blended rows and option "fused_blend" is on; a scan
+    // implementation that also performed the tail (scan_tc.cu) sets `done`, otherwise gather_blend runs afterwards
+    struct FusedTail {
+        bool active = false, done = false;
+        float* out = nullptr;
+        float r32 = 0.f, omr32 = 0.f;
+    } fuse;
 
     bool tc_counters_dirty = false;
     rvcr::Options opt;

@@ -540,11 +540,65 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
 // sequential over the row exactly like fvec_L2sqr -- then top-8 by (distance, position).
 constexpr int RC_WARPS = 4;
 
+// pipeline.py:500-506 for one query whose sorted top-8 sits in lanes 0..7 of the warp (td, tp; tp == INT_MAX = pad):
+// weights exactly as blend.cu computes them (divide, square, pairwise row sum, divide); every lane returns the
+// normalised weight / gather position of neighbour `lane & 7`.
+struct BlendArgs {
+    float* out;             // blended rows are written to out + qi * d (may alias the queries: in place)
+    int64_t last_row_pos;   // numpy's big_npy[-1] for (FLT_MAX, -1) padding
+    float r32, omr32;
+};
+
+__device__ __forceinline__ void blend_weights(float td, int tp, int lane, int64_t last_row_pos, float& wn, int& spos) {
+    float w = 0.f;
+    int pos = -1;
+    if (lane < RVCR_K) {
+        const bool pad = tp == 0x7fffffff;
+        const float score = pad ? RVCR_FLT_MAX : td;
+        const float inv = __fdiv_rn(1.0f, score);
+        w = __fmul_rn(inv, inv);
+        pos = pad ? -1 : tp;
+    }
+    float sum = __fadd_rn(w, __shfl_xor_sync(0xffffffffu, w, 1));
+    sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 2));
+    sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, 4));
+    wn = __fdiv_rn(w, sum);
+    spos = pos < 0 ? (int)last_row_pos : pos;
+}
+
+// out[c] = fl(fl(acc * r32) + fl(omr32 * f)), acc = products rounded then summed k = 0..7 (blend.cu's contract)
+__device__ __forceinline__ float4 blend_vec(const float4 (&v)[RVCR_K], const float (&wk)[RVCR_K], const float4 f, float r32,
+                                            float omr32) {
+    float4 acc;
+    acc.x = __fmul_rn(v[0].x, wk[0]);
+    acc.y = __fmul_rn(v[0].y, wk[0]);
+    acc.z = __fmul_rn(v[0].z, wk[0]);
+    acc.w = __fmul_rn(v[0].w, wk[0]);
+#pragma unroll
+    for (int k = 1; k < RVCR_K; ++k) {
+        acc.x = __fadd_rn(acc.x, __fmul_rn(v[k].x, wk[k]));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(v[k].y, wk[k]));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(v[k].z, wk[k]));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(v[k].w, wk[k]));
+    }
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(acc.x, r32), __fmul_rn(omr32, f.x));
+    o.y = __fadd_rn(__fmul_rn(acc.y, r32), __fmul_rn(omr32, f.y));
+    o.z = __fadd_rn(__fmul_rn(acc.z, r32), __fmul_rn(omr32, f.z));
+    o.w = __fadd_rn(__fmul_rn(acc.w, r32), __fmul_rn(omr32, f.w));
+    return o;
+}
+
+// BLEND: the warp that has just found a query's exact top-8 also gathers those 8 rows (it read them a moment ago:
+// L1 / L2 hits instead of a second trip to HBM), applies the 1/score^2 weights and the index_rate blend and writes
+// the output row -- rvc/infer/pipeline.py:500-506 without a separate gather kernel.
+template <bool BLEND>
 __global__ void __launch_bounds__(RC_WARPS * 32)
-scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qorder, const int32_t* __restrict__ items,
-                    const int32_t* __restrict__ nitems_ptr, int item_begin, int item_end, int64_t n, int d,
-                    const float* __restrict__ vecs, const int64_t* __restrict__ ids, const int32_t* __restrict__ cand,
-                    const int32_t* __restrict__ candcnt, float* __restrict__ D, int32_t* __restrict__ P, int64_t* __restrict__ I) {
+scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qorder, const uint32_t* __restrict__ keys,
+                    uint32_t nlist, const int32_t* __restrict__ items, const int32_t* __restrict__ nitems_ptr, int item_begin,
+                    int item_end, int64_t n, int d, const float* __restrict__ vecs, const int64_t* __restrict__ ids,
+                    const int32_t* __restrict__ cand, const int32_t* __restrict__ candcnt, float* __restrict__ D,
+                    int32_t* __restrict__ P, int64_t* __restrict__ I, BlendArgs ba) {
     extern __shared__ __align__(16) float rc_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* sq = rc_smem + (size_t)w * d;
@@ -554,16 +608,19 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
     const int h = lane & 1;
     const int nvec = d >> 2;
     for (int64_t p = first + (int64_t)blockIdx.x * RC_WARPS + w; p < last; p += (int64_t)gridDim.x * RC_WARPS) {
+        if (keys[p] == nlist + 1u) continue;   // another shard's query (sorted last; forms no work item)
         const int64_t qi = qorder[p];
         const int nc = candcnt[qi];
         if (nc < 0) continue;   // overflowed: the exact fallback kernel answers this query
         float td = RVCR_FLT_MAX;
         int tp = 0x7fffffff;
-        if (nc > 0) {
+        if (nc > 0 || BLEND) {
             __syncwarp();
             const float4* q4 = reinterpret_cast<const float4*>(q + qi * d);
             for (int c = lane; c < nvec; c += 32) reinterpret_cast<float4*>(sq)[c] = q4[c];
             __syncwarp();
+        }
+        if (nc > 0) {
             for (int base = 0; base < nc; base += 16) {
                 const int c = base + (lane >> 1);
                 const bool have = c < nc;
@@ -596,19 +653,42 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
             P[qi * RVCR_K + lane] = pad ? -1 : tp;
             if (I) I[qi * RVCR_K + lane] = pad ? (int64_t)-1 : ids[tp];
         }
+        if (BLEND) {
+            float wn;
+            int spos;
+            blend_weights(td, tp, lane, ba.last_row_pos, wn, spos);
+            float wk[RVCR_K];
+            const float4* rows[RVCR_K];
+#pragma unroll
+            for (int k = 0; k < RVCR_K; ++k) {
+                wk[k] = __shfl_sync(0xffffffffu, wn, k);
+                const int pk = __shfl_sync(0xffffffffu, spos, k);
+                rows[k] = pk >= 0 ? reinterpret_cast<const float4*>(vecs + (int64_t)pk * d) : nullptr;
+            }
+            float4* o4 = reinterpret_cast<float4*>(ba.out + qi * d);
+            for (int c = lane; c < nvec; c += 32) {
+                float4 v[RVCR_K];
+#pragma unroll
+                for (int k = 0; k < RVCR_K; ++k) v[k] = rows[k] ? __ldg(rows[k] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                o4[c] = blend_vec(v, wk, reinterpret_cast<const float4*>(sq)[c], ba.r32, ba.omr32);
+            }
+        }
     }
 }
 
 // Brute-force exact scan of one list for the queries the tensor-core pass could not bound (rare): one CTA
 // per query, 8 lanes per row (canonical order), 32 rows per step.
+template <bool BLEND>
 __global__ void __launch_bounds__(256)
 scan_exact_fallback_kernel(const float* __restrict__ q, const int32_t* __restrict__ qorder, const uint32_t* __restrict__ keys,
                            const int32_t* __restrict__ fb_list, const int32_t* __restrict__ fb_count, uint32_t nlist, int d,
                            const float* __restrict__ vecs, const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
-                           float* __restrict__ D, int32_t* __restrict__ P, int64_t* __restrict__ I) {
+                           float* __restrict__ D, int32_t* __restrict__ P, int64_t* __restrict__ I, BlendArgs ba) {
     extern __shared__ __align__(16) float fb_smem[];
     float* sq = fb_smem;          // d
     float* sd = fb_smem + d;      // 32
+    float* sw = fb_smem + d + 32; // 8 weights
+    int* sp = reinterpret_cast<int*>(fb_smem + d + 40);   // 8 gather positions
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int l8 = tid & 7, grp = tid >> 3;   // 32 groups of 8 lanes
     const int nfb = *fb_count;
@@ -650,6 +730,32 @@ scan_exact_fallback_kernel(const float* __restrict__ q, const int32_t* __restric
             D[qi * RVCR_K + lane] = pad ? RVCR_FLT_MAX : td;
             P[qi * RVCR_K + lane] = pad ? -1 : tp;
             if (I) I[qi * RVCR_K + lane] = pad ? (int64_t)-1 : ids[tp];
+        }
+        if (BLEND) {
+            if (w == 0) {
+                float wn;
+                int spos;
+                blend_weights(td, tp, lane, ba.last_row_pos, wn, spos);
+                if (lane < RVCR_K) {
+                    sw[lane] = wn;
+                    sp[lane] = spos;
+                }
+            }
+            __syncthreads();
+            float wk[RVCR_K];
+            const float4* rows[RVCR_K];
+#pragma unroll
+            for (int k = 0; k < RVCR_K; ++k) {
+                wk[k] = sw[k];
+                rows[k] = sp[k] >= 0 ? reinterpret_cast<const float4*>(vecs + (int64_t)sp[k] * d) : nullptr;
+            }
+            float4* o4 = reinterpret_cast<float4*>(ba.out + qi * d);
+            for (int c = tid; c < (d >> 2); c += 256) {
+                float4 v[RVCR_K];
+#pragma unroll
+                for (int k = 0; k < RVCR_K; ++k) v[k] = rows[k] ? __ldg(rows[k] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                o4[c] = blend_vec(v, wk, reinterpret_cast<const float4*>(sq)[c], ba.r32, ba.omr32);
+            }
         }
     }
 }
@@ -782,25 +888,38 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
         h->ws_fb.as<int32_t>(), fb_count, reinterpret_cast<unsigned long long*>(h->ws_misc.as<int32_t>() + 48),
         h->ws_cstage.as<float2>(), getenv("RVCR_STC_FLAGS") ? atoi(getenv("RVCR_STC_FLAGS")) : 0);
     RVCR_CHECK_LAUNCH();
+    // fused tail (search_device sets h->fuse for rvcr_retrieve_blend*): the re-check / fallback kernels also blend
+    const bool blend = h->fuse.active;
+    BlendArgs ba{h->fuse.out, h->last_row_pos, h->fuse.r32, h->fuse.omr32};
     {
         PhaseTimer pt(h, RVCR_PHASE_SCAN_RECHECK, s);
-        const size_t rsm = (size_t)RC_WARPS * d * 4;
-        int64_t rgrid = (int64_t)h->num_sms * 8;
-        if (rgrid * RC_WARPS > n) rgrid = (n + RC_WARPS - 1) / RC_WARPS;
-        scan_recheck_kernel<<<(unsigned)rgrid, RC_WARPS * 32, rsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_items.as<int32_t>(),
-                                                                        h->ws_misc.as<int32_t>(), item_begin, item_end, n, d, h->vecs,
-                                                                        h->ids, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(), D,
-                                                                        P, I);
+        // One warp per query, 32 warps per SM.  A variant that staged the candidate rows in shared memory with
+        // cp.async.bulk (so the fused gather never left the SM) was measured slower (r01: 14.2 vs 8.1 ms at C5 -- with
+        // 52 KB per query only 4 warps fit per SM, and the per-query chain header -> copies -> distances -> top-8 ->
+        // blend is serial inside a warp) and was removed.
+        {
+            const size_t rsm = (size_t)RC_WARPS * d * 4;
+            int per_sm = 8;
+            if (const char* e = getenv("RVCR_RC_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // tuning knob
+            int64_t rgrid = (int64_t)h->num_sms * per_sm;
+            if (rgrid * RC_WARPS > n) rgrid = (n + RC_WARPS - 1) / RC_WARPS;
+            auto kern = blend ? scan_recheck_kernel<true> : scan_recheck_kernel<false>;
+            kern<<<(unsigned)rgrid, RC_WARPS * 32, rsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), (uint32_t)h->nlist,
+                                                             h->ws_items.as<int32_t>(), h->ws_misc.as<int32_t>(), item_begin, item_end, n,
+                                                             d, h->vecs, h->ids, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
+                                                             D, P, I, ba);
+        }
         RVCR_CHECK_LAUNCH();
     }
     {
         PhaseTimer pt(h, RVCR_PHASE_SCAN_FALLBACK, s);
-        const size_t fsm = (size_t)(d + 32) * 4;
-        scan_exact_fallback_kernel<<<h->num_sms * 2, 256, fsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(),
-                                                                    h->ws_fb.as<int32_t>(), fb_count, (uint32_t)h->nlist, d, h->vecs,
-                                                                    h->ids, h->offsets, D, P, I);
+        const size_t fsm = (size_t)(d + 48) * 4;
+        auto kern = blend ? scan_exact_fallback_kernel<true> : scan_exact_fallback_kernel<false>;
+        kern<<<h->num_sms * 2, 256, fsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), h->ws_fb.as<int32_t>(), fb_count,
+                                              (uint32_t)h->nlist, d, h->vecs, h->ids, h->offsets, D, P, I, ba);
         RVCR_CHECK_LAUNCH();
     }
+    if (blend) h->fuse.done = true;
     // running total of fallback queries (read back lazily by rvcr_get_stats)
     h->scan_fb_dirty = true;
     count_launch(h, fill ? 4 : 3);

@@ -116,3 +116,26 @@ def test_tc_small_and_ragged_shapes(rvcr):
             index.set_option("tc_cluster", cluster)
             l_tc, d_tc = [t.cpu().numpy() for t in index.assign(qd)]
             assert np.array_equal(l_tc, l_ex) and np.array_equal(d_tc, d_ex), (nq, nlist, d, cluster)
+
+
+@pytest.mark.parametrize("d", [768, 256, 1024])
+def test_tc_resident_query_blocks(rvcr, d):
+    """option tc_resident: 0 streams both operands; 8 / 9 / 10 pin that many 64-element k-blocks of the query
+    operand in shared memory (d = 256: everything resident; d = 1024: 16 k-blocks, 6-8 still streamed).  Several
+    work items per CTA pair (resident block reloaded), identical assignments and distances every way."""
+    import torch
+    rng = np.random.default_rng(5)
+    nq, nlist = 128 * 2 * 74 * 2 + 77, 700          # > 2 m-blocks per CTA pair on 148 SMs
+    q, cent = clustered_problem(rng, nq, nlist, d)
+    index = rvcr.index_factory(d, f"IVF{nlist},Flat")
+    index.set_centroids(cent)
+    qd = torch.from_numpy(q).cuda()
+    index.set_option("coarse_mode", 1)
+    l_ex, d_ex = [t.cpu().numpy() for t in index.assign(qd)]
+    index.set_option("coarse_mode", 2)
+    for cluster in (2, 1):
+        index.set_option("tc_cluster", cluster)
+        for res in (0, 6, 8, 9, 10):
+            index.set_option("tc_resident", res)
+            l_tc, d_tc = [t.cpu().numpy() for t in index.assign(qd)]
+            assert np.array_equal(l_tc, l_ex) and np.array_equal(d_tc, d_ex), (d, cluster, res)

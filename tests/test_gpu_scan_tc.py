@@ -99,3 +99,54 @@ def test_scan_tc_blend_and_host_waves(rvcr, oracle):
     hp = torch.from_numpy(pr.q.copy()).pin_memory()
     index.retrieve_blend_host_(hp.numpy(), 0.75)
     assert np.array_equal(hp.numpy(), want, equal_nan=True)
+
+
+def test_fused_tail_equals_separate_blend_kernel(rvcr, oracle):
+    """option fused_blend: the re-check / fallback kernels also do pipeline.py:500-506; both settings must be
+    bit-identical to the separate gather_blend kernel and to the oracle -- on ordinary lists, on the overflow
+    fallback (identical rows), on 40 near-duplicates (3 candidate passes), on short lists (padding -> big_npy[-1], weight 0), on an empty probe (NaN
+    row), an exact-match query (NaN row) and a NaN query (assignment -1)."""
+    import torch
+    rng = np.random.default_rng(11)
+    d = 768
+    cent = (rng.standard_normal((6, d)) * 2).astype(np.float32)
+    a = np.repeat(cent[0:1] + np.float32(0.05), 300, axis=0)                       # overflow -> exact fallback
+    b = cent[1] + (rng.standard_normal((5, d)) * 0.14).astype(np.float32)         # short list: 3 pads
+    c = cent[2] + (rng.standard_normal((700, d)) * 0.14).astype(np.float32)       # two chunks
+    e = cent[4] + (rng.standard_normal((64, d)) * 0.14).astype(np.float32)        # list 3 stays empty
+    g = cent[5] + (rng.standard_normal((40, d)) * 1e-4).astype(np.float32)        # 40 candidates inside the margin
+    x = np.concatenate([a, b, c, e, g]).astype(np.float32)
+    index = _build(rvcr, x, cent)
+    oidx = oracle.OracleIndex.from_vectors(x, cent)
+    q = np.concatenate([cent[0:1] + np.float32(0.01), cent[1:2] + np.float32(0.01), c[:40] + np.float32(0.003),
+                        cent[3:4], c[100:101], e[:30] + np.float32(0.002), cent[5:6] + np.float32(0.01),
+                        cent[2:3]]).astype(np.float32)
+    q[-1, 7] = np.nan
+    Do, Io = oidx.search(q, k=8)
+    with np.errstate(all="ignore"):
+        want = oracle.tail(Do, Io, x, 0.3, q)
+    assert np.isnan(want[42]).all() and np.isnan(want[43]).all()           # empty probe, exact match
+    for fused in (1, 0):
+        index.set_option("fused_blend", fused)
+        f = torch.from_numpy(q.copy()).cuda()
+        _, D, I = index.retrieve_blend_(f, 0.3, want_neighbours=True)
+        assert np.array_equal(I.cpu().numpy(), Io) and np.array_equal(D.cpu().numpy(), Do), fused
+        assert np.array_equal(f.cpu().numpy(), want, equal_nan=True), fused
+        D2, I2 = index.search(q, k=8)
+        assert np.array_equal(I2, Io) and np.array_equal(D2, Do), fused
+
+
+def test_fused_tail_v1_256(rvcr, oracle):
+    """d = 256, i.i.d. data with many short / empty lists, index_rate 1.0 through the fused tail"""
+    import torch
+    synth = import_module("codename-rvc-fork-3_b200.synth")
+    n, d, nq, nlist = 30_000, 256, 3_000, 1500
+    pr = synth.make_host_problem(n, d, nq, nlist, iid=True)
+    index = _build(rvcr, pr.x, pr.centroids)
+    oidx = oracle.OracleIndex.from_vectors(pr.x, pr.centroids)
+    Do, Io = oidx.search(pr.q, k=8)
+    with np.errstate(all="ignore"):
+        want = oracle.tail(Do, Io, pr.x, 1.0, pr.q)
+    f = torch.from_numpy(pr.q.copy()).cuda()
+    index.retrieve_blend_(f, 1.0)
+    assert np.array_equal(f.cpu().numpy(), want, equal_nan=True)
