@@ -353,10 +353,7 @@ def main():
             if sh is None:
                 index.retrieve_blend_host_(host.numpy(), INDEX_RATE)     # H2D, search+blend, D2H, sync
             else:
-                b = host.to(dev, non_blocking=True)
-                sh.retrieve_blend_(b, INDEX_RATE)
-                host.copy_(b, non_blocking=True)
-                torch.cuda.synchronize()
+                sh.retrieve_blend_host_(host, INDEX_RATE)                # chunked H2D under the coarse step, D2H, sync
             barrier()
             if it > 0:
                 times.append(time.perf_counter() - t0)
@@ -367,7 +364,7 @@ def main():
             sec = float(t.item())
         e2e = {"value": nq / sec, "unit": UNIT, "h2d_bytes_per_step": int(nq) * d * 4, "d2h_bytes_per_step": int(nq) * d * 4,
                "ms_per_step": sec * 1e3, "api": "IndexIVFFlat.retrieve_blend_host_ (rvcr_retrieve_blend_host), pinned host buffers"
-               if sh is None else "ShardedIndex.retrieve_blend_ with pinned host buffers per rank"}
+               if sh is None else "ShardedIndex.retrieve_blend_host_, pinned host buffers per rank"}
         del host, src
 
     # ---- CPU baseline on rank 0 (N = 1 only): bounded sample of the same workload ------------------

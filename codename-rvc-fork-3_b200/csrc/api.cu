@@ -547,16 +547,36 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     RVCR_TRY(stream_enter(h, s));
     for (int i = 0; i < RVCR_NUM_PHASES; ++i) h->pev_used[i] = false;
     char* dq = reinterpret_cast<char*>(h->ws_q.p);
+    const bool trace = getenv("RVCR_HOST_TRACE") != nullptr;
+    std::vector<cudaEvent_t> cev;   // trace only: [0] start, [1 + 2c] chunk c copied, [2 + 2c] chunk c assigned
+    if (trace) {
+        cev.resize(1 + 2 * (size_t)nchunks);
+        for (auto& e : cev) cudaEventCreate(&e);
+        cudaEventRecord(cev[0], h->copy_stream);
+    }
     for (int64_t c = 0; c < nchunks; ++c) {
         const int64_t off = coff[c], m = coff[c + 1] - off;
         RVCR_CUDA(cudaMemcpyAsync(dq + (size_t)off * rowb, reinterpret_cast<const char*>(feats_host) + (size_t)off * rowb,
                                   (size_t)m * rowb, cudaMemcpyHostToDevice, h->copy_stream));
         RVCR_CUDA(cudaEventRecord(h->copy_events[c], h->copy_stream));
+        if (trace) cudaEventRecord(cev[1 + 2 * c], h->copy_stream);
     }
     for (int64_t c = 0; c < nchunks; ++c) {
         const int64_t off = coff[c], m = coff[c + 1] - off;
         RVCR_CUDA(cudaStreamWaitEvent(s, h->copy_events[c], 0));
         RVCR_TRY(coarse_dispatch(h, h->ws_q.as<float>() + (size_t)off * h->d, m, h->ws_assign.as<int32_t>() + off, nullptr, s));
+        if (trace) cudaEventRecord(cev[2 + 2 * c], s);
+    }
+    if (trace) {
+        cudaStreamSynchronize(s);
+        for (int64_t c = 0; c < nchunks; ++c) {
+            float a, b;
+            cudaEventElapsedTime(&a, cev[0], cev[1 + 2 * c]);
+            cudaEventElapsedTime(&b, cev[0], cev[2 + 2 * c]);
+            fprintf(stderr, "[rvcr trace] chunk %lld (%lld rows): copied %.2f ms, assigned %.2f ms\n", (long long)c,
+                    (long long)(coff[c + 1] - coff[c]), a, b);
+        }
+        for (auto& e : cev) cudaEventDestroy(e);
     }
     // Device -> host: when the caller's buffer is pinned (device-mapped), the lists are scanned in waves of
     // work items and each wave's blended rows are written by the blend kernel straight into the host buffer
@@ -591,7 +611,6 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     }
     RVCR_CUDA(cudaMemsetAsync(h->ws_misc.as<int32_t>() + 32, 0, 4 * 16, s));   // per-wave tickets
     float* out_dev = reinterpret_cast<float*>(pat.devicePointer);
-    const bool trace = getenv("RVCR_HOST_TRACE") != nullptr;
     // Enough CTAs to keep PCIe busy; more of them slow the concurrent scan (LSU back-pressure).  SM-issued writes to the
     // mapped buffer top out at ~46-48 GB/s (cudaMemcpy D2H: 57 GB/s); a cp.async.bulk (TMA store) variant of the write-back
     // was measured at the same rate (r01, 187-193 ms e2e for every CTA count / buffer depth tried) and was dropped.

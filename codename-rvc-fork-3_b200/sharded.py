@@ -124,12 +124,57 @@ class ShardedIndex:
         """In place on this rank's (n_r, d) float32 rows; every rank of the group must call it.
         Returns feats (and this rank's (D, I) rows when asked)."""
         import torch
-        G = self.world
-        n, d = feats.shape
+        n = feats.shape[0]
         if n:
             assign, _ = self.be.assign(feats)                                            # 1
         else:
             assign = torch.empty(0, dtype=torch.int32, device=feats.device)
+        return self._route_scan_combine(feats, assign, index_rate, want_neighbours)
+
+    def retrieve_blend_host_(self, host, index_rate: float, chunk_rows: int = 131072):
+        """Same step on this rank's HOST rows (a pinned (n_r, d) float32 torch tensor), in place: the rows go up in
+        chunks on a copy stream while the tensor cores already assign the previous chunk (the coarse step is
+        per-query independent, rvcr_retrieve_blend_host does the same on one GPU); dispatch / scan / combine run on
+        the whole batch; one device -> host copy brings the blended rows back.  Every rank must call it."""
+        import torch
+        n, d = host.shape
+        dev = self._device()
+        if dev.type != "cuda":
+            feats = host.clone()
+            self.retrieve_blend_(feats, index_rate)
+            host.copy_(feats)
+            return host
+        feats = torch.empty((n, d), dtype=torch.float32, device=dev)
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(dev)
+        offs, off, c = [], 0, min(32768, chunk_rows)
+        while off < n:                       # chunk sizes ramp up: only a small first copy is exposed
+            offs.append((off, min(n, off + c)))
+            off += c
+            c = min(chunk_rows, c * 2)
+        events = []
+        self._copy_stream.wait_stream(main)
+        with torch.cuda.stream(self._copy_stream):
+            for a, b in offs:
+                feats[a:b].copy_(host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append(ev)
+        parts = []
+        for (a, b), ev in zip(offs, events):
+            main.wait_event(ev)
+            parts.append(self.be.assign(feats[a:b])[0])                                  # 1, chunk by chunk
+        assign = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int32, device=dev)
+        self._route_scan_combine(feats, assign, index_rate, False)
+        host.copy_(feats, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return host
+
+    def _route_scan_combine(self, feats, assign, index_rate, want_neighbours):
+        import torch
+        G = self.world
+        n, d = feats.shape
         owner = self._owner(assign)
         order = torch.argsort(owner, stable=True)                                        # rows grouped by owner
         send_counts = torch.bincount(owner, minlength=G)

@@ -56,6 +56,10 @@ def _worker(rank, world, port, tmp):
         assert np.array_equal(got.cpu().numpy(), ref.cpu().numpy(), equal_nan=True)
         Ds, Is = sh.search(torch.from_numpy(q.copy()).cuda())
         assert torch.equal(Is, Ir) and torch.equal(Ds, Dr)
+        # host rows: chunked H2D overlapped with the coarse step (3 chunks here), one D2H back
+        hp = torch.from_numpy(q.copy()).pin_memory()
+        sh.retrieve_blend_host_(hp, 0.75, chunk_rows=400)
+        assert np.array_equal(hp.numpy(), ref.cpu().numpy(), equal_nan=True)
     # an empty home batch on one rank
     q2 = q[:0] if rank == world - 1 else q[:7]
     f2 = torch.from_numpy(q2.copy()).cuda()

@@ -107,6 +107,10 @@ def _worker(rank, world, port, tmp):
     Ds, Is = sh.search(torch.from_numpy(q.copy()))
     np.testing.assert_array_equal(Ds.numpy(), Dw)
     np.testing.assert_array_equal(Is.numpy(), Iw)
+    # host-buffer entry point (on CPU: same step on a copy, written back in place)
+    fh = torch.from_numpy(q.copy())
+    assert sh.retrieve_blend_host_(fh, 0.75) is fh
+    assert np.array_equal(fh.numpy(), want, equal_nan=True)
     # an empty home batch on one rank
     q2 = q[:0] if rank == world - 1 else q[:5]
     f2 = torch.from_numpy(q2.copy())
