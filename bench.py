@@ -50,19 +50,48 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank's host threads to the CPUs of its GPU's NUMA node (sysfs local_cpulist of the PCI device) before
+    any pinned host buffer is allocated, so that the H2D / D2H copies of the e2e leg do not cross the socket
+    interconnect when 8 ranks transfer at once.  Best effort: returns a short description or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} cpus local to GPU {local_rank}"
+    except Exception:
+        return None
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe).  The sampler is
+    started before the warm-up steps (nvidia-smi needs ~100 ms to deliver its first line) and polls every 20 ms; samples
+    are kept if their arrival time falls inside the timed region, which the caller brackets with mark_begin() /
+    mark_end().  If the region is shorter than the polling can resolve, the samples of the warm-up steps (same kernels,
+    same load) are used as well and `window` says so."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -70,28 +99,44 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for _, ln in rows:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 10:
+                    continue
+                try:
+                    sm.append(float(f[2]))
+                    mx.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        inside = [r for r in self.lines if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1 + 0.02]
+        window = "timed region"
+        sm, mx, reasons = parse(inside)
+        if len(sm) < 2:
+            window = "warm-up + timed region (timed region shorter than the 20 ms polling resolves)"
+            sm, mx, reasons = parse([r for r in self.lines if self.t1 is None or r[0] <= self.t1 + 0.02])
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -214,6 +259,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
@@ -259,19 +305,24 @@ def main():
 
     total_steps = args.warmup + args.steps
     bufs = [q_home.clone() for _ in range(total_steps)]       # every step gets a fresh (un-blended) input
-    for i in range(args.warmup):
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step(bufs[0])                                             # first call: lazy setup (row norms, tensor maps, scratch)
+    barrier()
+    time.sleep(0.25)                                          # let nvidia-smi deliver its first samples
+    for i in range(1, args.warmup):
         step(bufs[i])
     barrier()
     launches0 = index.stats()["kernels_launched"]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for i in range(args.steps):
         step(bufs[args.warmup + i])
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = index.stats()["kernels_launched"] - launches0
@@ -409,7 +460,7 @@ def main():
                            "setup_s": round(setup_s, 1)},
                 "roofline": dict(roof[dominant], dominant=dominant) if dominant else None,
                 "roofline_all": roof, "phase_ms": phase_acc, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-                "clocks": clocks,
+                "clocks": clocks, "host_affinity": numa,
                 "coarse_stats": {"tc_queries": st["coarse_tc_queries"], "rechecked_candidates": st["coarse_candidates"],
                                  "exact_fallback_queries": st["coarse_fallback"]},
                 "scan_stats": {"tc_candidates_rechecked": st.get("scan_tc_candidates", 0), "exact_fallback_queries": st.get("scan_tc_fallback", 0),
