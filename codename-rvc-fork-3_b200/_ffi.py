@@ -67,6 +67,8 @@ SIGNATURES = {
     "rvcr_search": (C.c_int, [_H, _P, _I64, _I32, _P, _P, _P]),
     "rvcr_search_host": (C.c_int, [_H, _P, _I64, _I32, _P, _P]),
     "rvcr_retrieve_blend": (C.c_int, [_H, _P, _I64, C.c_double, _P, _P, _P]),
+    "rvcr_retrieve_blend_upsample": (C.c_int, [_H, _P, _I64, C.c_double, _P, C.c_double, _P, _P, _P, _P]),
+    "rvcr_upsample_protect": (C.c_int, [_P, _P, _P, _I64, _I32, C.c_double, _P, C.c_int, _P]),
     "rvcr_retrieve_blend_host": (C.c_int, [_H, _P, _I64, C.c_double]),
     "rvcr_retrieve_blend_assigned": (C.c_int, [_H, _P, _I64, _P, C.c_double, _P, _P, _P]),
     "rvcr_search_assigned": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P]),

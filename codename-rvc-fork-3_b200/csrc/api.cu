@@ -512,6 +512,42 @@ int rvcr_retrieve_blend(rvcr_index* h, float* feats_dev, int64_t n, double index
     return search_device(h, feats_dev, n, nullptr, true, index_rate, D_dev, I_dev, (cudaStream_t)stream);
 }
 
+int rvcr_retrieve_blend_upsample(rvcr_index* h, const float* feats_dev, int64_t n, double index_rate, const float* pitchf_dev,
+                                 double protect, float* out_dev, float* D_dev, int64_t* I_dev, void* stream) {
+    RVCR_ENTER(h);
+    if (n > 0 && (!feats_dev || !out_dev)) return RVCR_ERR_INVALID;
+    if (n > 0 && out_dev == feats_dev) {
+        set_error("retrieve_blend_upsample: out (2n x d) must not alias feats (n x d)");
+        return RVCR_ERR_INVALID;
+    }
+    if (h->d % 4 != 0) {
+        set_error("d=%d unsupported (must be a multiple of 4)", h->d);
+        return RVCR_ERR_UNSUPPORTED;
+    }
+    // the blend epilogues (scan re-check / fallback / gather_blend) write rows 2i, 2i+1 of out_dev instead of feats
+    h->fuse.post.out2 = out_dev;
+    h->fuse.post.pitchf = pitchf_dev;
+    h->fuse.post.protect = (float)protect;
+    const int rc = search_device(h, const_cast<float*>(feats_dev), n, nullptr, true, index_rate, D_dev, I_dev, (cudaStream_t)stream);
+    h->fuse.post = PostArgs{};
+    return rc;
+}
+
+int rvcr_upsample_protect(const float* feats_dev, const float* feats0_dev, const float* pitchf_dev, int64_t n, int32_t d,
+                          double protect, float* out_dev, int device, void* stream) {
+    if (n < 0 || d < 1 || (n > 0 && (!feats_dev || !out_dev))) return RVCR_ERR_INVALID;
+    if ((pitchf_dev != nullptr) != (feats0_dev != nullptr)) {
+        set_error("upsample_protect: pitchf and feats0 go together (both or neither)");
+        return RVCR_ERR_INVALID;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) {
+        set_error("cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return RVCR_ERR_CUDA;
+    }
+    return upsample_protect(feats_dev, feats0_dev, pitchf_dev, n, d, protect, out_dev, (cudaStream_t)stream);
+}
+
 int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double index_rate) {
     RVCR_ENTER(h);
     if (n > 0 && !feats_host) return RVCR_ERR_INVALID;

@@ -68,6 +68,15 @@ struct Options {
     int64_t tc_resident = 9;  // coarse tcgen05 kernel: query-operand k-blocks pinned in shared memory per work item (0, 6, 8, 9, 10)
 };
 
+// The step AFTER the path, fused into the blend epilogue (rvc/infer/pipeline.py:463-481): 2x nearest
+// upsample along time (F.interpolate(scale_factor=2): out[t] = in[t / 2]) and the pitch-protect mix against the
+// un-blended features, feats * pf + feats0 * (1 - pf).
+struct PostArgs {
+    float* out2 = nullptr;          // (2n, d) destination rows; nullptr = no post step (blend in place as before)
+    const float* pitchf = nullptr;  // 2n per-frame pitch values, or nullptr = upsample only (protect >= 0.5 / no pitch guidance)
+    float protect = 0.f;
+};
+
 }  // namespace rvcr
 
 // The handle behind the C ABI.
@@ -138,6 +147,7 @@ struct rvcr_index {
         bool active = false, done = false;
         float* out = nullptr;
         float r32 = 0.f, omr32 = 0.f;
+        rvcr::PostArgs post;   // rvcr_retrieve_blend_upsample: rows go to post.out2 (2n x d), feats stay untouched
     } fuse;
 
     bool tc_counters_dirty = false;
@@ -179,6 +189,9 @@ int gather_blend_range(rvcr_index* h, const float* feats, int64_t n, const float
 int gather_blend(rvcr_index* h, float* feats, int64_t n, const float* D, const int32_t* P,
                  const int32_t* assign /*nullable: restrict to owned*/, double index_rate,
                  cudaStream_t s);
+// post.cu : standalone 2x upsample + protect mix (pipeline.py:463-481) for callers that skipped retrieval
+int upsample_protect(const float* feats, const float* feats0, const float* pitchf, int64_t n, int d, double protect, float* out,
+                     cudaStream_t s);
 int merge_coarse(const float* dist_all, const int32_t* list_all, int G, int64_t n, int32_t* out,
                  cudaStream_t s);
 int merge_topk(const float* D_all, const int64_t* I_all, int G, int64_t n, int k, float* D, int64_t* I,
@@ -224,6 +237,37 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// pipeline.py:476-478: pitchff = pitchf.clone(); pitchff[pitchf > 0] = 1; pitchff[pitchf < 1] = protect
+__device__ __forceinline__ float protect_factor(float pitchf, float protect) {
+    float pf = pitchf;
+    if (pitchf > 0.f) pf = 1.f;
+    if (pitchf < 1.f) pf = protect;
+    return pf;
+}
+// pipeline.py:479-481: feats * pf + feats0 * (1 - pf), three separately rounded fp32 ops (no FMA) like the torch kernels
+__device__ __forceinline__ float4 protect_mix(float4 o, float4 f0, float pf) {
+    const float om = __fsub_rn(1.0f, pf);
+    float4 r;
+    r.x = __fadd_rn(__fmul_rn(o.x, pf), __fmul_rn(f0.x, om));
+    r.y = __fadd_rn(__fmul_rn(o.y, pf), __fmul_rn(f0.y, om));
+    r.z = __fadd_rn(__fmul_rn(o.z, pf), __fmul_rn(f0.z, om));
+    r.w = __fadd_rn(__fmul_rn(o.w, pf), __fmul_rn(f0.w, om));
+    return r;
+}
+// Store float4 column c of the blended row `o` of query qi to rows 2qi and 2qi+1 of post.out2 (pipeline.py:463-465),
+// mixed with the un-blended row f0 when a pitch track is given.  pitchf loads are warp-uniform (L1 broadcast).
+__device__ __forceinline__ void post_store(const PostArgs& pa, int64_t qi, int d, int c, float4 o, float4 f0) {
+    float4* r0 = reinterpret_cast<float4*>(pa.out2 + (2 * qi) * d) + c;
+    float4* r1 = reinterpret_cast<float4*>(pa.out2 + (2 * qi + 1) * d) + c;
+    if (pa.pitchf) {
+        *r0 = protect_mix(o, f0, protect_factor(__ldg(pa.pitchf + 2 * qi), pa.protect));
+        *r1 = protect_mix(o, f0, protect_factor(__ldg(pa.pitchf + 2 * qi + 1), pa.protect));
+    } else {
+        *r0 = o;
+        *r1 = o;
+    }
 }
 
 // (dist, pos) strict total order used everywhere a top-k decision is made: distance ascending,

@@ -547,6 +547,7 @@ struct BlendArgs {
     float* out;             // blended rows are written to out + qi * d (may alias the queries: in place)
     int64_t last_row_pos;   // numpy's big_npy[-1] for (FLT_MAX, -1) padding
     float r32, omr32;
+    PostArgs post;          // optional fused 2x upsample + protect mix: rows go to post.out2 instead of `out`
 };
 
 __device__ __forceinline__ void blend_weights(float td, int tp, int lane, int64_t last_row_pos, float& wn, int& spos) {
@@ -592,7 +593,9 @@ __device__ __forceinline__ float4 blend_vec(const float4 (&v)[RVCR_K], const flo
 // BLEND: the warp that has just found a query's exact top-8 also gathers those 8 rows (it read them a moment ago:
 // L1 / L2 hits instead of a second trip to HBM), applies the 1/score^2 weights and the index_rate blend and writes
 // the output row -- rvc/infer/pipeline.py:500-506 without a separate gather kernel.
-template <bool BLEND>
+// BLEND: 0 = search only, 1 = + fused tail in place, 2 = + fused tail + 2x upsample / protect mix into post.out2 (a separate
+// instantiation so the default kernel's code and register count stay exactly as profiled).
+template <int BLEND>
 __global__ void __launch_bounds__(RC_WARPS * 32)
 scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qorder, const uint32_t* __restrict__ keys,
                     uint32_t nlist, const int32_t* __restrict__ items, const int32_t* __restrict__ nitems_ptr, int item_begin,
@@ -670,7 +673,10 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
                 float4 v[RVCR_K];
 #pragma unroll
                 for (int k = 0; k < RVCR_K; ++k) v[k] = rows[k] ? __ldg(rows[k] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                o4[c] = blend_vec(v, wk, reinterpret_cast<const float4*>(sq)[c], ba.r32, ba.omr32);
+                const float4 f0 = reinterpret_cast<const float4*>(sq)[c];
+                const float4 o = blend_vec(v, wk, f0, ba.r32, ba.omr32);
+                if (BLEND == 2) post_store(ba.post, qi, d, c, o, f0);
+                else o4[c] = o;
             }
         }
     }
@@ -678,7 +684,7 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
 
 // Brute-force exact scan of one list for the queries the tensor-core pass could not bound (rare): one CTA
 // per query, 8 lanes per row (canonical order), 32 rows per step.
-template <bool BLEND>
+template <int BLEND>
 __global__ void __launch_bounds__(256)
 scan_exact_fallback_kernel(const float* __restrict__ q, const int32_t* __restrict__ qorder, const uint32_t* __restrict__ keys,
                            const int32_t* __restrict__ fb_list, const int32_t* __restrict__ fb_count, uint32_t nlist, int d,
@@ -754,7 +760,10 @@ scan_exact_fallback_kernel(const float* __restrict__ q, const int32_t* __restric
                 float4 v[RVCR_K];
 #pragma unroll
                 for (int k = 0; k < RVCR_K; ++k) v[k] = rows[k] ? __ldg(rows[k] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                o4[c] = blend_vec(v, wk, reinterpret_cast<const float4*>(sq)[c], ba.r32, ba.omr32);
+                const float4 f0 = reinterpret_cast<const float4*>(sq)[c];
+                const float4 o = blend_vec(v, wk, f0, ba.r32, ba.omr32);
+                if (BLEND == 2) post_store(ba.post, qi, d, c, o, f0);
+                else o4[c] = o;
             }
         }
     }
@@ -890,7 +899,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     RVCR_CHECK_LAUNCH();
     // fused tail (search_device sets h->fuse for rvcr_retrieve_blend*): the re-check / fallback kernels also blend
     const bool blend = h->fuse.active;
-    BlendArgs ba{h->fuse.out, h->last_row_pos, h->fuse.r32, h->fuse.omr32};
+    BlendArgs ba{h->fuse.out, h->last_row_pos, h->fuse.r32, h->fuse.omr32, h->fuse.post};
     {
         PhaseTimer pt(h, RVCR_PHASE_SCAN_RECHECK, s);
         // One warp per query, 32 warps per SM.  A variant that staged the candidate rows in shared memory with
@@ -903,7 +912,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
             if (const char* e = getenv("RVCR_RC_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // tuning knob
             int64_t rgrid = (int64_t)h->num_sms * per_sm;
             if (rgrid * RC_WARPS > n) rgrid = (n + RC_WARPS - 1) / RC_WARPS;
-            auto kern = blend ? scan_recheck_kernel<true> : scan_recheck_kernel<false>;
+            auto kern = !blend ? scan_recheck_kernel<0> : (ba.post.out2 ? scan_recheck_kernel<2> : scan_recheck_kernel<1>);
             kern<<<(unsigned)rgrid, RC_WARPS * 32, rsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), (uint32_t)h->nlist,
                                                              h->ws_items.as<int32_t>(), h->ws_misc.as<int32_t>(), item_begin, item_end, n,
                                                              d, h->vecs, h->ids, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
@@ -914,7 +923,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     {
         PhaseTimer pt(h, RVCR_PHASE_SCAN_FALLBACK, s);
         const size_t fsm = (size_t)(d + 48) * 4;
-        auto kern = blend ? scan_exact_fallback_kernel<true> : scan_exact_fallback_kernel<false>;
+        auto kern = !blend ? scan_exact_fallback_kernel<0> : (ba.post.out2 ? scan_exact_fallback_kernel<2> : scan_exact_fallback_kernel<1>);
         kern<<<h->num_sms * 2, 256, fsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), h->ws_fb.as<int32_t>(), fb_count,
                                               (uint32_t)h->nlist, d, h->vecs, h->ids, h->offsets, D, P, I, ba);
         RVCR_CHECK_LAUNCH();

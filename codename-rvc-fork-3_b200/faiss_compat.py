@@ -17,7 +17,10 @@ All arithmetic runs in librvcr.so on the GPU; there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import re
+import threading
+from collections import OrderedDict
 
 import numpy as np
 
@@ -186,12 +189,23 @@ class IndexIVFFlat:
                                 C.c_void_p(dist.data_ptr()), _stream_of(t)))
         return lst, dist
 
-    def reconstruct_n(self, n0: int = 0, ni: int | None = None) -> np.ndarray:
-        """index.reconstruct_n(n0, ni) -> new (ni, d) float32 array (`big_npy`)."""
+    lazy_reconstruct = False      # patch_pipeline sets this on the class: reconstruct_n -> LazyBigNpy
+
+    def reconstruct_n(self, n0: int = 0, ni: int | None = None):
+        """index.reconstruct_n(n0, ni) -> new (ni, d) float32 array (`big_npy`, pipeline.py:556).
+        With `lazy_reconstruct` the (ntotal, d) host copy is only built if somebody actually indexes
+        it (the fused path never does: the gather reads the index's own list-ordered storage)."""
         inf = self._info()
         ni = inf.ntotal - n0 if ni is None or ni < 0 else ni
-        out = np.empty((ni, inf.d), np.float32)
-        check(lib().rvcr_reconstruct_n(self.handle, int(n0), int(ni), out.ctypes.data_as(C.c_void_p), 0))
+        if n0 < 0 or ni < 0 or n0 + ni > inf.ntotal:
+            raise RvcrError(-1, f"reconstruct_n: range [{n0}, {n0 + ni}) outside [0, {inf.ntotal})")
+        if self.lazy_reconstruct:
+            return LazyBigNpy(self, int(n0), int(ni), int(inf.d))
+        return self._reconstruct_now(int(n0), int(ni), int(inf.d))
+
+    def _reconstruct_now(self, n0: int, ni: int, d: int) -> np.ndarray:
+        out = np.empty((ni, d), np.float32)
+        check(lib().rvcr_reconstruct_n(self.handle, n0, ni, out.ctypes.data_as(C.c_void_p), 0))
         return out
 
     def retrieve_blend_(self, feats, index_rate: float, want_neighbours: bool = False):
@@ -215,6 +229,33 @@ class IndexIVFFlat:
                                         C.c_void_p(D.data_ptr()) if D is not None else None,
                                         C.c_void_p(I.data_ptr()) if I is not None else None, _stream_of(t)))
         return (feats, D, I) if want_neighbours else feats
+
+    def retrieve_blend_upsample(self, feats, index_rate: float, pitchf=None, protect: float = 0.5,
+                                want_neighbours: bool = False):
+        """The path plus the step after it in one call (pipeline.py:455-481): retrieval + blend, 2x
+        nearest upsample along time, and -- when `pitchf` (2n values, CUDA float32) is given and protect < 0.5 --
+        the pitch-protect mix against the UN-blended features.  `feats` ((n, d) or (1, n, d)) is left untouched
+        (it plays the reference's `feats0` clone); returns a NEW (2n, d) / (1, 2n, d) tensor."""
+        import torch
+        inf = self._info()
+        t = feats[0] if feats.dim() == 3 else feats
+        if feats.dim() == 3 and feats.shape[0] != 1:
+            raise AssertionError("retrieve_blend_upsample: batch dimension must be 1")
+        t = _check_cuda_tensor(t, inf, "retrieve_blend_upsample")
+        n = t.shape[0]
+        pf = _check_pitchf(pitchf, n, t.device) if (pitchf is not None and protect < 0.5) else None
+        out = torch.empty((2 * n, inf.d), dtype=torch.float32, device=t.device)
+        D = I = None
+        if want_neighbours:
+            D = torch.empty((n, 8), dtype=torch.float32, device=t.device)
+            I = torch.empty((n, 8), dtype=torch.int64, device=t.device)
+        check(lib().rvcr_retrieve_blend_upsample(
+            self.handle, C.c_void_p(t.data_ptr()), n, float(index_rate),
+            C.c_void_p(pf.data_ptr()) if pf is not None else None, float(protect), C.c_void_p(out.data_ptr()),
+            C.c_void_p(D.data_ptr()) if D is not None else None, C.c_void_p(I.data_ptr()) if I is not None else None,
+            _stream_of(t)))
+        out = out.unsqueeze(0) if feats.dim() == 3 else out
+        return (out, D, I) if want_neighbours else out
 
     def retrieve_blend_host_(self, feats: np.ndarray, index_rate: float) -> np.ndarray:
         """Same, on a host (n, d) float32 C-contiguous array, in place (H2D / D2H inside)."""
@@ -289,6 +330,40 @@ class IndexIVFFlat:
         check(lib().rvcr_index_commit(self.handle, None))
 
 
+class LazyBigNpy:
+    """Stand-in for `big_npy = index.reconstruct_n(0, index.ntotal)` (pipeline.py:556) that defers the
+    D2H scatter until the array is really consumed.  Quacks like the (ni, d) float32 ndarray for what the
+    reference does with it -- `big_npy[ix]` (pipeline.py:502), np.asarray, shape / dtype / len -- so the
+    UNPATCHED `_retrieve_speaker_embeddings` body still works; the fused path ignores it entirely."""
+
+    def __init__(self, index: "IndexIVFFlat", n0: int, ni: int, d: int):
+        self._index, self._n0, self._ni, self._d = index, n0, ni, d
+        self._arr = None
+
+    shape = property(lambda self: (self._ni, self._d))
+    dtype = np.dtype(np.float32)
+    ndim = 2
+
+    @property
+    def materialized(self) -> bool:
+        return self._arr is not None
+
+    def _get(self) -> np.ndarray:
+        if self._arr is None:
+            self._arr = self._index._reconstruct_now(self._n0, self._ni, self._d)
+        return self._arr
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._get()
+        return a if dtype is None or np.dtype(dtype) == a.dtype else a.astype(dtype)
+
+    def __getitem__(self, key):
+        return self._get()[key]
+
+    def __len__(self) -> int:
+        return self._ni
+
+
 class _CudaArray:
     def __init__(self, ptr, shape, typestr):
         self.__cuda_array_interface__ = {"data": (ptr, False), "shape": tuple(shape), "typestr": typestr,
@@ -318,6 +393,40 @@ def _check_cuda_tensor(t, inf: Info, what: str):
     return t
 
 
+def _check_pitchf(pitchf, n: int, device):
+    import torch
+    pf = pitchf.reshape(-1)
+    if not (pf.is_cuda and pf.dtype == torch.float32 and pf.is_contiguous() and pf.device == device):
+        raise AssertionError("pitchf: need a contiguous float32 CUDA tensor on the features' device")
+    if pf.shape[0] != 2 * n:
+        raise AssertionError(f"pitchf: expected {2 * n} values (2 per feature frame, pipeline.py:466-474), got {pf.shape[0]}")
+    return pf
+
+
+def upsample_protect(feats, feats0=None, pitchf=None, protect: float = 0.5):
+    """pipeline.py:463-481 alone (for calls that skipped retrieval): `feats` / `feats0` (n, d) or (1, n, d) CUDA
+    float32 -> new (2n, d) / (1, 2n, d) tensor.  The protect mix is applied iff feats0 and pitchf are given and
+    protect < 0.5 (the reference's `if pitch_guidance` / `if protect < 0.5`)."""
+    import torch
+    t = feats[0] if feats.dim() == 3 else feats
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.is_contiguous()):
+        raise AssertionError("upsample_protect: need a contiguous float32 CUDA tensor (n, d) or (1, n, d)")
+    n, d = t.shape
+    mix = feats0 is not None and pitchf is not None and protect < 0.5
+    t0 = pf = None
+    if mix:
+        t0 = feats0[0] if feats0.dim() == 3 else feats0
+        if not (t0.is_cuda and t0.dtype == torch.float32 and t0.shape == t.shape and t0.is_contiguous()
+                and t0.device == t.device):
+            raise AssertionError("upsample_protect: feats0 must match feats (shape, dtype, device)")
+        pf = _check_pitchf(pitchf, n, t.device)
+    out = torch.empty((2 * n, d), dtype=torch.float32, device=t.device)
+    check(lib().rvcr_upsample_protect(C.c_void_p(t.data_ptr()), C.c_void_p(t0.data_ptr()) if mix else None,
+                                      C.c_void_p(pf.data_ptr()) if mix else None, n, d, float(protect),
+                                      C.c_void_p(out.data_ptr()), int(t.device.index), _stream_of(t)))
+    return out.unsqueeze(0) if feats.dim() == 3 else out
+
+
 def _stream_of(t):
     import torch
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
@@ -325,15 +434,103 @@ def _stream_of(t):
 
 # ---- module-level faiss functions ------------------------------------------------------------
 
-def read_index(path: str, device: int | None = None, shard: tuple[int, int] | None = None) -> IndexIVFFlat:
-    """faiss.read_index(path) (pipeline.py:555).  `shard=(rank, world)` keeps one shard's lists."""
+def _open_index(path: str, dev: int, shard: tuple[int, int] | None) -> IndexIVFFlat:
+    """Stream the `.index` file into list-ordered HBM (rvcr_index_read / rvcr_index_read_shard)."""
     h = C.c_void_p()
-    dev = _default_device() if device is None else int(device)
     if shard is None:
         check(lib().rvcr_index_read(str(path).encode(), dev, C.byref(h)))
     else:
         check(lib().rvcr_index_read_shard(str(path).encode(), dev, int(shard[0]), int(shard[1]), C.byref(h)))
     return IndexIVFFlat(h.value)
+
+
+class IndexCache:
+    """Device-resident index cache.
+
+    The reference calls `faiss.read_index(file_index)` + `index.reconstruct_n(0, ntotal)` at the top of
+    EVERY `Pipeline.pipeline()` call (pipeline.py:553-561), i.e. once per converted file / chunk
+    (infer.py:291-311): the whole file is re-read and a second host copy rebuilt each time.  With the
+    cache enabled `read_index` returns the SAME device-resident object while the file is unchanged --
+    keyed by (realpath, mtime_ns, size, device, shard) -- so only the first call touches the disk.
+    LRU over `max_entries` handles and `max_bytes` of list storage; an evicted handle is freed when its
+    last user drops it (plain Python reference counting, no handle is ever closed under a user).
+
+    Off by default: faiss's `read_index` returns independent objects, and a caller that `add`s to a
+    loaded index must not mutate a shared one.  `patch_pipeline` turns it on (the inference path is
+    read-only)."""
+
+    def __init__(self, max_entries: int = 4, max_bytes: int = 120 << 30):
+        self.max_entries = int(max_entries)
+        self.max_bytes = int(max_bytes)
+        self.enabled = False
+        self.hits = 0
+        self.misses = 0
+        self._lock = threading.Lock()
+        self._entries: "OrderedDict[tuple, tuple[IndexIVFFlat, int]]" = OrderedDict()
+
+    @staticmethod
+    def key(path: str, dev: int, shard) -> tuple:
+        rp = os.path.realpath(path)
+        st = os.stat(rp)                                    # FileNotFoundError propagates like faiss's RuntimeError
+        return (rp, st.st_mtime_ns, st.st_size, int(dev), tuple(shard) if shard is not None else None)
+
+    def get(self, path: str, dev: int, shard, opener) -> IndexIVFFlat:
+        k = self.key(path, dev, shard)
+        with self._lock:
+            hit = self._entries.get(k)
+            if hit is not None:
+                self._entries.move_to_end(k)
+                self.hits += 1
+                return hit[0]
+            # a rewritten file (same path, new mtime / size) supersedes its stale entry
+            for old in [e for e in self._entries if e[0] == k[0] and e[3:] == k[3:]]:
+                del self._entries[old]
+        index = opener(path, dev, shard)                   # outside the lock: may take seconds for a 100 GB file
+        nbytes = int(k[2])
+        with self._lock:
+            self.misses += 1
+            self._entries[k] = (index, nbytes)
+            self._entries.move_to_end(k)
+            while len(self._entries) > max(self.max_entries, 1) or (
+                    len(self._entries) > 1 and sum(b for _, b in self._entries.values()) > self.max_bytes):
+                self._entries.popitem(last=False)
+        return index
+
+    def clear(self) -> None:
+        with self._lock:
+            self._entries.clear()
+
+    def __len__(self) -> int:
+        return len(self._entries)
+
+
+index_cache = IndexCache()
+
+
+def enable_index_cache(enabled: bool = True, max_entries: int | None = None, max_bytes: int | None = None) -> IndexCache:
+    index_cache.enabled = bool(enabled)
+    if max_entries is not None:
+        index_cache.max_entries = int(max_entries)
+    if max_bytes is not None:
+        index_cache.max_bytes = int(max_bytes)
+    if not enabled:
+        index_cache.clear()
+    return index_cache
+
+
+def read_index(path: str, device: int | None = None, shard: tuple[int, int] | None = None,
+               cache: bool | None = None) -> IndexIVFFlat:
+    """faiss.read_index(path) (pipeline.py:555).  `shard=(rank, world)` keeps one shard's lists.
+    `cache` (default: the module switch set by enable_index_cache / patch_pipeline) returns the
+    already-resident index while the file is unchanged."""
+    dev = _default_device() if device is None else int(device)
+    use_cache = index_cache.enabled if cache is None else bool(cache)
+    if use_cache:
+        try:
+            return index_cache.get(str(path), dev, shard, _open_index)
+        except FileNotFoundError:
+            pass                                            # fall through: the C reader reports RVCR_ERR_IO
+    return _open_index(path, dev, shard)
 
 
 def write_index(index: IndexIVFFlat, path: str) -> None:

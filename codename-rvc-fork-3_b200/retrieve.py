@@ -26,22 +26,52 @@ def retrieve_speaker_embeddings(feats, index: IndexIVFFlat, big_npy=None, index_
     return f
 
 
+def convert_features(feats, index, index_rate: float, pitchf=None, protect: float = 0.5):
+    """Everything between the feature extractor and `net_g.infer` in `Pipeline.voice_conversion`
+    (pipeline.py:455-481) as ONE library call when an index is loaded:
+
+        feats0 = feats.clone()                       # :455   (not needed: feats is read only here)
+        feats = self._retrieve_speaker_embeddings()  # :456-461
+        feats = F.interpolate(..., scale_factor=2)   # :463-465
+        feats0 = F.interpolate(...); pitchff = ...; feats = feats * pitchff + feats0 * (1 - pitchff)   # :468-481
+
+    `pitchf` is the (1, p_len) F0 track already cut to p_len = 2n (pipeline.py:466,474), or None without pitch
+    guidance.  With `index` None / falsy or index_rate <= 0 (pipeline.py:553) only the post step runs.
+    Returns a new (1, 2n, d) tensor."""
+    from .faiss_compat import upsample_protect
+    if index and index_rate > 0:
+        if not isinstance(index, IndexIVFFlat):
+            raise TypeError("index must come from codename-rvc-fork-3_b200.read_index / index_factory")
+        return index.retrieve_blend_upsample(feats.contiguous(), index_rate, pitchf=pitchf, protect=protect)
+    f = feats.contiguous()
+    return upsample_protect(f, f if pitchf is not None else None, pitchf, protect)
+
+
 def _method(self, feats, index, big_npy, index_rate):
     return retrieve_speaker_embeddings(feats, index, big_npy, index_rate)
 
 
-def patch_pipeline(pipeline_cls_or_module, faiss_module_name: str = "faiss") -> None:
+def patch_pipeline(pipeline_cls_or_module, faiss_module_name: str = "faiss", cache: bool = True,
+                   lazy_big_npy: bool = True) -> None:
     """Install the fused path on the reference without editing it:
 
         import rvc.infer.pipeline as P
         patch_pipeline(P)            # P.faiss -> this package, P.Pipeline._retrieve_speaker_embeddings -> fused
 
     After this `faiss.read_index` / `index.reconstruct_n` at pipeline.py:555-556 build a device-resident
-    index (big_npy becomes a cheap placeholder) and pipeline.py:459 calls the fused kernel path."""
+    index (big_npy becomes a lazy placeholder that is never materialised) and pipeline.py:459 calls the
+    fused kernel path.  `cache=True` keeps the index resident across `pipeline()` calls -- the reference
+    re-reads the file for every converted file / chunk (pipeline.py:553-561, infer.py:291-311); see
+    faiss_compat.IndexCache."""
     import sys
+    from . import faiss_compat
     pkg = sys.modules[__package__]
     target = pipeline_cls_or_module
     if hasattr(target, "Pipeline"):
         setattr(target, faiss_module_name, pkg)
         target = target.Pipeline
     target._retrieve_speaker_embeddings = _method
+    if cache:
+        faiss_compat.enable_index_cache(True)
+    if lazy_big_npy:
+        IndexIVFFlat.lazy_reconstruct = True

@@ -157,6 +157,22 @@ RVCR_API int rvcr_search_host(rvcr_index* h, const float* q_host, int64_t n, int
  * into feats_dev (n x d fp32).  D_dev / I_dev (n x 8) are optional outputs. */
 RVCR_API int rvcr_retrieve_blend(rvcr_index* h, float* feats_dev, int64_t n, double index_rate, float* D_dev,
                         int64_t* I_dev, void* stream);
+/* The path plus the step after it, one call: retrieve_blend, then the 2x nearest
+ * upsample along time and the pitch-protect mix against the UN-blended features
+ *     feats = F.interpolate(feats.permute(0,2,1), scale_factor=2).permute(0,2,1)      pipeline.py:463-465
+ *     pitchff[pitchf > 0] = 1; pitchff[pitchf < 1] = protect                          pipeline.py:476-478
+ *     feats = feats * pitchff[..., None] + feats0 * (1 - pitchff[..., None])          pipeline.py:479-481
+ * done in the blend kernel's epilogue.  feats_dev (n x d) is read only (it is the reference's
+ * feats0 clone, pipeline.py:455); out_dev is 2n x d; pitchf_dev holds 2n values, or NULL for
+ * upsample only (no pitch guidance, or protect >= 0.5: the caller applies that condition). */
+RVCR_API int rvcr_retrieve_blend_upsample(rvcr_index* h, const float* feats_dev, int64_t n, double index_rate,
+                                 const float* pitchf_dev, double protect, float* out_dev, float* D_dev,
+                                 int64_t* I_dev, void* stream);
+/* The same post step alone, for calls that skipped retrieval (no index / index_rate 0,
+ * pipeline.py:456-461): feats_dev, feats0_dev n x d, out_dev 2n x d.  pitchf_dev and feats0_dev are
+ * both given (mix) or both NULL (upsample only). */
+RVCR_API int rvcr_upsample_protect(const float* feats_dev, const float* feats0_dev, const float* pitchf_dev, int64_t n,
+                          int32_t d, double protect, float* out_dev, int device, void* stream);
 /* Same with host buffers (pinned or pageable): H2D, retrieve_blend, D2H, synchronises. */
 RVCR_API int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double index_rate);
 /* index.reconstruct_n(i0, ni)  ->  big_npy                      rvc/infer/pipeline.py:556 */

@@ -16,6 +16,8 @@ Functions mirror the reference call sites:
     tail               weights, gather-sum, blend                     pipeline.py:500-506
     retrieve           the whole of _retrieve_speaker_embeddings      pipeline.py:497-507
     build_lists        IndexIVFFlat::add_core                         extract_index.py:67-69
+    upsample_protect   2x nearest upsample + pitch-protect mix        pipeline.py:463-481  (PINNED:
+                       tests/golden/post_*.npz are outputs of the reference's own statements, make_golden_post.py)
 """
 from __future__ import annotations
 
@@ -155,6 +157,24 @@ def tail_numpy_verbatim(score, ix, big_npy, index_rate, feats):
     r32 = np.float32(index_rate)
     omr32 = np.float32(1 - index_rate)
     return npy * r32 + omr32 * feats
+
+
+def upsample_protect(feats, feats0=None, pitchf=None, protect: float = 0.5):
+    """pipeline.py:463-481 on (n, d) arrays -> (2n, d): F.interpolate(scale_factor=2) along time is nearest
+    (out[t] = in[t // 2]); with a pitch track, pitchff = pitchf; pitchff[pitchf > 0] = 1; pitchff[pitchf < 1] =
+    protect, and out = feats * pitchff + feats0 * (1 - pitchff): three separately rounded fp32 operations.
+    The CALLER applies the reference's conditions (pitch guidance and protect < 0.5) by passing pitchf or None."""
+    up = np.repeat(_f32(feats), 2, axis=0)
+    if pitchf is None or feats0 is None:
+        return up
+    up0 = np.repeat(_f32(feats0), 2, axis=0)
+    pitchf = _f32(pitchf).reshape(-1)
+    assert pitchf.shape[0] == up.shape[0], "pitchf must have 2n entries (the reference broadcasts it over 2n frames)"
+    pf = pitchf.copy()
+    pf[pitchf > 0] = np.float32(1)
+    pf[pitchf < 1] = np.float32(protect)
+    om = (np.float32(1) - pf).astype(np.float32)
+    return (up * pf[:, None]).astype(np.float32) + (up0 * om[:, None]).astype(np.float32)
 
 
 def build_lists(x, assign, nlist: int):
