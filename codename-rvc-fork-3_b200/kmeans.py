@@ -53,7 +53,7 @@ def train_ivf_centroids(index, x: np.ndarray, k: int, niter: int = 10, seed: int
         sums = torch.zeros((k, d), dtype=torch.float32, device=dev)
         sums.index_add_(0, a[ok], xd[ok])
         nz = cnt > 0
-        cent = torch.where(nz[:, None], sums / cnt.clamp(min=1)[:, None].to(torch.float32), cent)
+        cent = torch.where(nz[:, None], sums * (1.0 / cnt.clamp(min=1).to(torch.float32))[:, None], cent)   # faiss: c *= 1 / hassign
         empty = torch.nonzero(~nz).flatten().tolist()
         if empty:                                                          # faiss split_clusters
             h = cnt.cpu().numpy().astype(np.float64)
@@ -63,7 +63,7 @@ def train_ivf_centroids(index, x: np.ndarray, k: int, niter: int = 10, seed: int
                 cj = 0
                 while True:
                     p = (h[cj] - 1.0) / float(n - k)
-                    r = rng.randint(0, 2 ** 32, dtype=np.uint64) / float(2 ** 32 - 1)
+                    r = float(np.float32(rng.randint(0, 2 ** 32, dtype=np.uint64)) / np.float32(4294967295.0))   # mt() / float(mt.max())
                     if r < p:
                         break
                     cj = (cj + 1) % k

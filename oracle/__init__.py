@@ -16,6 +16,7 @@ Functions mirror the reference call sites:
     tail               weights, gather-sum, blend                     pipeline.py:500-506
     retrieve           the whole of _retrieve_speaker_embeddings      pipeline.py:497-507
     build_lists        IndexIVFFlat::add_core                         extract_index.py:67-69
+    kmeans_train       index.train -> faiss Clustering::train (A9)    extract_index.py:65   (PARITY UNPINNED)
     upsample_protect   2x nearest upsample + pitch-protect mix        pipeline.py:463-481  (PINNED:
                        tests/golden/post_*.npz are outputs of the reference's own statements, make_golden_post.py)
 """
@@ -157,6 +158,61 @@ def tail_numpy_verbatim(score, ix, big_npy, index_rate, feats):
     r32 = np.float32(index_rate)
     omr32 = np.float32(1 - index_rate)
     return npy * r32 + omr32 * feats
+
+
+def rand_perm(n: int, seed: int) -> np.ndarray:
+    """faiss utils/random.cpp rand_perm [EXT, SURVEY A9]: identity, then for i in 0..n-2 swap(perm[i],
+    perm[i + mt() % (n - i)]) with std::mt19937(seed).  numpy's legacy RandomState(seed) seeds MT19937 with the
+    same init_genrand(seed); random_raw yields its raw 32-bit outputs."""
+    raw = np.random.RandomState(seed)._bit_generator.random_raw(max(n - 1, 0)).astype(np.uint64)
+    perm = list(range(n))
+    for i in range(n - 1):
+        j = i + int(raw[i] % np.uint64(n - i))
+        perm[i], perm[j] = perm[j], perm[i]
+    return np.asarray(perm, np.int64)
+
+
+def kmeans_train(x, k: int, niter: int = 10, seed: int = 1234, max_points_per_centroid: int = 256):
+    """faiss 1.7.3 Clustering::train as IndexIVF::train runs it (SURVEY A9) [EXT -- PARITY UNPINNED: restated
+    from the published algorithm, faiss is not installable here].  Returns (centroids (k, d) f32, assign of the
+    LAST iteration, objective per iteration).  Means accumulate in fp32 in point order like faiss's
+    compute_centroids; empty clusters are re-seeded by split_clusters (EPS = 1/1024, RandomGenerator(1234))."""
+    x = _f32(x)
+    n, d = x.shape
+    if n < k:
+        raise RuntimeError(f"Number of training points ({n}) should be at least as large as number of clusters ({k})")
+    if n > k * max_points_per_centroid:
+        x = np.ascontiguousarray(x[rand_perm(n, seed)[: k * max_points_per_centroid]])
+        n = x.shape[0]
+    cent = np.ascontiguousarray(x[rand_perm(n, seed + 1)[:k]])
+    rs = np.random.RandomState(1234)
+    eps = np.float32(1.0 / 1024.0)
+    obj = []
+    a = None
+    for _ in range(niter):
+        a, dist = coarse_assign(x, cent)
+        obj.append(float(dist.astype(np.float64).sum()))
+        sums = np.zeros((k, d), np.float32)
+        np.add.at(sums, a, x)                               # fp32, point order
+        hass = np.bincount(a, minlength=k).astype(np.float32)
+        nz = hass > 0
+        cent = cent.copy()
+        cent[nz] = sums[nz] * (np.float32(1.0) / hass[nz])[:, None]       # faiss: norm = 1 / hassign; c *= norm
+        sign = np.where(np.arange(d) % 2 == 0, eps, -eps).astype(np.float32)
+        for ci in np.nonzero(~nz)[0]:
+            cj = 0
+            while True:
+                p = (hass[cj] - 1.0) / float(n - k)
+                r = float(np.float32(rs._bit_generator.random_raw(1)[0]) / np.float32(4294967295.0))   # mt() / float(mt.max())
+                if r < p:
+                    break
+                cj = (cj + 1) % k
+            cent[ci] = cent[cj]
+            cent[ci] *= (np.float32(1) + sign)
+            cent[cj] *= (np.float32(1) - sign)
+            hass[ci] = hass[cj] // 2
+            hass[cj] -= hass[ci]
+    return cent.astype(np.float32), a, obj
 
 
 def upsample_protect(feats, feats0=None, pitchf=None, protect: float = 0.5):

@@ -78,9 +78,9 @@ def test_gpu_upsample_protect_standalone(rvcr, oracle, golden, name):
 def test_gpu_retrieve_blend_upsample_fused(rvcr, oracle, golden, tmp_path, rname, pname, route):
     """Retrieval + blend + upsample + protect in one call == the reference statements chained (goldens)."""
     import torch
-    from test_gpu_parity import write_oracle_index
     r, p = golden(rname), golden(pname)
-    _, path = write_oracle_index(oracle, tmp_path, r["x"], r["centroids"])
+    path = str(tmp_path / "o.index")
+    oracle.write_index(oracle.OracleIndex.from_vectors(r["x"], r["centroids"]).to_data(), path)
     index = rvcr.read_index(path)
     if route == "scan_tc":
         index.set_option("scan_impl", 5)
