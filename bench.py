@@ -382,7 +382,7 @@ def main():
                          "bytes_per_launch": blend_bytes, "peak_source": pk["source"]}
     dominant = max(roof, key=lambda k: roof[k]["ms"]) if roof else None
     traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if dominant and os.path.exists(traffic_file):
+    if dominant and world == 1 and os.path.exists(traffic_file):   # the capture is of the 1-GPU step
         try:
             tr = json.load(open(traffic_file))
             for k in roof:

@@ -75,7 +75,7 @@ def test_train_subsamples_and_reseeds_empty_clusters(rvcr, oracle):
     """n > 256 * nlist triggers faiss's rand_perm subsample; duplicated points leave clusters empty so
     split_clusters runs.  Too few points raise like faiss."""
     rng = np.random.default_rng(3)
-    k, d = 8, 64
+    k, d = 8, 128                                        # d must be a multiple of 128 (PD_KC tile of the exact kernels)
     base = clustered(rng, 300, d, 3, sigma=0.02)
     x = np.concatenate([base, np.repeat(base[:1], 2400, axis=0)]).astype(np.float32)     # 2700 > 256 * 8
     from importlib import import_module
