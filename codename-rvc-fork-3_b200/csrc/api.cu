@@ -195,6 +195,11 @@ int stage_rows(rvcr_index* h, const float* x_dev, int64_t n, const int32_t* assi
 }
 
 }  // namespace
+
+// kmeans.cu's assignment step: the same dispatch (FFMA-exact vs tcgen05 + exact re-check) as the search path
+int coarse_dispatch_for_train(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, cudaStream_t s) {
+    return coarse_dispatch(h, q, n, list_out, nullptr, s);
+}
 }  // namespace rvcr
 
 using namespace rvcr;
@@ -375,11 +380,16 @@ int rvcr_index_list_sizes(rvcr_index* h, int64_t* sizes_host) {
 }
 
 int rvcr_index_train(rvcr_index* h, const float* x_host, int64_t n) {
-    (void)x_host;
-    (void)n;
-    if (!h) return RVCR_ERR_INVALID;
-    set_error("index.train (faiss k-means) is a SURVEY 8(f) 'next' row; supply centroids with rvcr_index_set_centroids");
-    return RVCR_ERR_UNSUPPORTED;
+    RVCR_ENTER(h);
+    if (!x_host || n <= 0) {
+        set_error("train: need n > 0 host rows");
+        return RVCR_ERR_INVALID;
+    }
+    if (h->nstored > 0 || h->npending > 0) {
+        set_error("train on an index that already holds vectors is unsupported");
+        return RVCR_ERR_STATE;
+    }
+    return kmeans_train(h, x_host, n, nullptr);
 }
 
 int rvcr_index_add_preassigned(rvcr_index* h, const float* x_dev, int64_t n, const int32_t* assign_dev, void* stream) {
@@ -765,6 +775,9 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "tc_resident")) {
         if (value != 0 && value != 6 && value != 8 && value != 9 && value != 10) return RVCR_ERR_INVALID;
         h->opt.tc_resident = value;
+    } else if (!strcmp(key, "kmeans_niter")) {
+        if (value < 0 || value > 1000) return RVCR_ERR_INVALID;
+        h->opt.kmeans_niter = value;
     } else if (!strcmp(key, "fused_blend")) {
         h->opt.fused_blend = value ? 1 : 0;
     } else if (!strcmp(key, "nan_on_zero_score")) {
@@ -790,6 +803,7 @@ int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out) {
     else if (!strcmp(key, "scan_impl")) *value_out = h->opt.scan_impl;
     else if (!strcmp(key, "tc_resident")) *value_out = h->opt.tc_resident;
     else if (!strcmp(key, "fused_blend")) *value_out = h->opt.fused_blend;
+    else if (!strcmp(key, "kmeans_niter")) *value_out = h->opt.kmeans_niter;
     else if (!strcmp(key, "coarse_tc_available")) *value_out = coarse_tc_available() ? 1 : 0;
     else {
         set_error("unknown option '%s'", key);

@@ -65,6 +65,7 @@ struct Options {
                               // TQx4, 3 same with 16 warps, 4 packed TQx8 tile
     int64_t tc_cluster = 2;   // tcgen05 path: 1 = one CTA per SM, 2 = CTA pairs (cta_group::2)
     int64_t fused_blend = 1;  // scan_impl 5: re-check kernel also does the gather + weights + blend
+    int64_t kmeans_niter = 10; // index.train: Lloyd iterations (faiss ClusteringParameters::niter of the Level1Quantizer)
     int64_t tc_resident = 9;  // coarse tcgen05 kernel: query-operand k-blocks pinned in shared memory per work item (0, 6, 8, 9, 10)
 };
 
@@ -196,6 +197,8 @@ int merge_coarse(const float* dist_all, const int32_t* list_all, int G, int64_t 
                  cudaStream_t s);
 int merge_topk(const float* D_all, const int64_t* I_all, int G, int64_t n, int k, float* D, int64_t* I,
                cudaStream_t s);
+// kmeans.cu : index.train (faiss Clustering::train), assignment on the coarse kernels above
+int kmeans_train(rvcr_index* h, const float* x_host, int64_t n, cudaStream_t s);
 // lists.cu
 int finalize_pending(rvcr_index* h, cudaStream_t s);
 int reconstruct(rvcr_index* h, int64_t i0, int64_t ni, float* out_dev, cudaStream_t s);

@@ -141,11 +141,11 @@ class IndexIVFFlat:
 
     # -- build (extract_index.py:65-69) ----------------------------------------------------
     def train(self, x) -> None:
-        """faiss Clustering k-means: host-side Lloyd loop over the GPU assignment."""
-        from .kmeans import train_ivf_centroids
+        """index.train(x) (extract_index.py:65): faiss Clustering k-means, natively in librvcr
+        (rvcr_index_train: tensor-core assignment, deterministic fp32 means, split_clusters)."""
         inf = self._info()
         x = _as_f32_2d(x, inf.d, "train")
-        self.set_centroids(train_ivf_centroids(self, x, int(inf.nlist)))
+        check(lib().rvcr_index_train(self.handle, x.ctypes.data_as(C.c_void_p), x.shape[0]))
 
     def add(self, x) -> None:
         """index.add(x): host (numpy) or device (torch.cuda) rows."""

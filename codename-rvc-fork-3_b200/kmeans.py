@@ -1,76 +1,33 @@
-"""index.train(x) for IndexIVFFlat: faiss `Clustering::train` as a host-side Lloyd loop whose
-assignment step -- the 10 x (n x nlist x d) contractions that are all of the cost -- runs on the GPU
-through rvcr_assign (tcgen05 coarse quantizer + exact re-check).
+"""index.train(x) for IndexIVFFlat: faiss `Clustering::train` -- a thin host wrapper over
+`rvcr_index_train` (csrc/kmeans.cu), where the subsample, the initial centroids, the 10 Lloyd iterations (assignment
+on the tcgen05 coarse quantizer + exact re-check, deterministic point-order fp32 means) and faiss's split_clusters
+for empty clusters all run natively.
 
-Follows faiss 1.7.3 defaults for Level1Quantizer: niter = 10, nredo = 1, seed = 1234,
-max_points_per_centroid = 256 (subsample with rand_perm(n, seed)), initial centroids =
-x[rand_perm(n, seed + 1)[:k]], mean update, empty clusters re-seeded by split_clusters (EPS = 1/1024,
-RandomGenerator(1234)).  SURVEY 8f-2 ranks this row "next": the structure matches faiss, but centroid
-parity with the faiss wheel is NOT claimed (rand_perm / mt19937 draw order restated from memory, and the
-reference's own build is not reproducible: extract_index.py:40 shuffles unseeded).
+Follows faiss 1.7.3 defaults for Level1Quantizer: niter = 10, nredo = 1, seed = 1234, max_points_per_centroid = 256
+(subsample with rand_perm(n, seed)), initial centroids = x[rand_perm(n, seed + 1)[:k]], mean update, empty clusters
+re-seeded by split_clusters (EPS = 1/1024, RandomGenerator(1234)).  Centroid parity with the faiss WHEEL is not
+claimed (faiss is not installable here and the reference's own build is not reproducible: extract_index.py:40 shuffles
+unseeded); parity with the oracle's restatement of the same algorithm is bit for bit (tests/test_gpu_build_flow.py).
 
 Reference call site: `index.train(big_npy)`, rvc/train/process/extract_index.py:65.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
-EPS = 1.0 / 1024.0
+from ._ffi import check, lib
 
 
-def faiss_rand_perm(n: int, seed: int) -> np.ndarray:
-    """faiss utils/random.cpp rand_perm: Fisher-Yates driven by std::mt19937(seed) % (n - i)."""
-    rs = np.random.RandomState(seed)                       # init_genrand(seed), same as std::mt19937(seed)
-    draws = rs.randint(0, 2 ** 32, size=max(n - 1, 0), dtype=np.uint64)
-    perm = np.arange(n, dtype=np.int64)
-    span = np.arange(n, 1, -1, dtype=np.uint64)            # n - i for i = 0 .. n-2
-    j = (np.arange(n - 1, dtype=np.int64) + (draws % span).astype(np.int64)).tolist()
-    p = perm.tolist()
-    for i, i2 in enumerate(j):
-        p[i], p[i2] = p[i2], p[i]
-    return np.asarray(p, dtype=np.int64)
-
-
-def train_ivf_centroids(index, x: np.ndarray, k: int, niter: int = 10, seed: int = 1234,
-                        max_points_per_centroid: int = 256) -> np.ndarray:
-    import torch
-    n, d = x.shape
-    if n < k:
-        raise RuntimeError(f"Number of training points ({n}) should be at least as large as number of clusters ({k})")
-    if n > k * max_points_per_centroid:
-        x = x[faiss_rand_perm(n, seed)[: k * max_points_per_centroid]]
-        n = x.shape[0]
-    dev = torch.device(f"cuda:{index.device}")
-    xd = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(dev)
-    cent = xd[torch.from_numpy(faiss_rand_perm(n, seed + 1)[:k]).to(dev)].clone()
-    rng = np.random.RandomState(1234)
-    for _ in range(niter):
-        index.set_centroids(cent.cpu().numpy())
-        assign, _ = index.assign(xd)                                     # GPU: n x k x d contraction
-        a = assign.to(torch.int64)
-        ok = a >= 0
-        cnt = torch.bincount(a[ok], minlength=k)
-        sums = torch.zeros((k, d), dtype=torch.float32, device=dev)
-        sums.index_add_(0, a[ok], xd[ok])
-        nz = cnt > 0
-        cent = torch.where(nz[:, None], sums * (1.0 / cnt.clamp(min=1).to(torch.float32))[:, None], cent)   # faiss: c *= 1 / hassign
-        empty = torch.nonzero(~nz).flatten().tolist()
-        if empty:                                                          # faiss split_clusters
-            h = cnt.cpu().numpy().astype(np.float64)
-            c = cent.cpu().numpy()
-            sign = np.where(np.arange(d) % 2 == 0, 1.0, -1.0).astype(np.float32)
-            for ci in empty:
-                cj = 0
-                while True:
-                    p = (h[cj] - 1.0) / float(n - k)
-                    r = float(np.float32(rng.randint(0, 2 ** 32, dtype=np.uint64)) / np.float32(4294967295.0))   # mt() / float(mt.max())
-                    if r < p:
-                        break
-                    cj = (cj + 1) % k
-                c[ci] = c[cj]
-                c[ci] *= (1 + sign * EPS)
-                c[cj] *= (1 - sign * EPS)
-                h[ci] = h[cj] // 2
-                h[cj] -= h[ci]
-            cent = torch.from_numpy(c).to(dev)
-    return cent.cpu().numpy()
+def train_ivf_centroids(index, x: np.ndarray, k: int, niter: int = 10) -> np.ndarray:
+    """Train `index` (an untrained, empty IndexIVFFlat with nlist == k) on host rows x; returns the centroids."""
+    x = np.ascontiguousarray(x, np.float32)
+    if x.ndim != 2 or x.shape[1] != index.d or k != index.nlist:
+        raise AssertionError(f"train: expected (n, {index.d}) rows and k == nlist == {index.nlist}")
+    index.set_option("kmeans_niter", int(niter))
+    try:
+        check(lib().rvcr_index_train(index.handle, x.ctypes.data_as(C.c_void_p), x.shape[0]))
+    finally:
+        index.set_option("kmeans_niter", 10)
+    return index.get_centroids()

@@ -120,7 +120,11 @@ RVCR_API int rvcr_index_list_sizes(rvcr_index* h, int64_t* sizes_host);
 
 /* -------------------------------------------------------------------------------- build --- */
 
-/* index.train(x)   (faiss Clustering, niter=10, seed=1234)   extract_index.py:65 */
+/* index.train(x)                                        rvc/train/process/extract_index.py:65
+ * faiss Clustering::train as IndexIVF::train runs it (niter = 10 [option "kmeans_niter"], seed 1234,
+ * subsample to 256 points per centroid with rand_perm(seed), init = x[rand_perm(seed + 1)[:nlist]], fp32
+ * means accumulated in point order, split_clusters for empty clusters).  x_host: n x d fp32, host memory.
+ * The assignment of every iteration runs on the same kernels as rvcr_assign; the result is deterministic. */
 RVCR_API int rvcr_index_train(rvcr_index* h, const float* x_host, int64_t n);
 /* index.add(x)     extract_index.py:67-69 : nearest-centroid assignment + list append; ids are
  * ntotal .. ntotal+n-1; per-list order is ascending id.  x may be host or device memory. */
@@ -208,7 +212,8 @@ RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, i
  *                     in shared memory per work item (0 streams both operands through the L2)
  *       "fused_blend" 1 (default): with scan_impl 5 the exact re-check kernel also applies the 1/score^2 weights and
  *                     the index_rate blend (the 8 neighbour rows are still in cache); 0 = separate gather_blend kernel
- *       "scan_impl" 5 (default) tcgen05 tf32 scan + exact re-check; 1-4 exact FFMA scans */
+ *       "scan_impl" 5 (default) tcgen05 tf32 scan + exact re-check; 1-4 exact FFMA scans
+ *       "kmeans_niter" 10 (default): Lloyd iterations of rvcr_index_train (0 = the initial centroids only) */
 RVCR_API int rvcr_set_option(rvcr_index* h, const char* key, int64_t value);
 RVCR_API int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out);
 RVCR_API int rvcr_get_stats(rvcr_index* h, rvcr_stats* out);

@@ -185,7 +185,6 @@ def kmeans_train(x, k: int, niter: int = 10, seed: int = 1234, max_points_per_ce
         x = np.ascontiguousarray(x[rand_perm(n, seed)[: k * max_points_per_centroid]])
         n = x.shape[0]
     cent = np.ascontiguousarray(x[rand_perm(n, seed + 1)[:k]])
-    rs = np.random.RandomState(1234)
     eps = np.float32(1.0 / 1024.0)
     obj = []
     a = None
@@ -193,24 +192,26 @@ def kmeans_train(x, k: int, niter: int = 10, seed: int = 1234, max_points_per_ce
         a, dist = coarse_assign(x, cent)
         obj.append(float(dist.astype(np.float64).sum()))
         sums = np.zeros((k, d), np.float32)
-        np.add.at(sums, a, x)                               # fp32, point order
-        hass = np.bincount(a, minlength=k).astype(np.float32)
+        np.add.at(sums, a, x)                               # fp32, point order (faiss compute_centroids)
+        hass = np.bincount(a, minlength=k).astype(np.float32)          # faiss keeps hassign as float
         nz = hass > 0
         cent = cent.copy()
         cent[nz] = sums[nz] * (np.float32(1.0) / hass[nz])[:, None]       # faiss: norm = 1 / hassign; c *= norm
+        # split_clusters: `RandomGenerator rng(1234)` is a local of the function, i.e. re-seeded on every call
         sign = np.where(np.arange(d) % 2 == 0, eps, -eps).astype(np.float32)
+        rs = np.random.RandomState(1234)
         for ci in np.nonzero(~nz)[0]:
             cj = 0
             while True:
-                p = (hass[cj] - 1.0) / float(n - k)
-                r = float(np.float32(rs._bit_generator.random_raw(1)[0]) / np.float32(4294967295.0))   # mt() / float(mt.max())
+                p = np.float32((np.float64(hass[cj]) - 1.0) / np.float64(np.float32(n - k)))
+                r = np.float32(rs._bit_generator.random_raw(1)[0]) / np.float32(4294967295.0)   # mt() / float(mt.max())
                 if r < p:
                     break
                 cj = (cj + 1) % k
             cent[ci] = cent[cj]
             cent[ci] *= (np.float32(1) + sign)
             cent[cj] *= (np.float32(1) - sign)
-            hass[ci] = hass[cj] // 2
+            hass[ci] = hass[cj] / np.float32(2)
             hass[cj] -= hass[ci]
     return cent.astype(np.float32), a, obj
 
