@@ -92,4 +92,22 @@ oracle.build_lists(xs, np.asarray(a, np.int32), nlist)
 t_cpu = time.perf_counter() - t0
 res["cpu_port"] = {"sample_rows": 65536, "seconds": t_cpu, "vectors_per_s": 65536 / t_cpu,
                    "threads": oracle.num_threads(), "kind": "port (extrapolates linearly to 4 M rows)"}
+# ---- index.train at C4 scale: rvcr_index_train on 4 M host rows (extract_index.py:65) ----------------
+del index, vecs, ids, offs, seg
+torch.cuda.empty_cache()
+if "--train" in sys.argv:
+    xh = np.empty((N, d), np.float32)
+    for c0 in range(0, N, 1 << 19):
+        xh[c0:c0 + (1 << 19)] = make_rows(c0, min(N, c0 + (1 << 19))).cpu().numpy()
+    tindex = rvcr.index_factory(d, f"IVF{nlist},Flat", device=0)
+    t0 = time.perf_counter()
+    tindex.train(xh)
+    torch.cuda.synchronize()
+    t_train = time.perf_counter() - t0
+    c = tindex.get_centroids()
+    # 10 assignments of N rows against nlist centroids (n <= 256 * nlist: no subsampling at C4)
+    res["train"] = {"seconds": t_train, "niter": 10, "assign_pflop": 10 * 2.0 * N * nlist * d / 1e15,
+                    "pflops": 10 * 2.0 * N * nlist * d / 1e15 / t_train, "finite": bool(np.isfinite(c).all()),
+                    "cpu_port_estimate_s": 10 * N / res["cpu_port"]["vectors_per_s"],
+                    "cpu_port_note": "10 x the measured CPU assignment rate above (sgemm coarse), extrapolated"}
 print(json.dumps(res))
