@@ -236,6 +236,7 @@ def main():
     ap.add_argument("--fused-blend", type=int, default=-1, help="1 = re-check kernel also blends (default), 0 = separate gather_blend kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="N > 1: use the NCCL all-to-all transport instead of peer memory")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -289,8 +290,24 @@ def main():
     setup_s = time.time() - t_setup
 
     sh = None
+    peer = None
+    transport = None
+    total_steps = args.warmup + args.steps
     if world > 1:
         sh = sharded.ShardedIndex(sharded.CudaShardBackend(index))
+        transport = "nccl all-to-all (dispatch + combine)"
+        if not args.no_peer:
+            try:                                                   # collective: raises on every rank or on none
+                peer = sh.enable_peer((total_steps + 2) * n_home + 16, d)
+                transport = "peer memory over NVLink (cudaIpc): owner pulls rows, blend epilogue pushes them home"
+            except Exception as ex:
+                transport += f"; peer memory unavailable: {str(ex)[:160]}"
+
+    def fresh(slot):
+        """a fresh (un-blended) copy of this rank's queries; inside the peer buffer when that transport is on"""
+        if peer is None:
+            return q_home.clone()
+        return peer.rows(n_home, slot * n_home).copy_(q_home)
 
     def step(buf):
         if sh is None:
@@ -303,8 +320,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    total_steps = args.warmup + args.steps
-    bufs = [q_home.clone() for _ in range(total_steps)]       # every step gets a fresh (un-blended) input
+    bufs = [fresh(i) for i in range(total_steps)]             # every step gets a fresh (un-blended) input
     sampler = ClockSampler(local_rank)
     sampler.start()
     step(bufs[0])                                             # first call: lazy setup (row norms, tensor maps, scratch)
@@ -342,7 +358,7 @@ def main():
     phase_acc = {}
     reps = max(1, min(args.steps, 3))
     for _ in range(reps):
-        b = q_home.clone()
+        b = fresh(total_steps)
         step(b)
         torch.cuda.synchronize()
         for k, v in index.phase_ms().items():
@@ -404,7 +420,8 @@ def main():
             if sh is None:
                 index.retrieve_blend_host_(host.numpy(), INDEX_RATE)     # H2D, search+blend, D2H, sync
             else:
-                sh.retrieve_blend_host_(host, INDEX_RATE)                # chunked H2D under the coarse step, D2H, sync
+                sh.retrieve_blend_host_(host, INDEX_RATE,                 # chunked H2D under the coarse step, D2H, sync
+                                        device_rows=peer.rows(n_home, (total_steps + 1) * n_home) if peer is not None else None)
             barrier()
             if it > 0:
                 times.append(time.perf_counter() - t0)
@@ -454,6 +471,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": args.workload, "index_vectors": N, "d": d, "nlist": nlist, "query_frames": nq, "k": K,
                            "nprobe": 1, "index_rate": INDEX_RATE, "parallelism": f"lists sharded over {world} GPU(s)",
+                           **({"transport": transport} if transport else {}),
                            "l2": "inputs larger than L2 (fresh 3 KB/query feature buffer per step; lists >> 126 MB)"
                            if nq * d * 4 > (126 << 20) else "inputs smaller than L2",
                            "coarse": "tcgen05 bf16 + exact fp32 re-check" if st["coarse_tc_queries"] else "exact FFMA",
@@ -469,6 +487,8 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if peer is not None:
+            peer.close()
         dist.destroy_process_group()
 
 

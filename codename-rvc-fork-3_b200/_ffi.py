@@ -71,6 +71,12 @@ SIGNATURES = {
     "rvcr_upsample_protect": (C.c_int, [_P, _P, _P, _I64, _I32, C.c_double, _P, C.c_int, _P]),
     "rvcr_retrieve_blend_host": (C.c_int, [_H, _P, _I64, C.c_double]),
     "rvcr_retrieve_blend_assigned": (C.c_int, [_H, _P, _I64, _P, C.c_double, _P, _P, _P]),
+    "rvcr_retrieve_blend_assigned_push": (C.c_int, [_H, _P, _I64, _P, C.c_double, _P, _P, _P, _P]),
+    "rvcr_peer_alloc": (C.c_int, [C.c_int, _I64, C.POINTER(_P), _P]),
+    "rvcr_peer_open": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "rvcr_peer_close": (C.c_int, [C.c_int, _P]),
+    "rvcr_peer_free": (C.c_int, [C.c_int, _P]),
+    "rvcr_peer_pull_rows": (C.c_int, [_P, _P, _P, _I64, _I32, _P, C.c_int, _P]),
     "rvcr_search_assigned": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P]),
     "rvcr_reconstruct_n": (C.c_int, [_H, _I64, _I64, _P, C.c_int]),
     "rvcr_merge_coarse": (C.c_int, [_P, _P, _I32, _I64, _P, C.c_int, _P]),

@@ -707,6 +707,99 @@ int rvcr_retrieve_blend_assigned(rvcr_index* h, float* feats_dev, int64_t n, con
     return search_device(h, feats_dev, n, assign_dev, true, index_rate, D_dev, I_dev, (cudaStream_t)stream);
 }
 
+int rvcr_retrieve_blend_assigned_push(rvcr_index* h, const float* rows_dev, int64_t m, const int32_t* assign_dev,
+                                      double index_rate, float* const* dst_bases_dev, const int32_t* dst_rank_dev,
+                                      const int32_t* dst_row_dev, void* stream) {
+    RVCR_ENTER(h);
+    if (m > 0 && (!rows_dev || !assign_dev || !dst_bases_dev || !dst_rank_dev || !dst_row_dev)) return RVCR_ERR_INVALID;
+    if (h->d % 4 != 0) {
+        set_error("d=%d unsupported (must be a multiple of 4)", h->d);
+        return RVCR_ERR_UNSUPPORTED;
+    }
+    // the blend epilogues write row qi to dst_bases[dst_rank[qi]] + dst_row[qi] * d (peer-mapped memory) instead of rows_dev
+    h->fuse.push.bases = dst_bases_dev;
+    h->fuse.push.rank = dst_rank_dev;
+    h->fuse.push.row = dst_row_dev;
+    const int rc = search_device(h, const_cast<float*>(rows_dev), m, assign_dev, true, index_rate, nullptr, nullptr, (cudaStream_t)stream);
+    h->fuse.push = PushArgs{};
+    return rc;
+}
+
+int rvcr_peer_alloc(int device, int64_t bytes, void** ptr_out, unsigned char* handle64_out) {
+    if (bytes <= 0 || !ptr_out || !handle64_out) return RVCR_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    DeviceGuard g(device);
+    if (!g.ok) {
+        set_error("cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return RVCR_ERR_CUDA;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) {
+        set_error("peer buffer of %lld bytes: %s", (long long)bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return RVCR_ERR_OOM;
+    }
+    cudaIpcMemHandle_t hd;
+    e = cudaIpcGetMemHandle(&hd, p);
+    if (e != cudaSuccess) {
+        set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        cudaFree(p);
+        return RVCR_ERR_CUDA;
+    }
+    memcpy(handle64_out, &hd, 64);
+    *ptr_out = p;
+    return RVCR_OK;
+}
+
+int rvcr_peer_open(int device, const unsigned char* handle64, void** ptr_out) {
+    if (!handle64 || !ptr_out) return RVCR_ERR_INVALID;
+    DeviceGuard g(device);
+    if (!g.ok) {
+        set_error("cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return RVCR_ERR_CUDA;
+    }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        set_error("cudaIpcOpenMemHandle failed: %s (no peer access between these GPUs / processes?)", cudaGetErrorString(e));
+        cudaGetLastError();
+        return RVCR_ERR_CUDA;
+    }
+    *ptr_out = p;
+    return RVCR_OK;
+}
+
+int rvcr_peer_close(int device, void* ptr) {
+    if (!ptr) return RVCR_OK;
+    DeviceGuard g(device);
+    if (!g.ok) return RVCR_ERR_CUDA;
+    RVCR_CUDA(cudaIpcCloseMemHandle(ptr));
+    return RVCR_OK;
+}
+
+int rvcr_peer_free(int device, void* ptr) {
+    if (!ptr) return RVCR_OK;
+    DeviceGuard g(device);
+    if (!g.ok) return RVCR_ERR_CUDA;
+    RVCR_CUDA(cudaFree(ptr));
+    return RVCR_OK;
+}
+
+int rvcr_peer_pull_rows(const float* const* bases_dev, const int32_t* src_rank_dev, const int32_t* src_row_dev, int64_t m,
+                        int32_t d, float* out_dev, int device, void* stream) {
+    if (m < 0 || d < 1 || (m > 0 && (!bases_dev || !src_rank_dev || !src_row_dev || !out_dev))) return RVCR_ERR_INVALID;
+    DeviceGuard g(device);
+    if (!g.ok) {
+        set_error("cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return RVCR_ERR_CUDA;
+    }
+    return peer_pull_rows(bases_dev, src_rank_dev, src_row_dev, m, d, out_dev, (cudaStream_t)stream);
+}
+
 int rvcr_search_assigned(rvcr_index* h, const float* q_dev, int64_t n, const int32_t* assign_dev, float* D_dev, int64_t* I_dev,
                          void* stream) {
     RVCR_ENTER(h);

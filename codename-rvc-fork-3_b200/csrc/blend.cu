@@ -24,16 +24,16 @@ namespace rvcr {
 // work items [item_begin, item_end) (a contiguous range: items are ordered by sorted position) and writes
 // the blended row of query qorder[p] to out + qorder[p]*d -- `out` may be mapped pinned host memory, in
 // which case the rows go straight over PCIe while the next wave of lists is being scanned.
-// POST: also apply the 2x upsample + protect mix and write to post.out2 (separate instantiation: the default kernel
-// is unchanged).
-template <bool POST>
+// MODE 1: also apply the 2x upsample + protect mix and write to post.out2; MODE 2: push the row to its home rank's buffer
+// over NVLink (separate instantiations: the default kernel, MODE 0, is unchanged).
+template <int MODE>
 __global__ void __launch_bounds__(256)
 gather_blend_kernel(float* __restrict__ feats, int64_t n, int d, const float* __restrict__ D,
                     const int32_t* __restrict__ P, const int32_t* __restrict__ assign, int64_t own_lo,
                     int64_t own_hi, const float* __restrict__ vecs, int64_t last_row_pos, float r32, float omr32,
                     const int32_t* __restrict__ qorder, const int32_t* __restrict__ items,
                     const int32_t* __restrict__ nitems_ptr, int item_begin, int item_end, float* __restrict__ out,
-                    PostArgs post) {
+                    PostArgs post, PushArgs push) {
     __shared__ float sw[RVCR_K];
     __shared__ int spos[RVCR_K];
     const int tid = threadIdx.x;
@@ -76,7 +76,7 @@ gather_blend_kernel(float* __restrict__ feats, int64_t n, int d, const float* __
             rows[k] = spos[k] >= 0 ? reinterpret_cast<const float4*>(vecs + (int64_t)spos[k] * d) : nullptr;
         }
         const float4* f4 = reinterpret_cast<const float4*>(feats + qi * d);
-        float4* o4 = reinterpret_cast<float4*>((out ? out : feats) + qi * d);
+        float4* o4 = MODE == 2 ? push_row_ptr(push, qi, d) : reinterpret_cast<float4*>((out ? out : feats) + qi * d);
         for (int c = tid; c < nvec; c += blockDim.x) {
             float4 v[RVCR_K];
 #pragma unroll
@@ -99,7 +99,7 @@ gather_blend_kernel(float* __restrict__ feats, int64_t n, int d, const float* __
             o.y = __fadd_rn(__fmul_rn(acc.y, r32), __fmul_rn(omr32, f.y));
             o.z = __fadd_rn(__fmul_rn(acc.z, r32), __fmul_rn(omr32, f.z));
             o.w = __fadd_rn(__fmul_rn(acc.w, r32), __fmul_rn(omr32, f.w));
-            if (POST) post_store(post, qi, d, c, o, f);   // fused 2x upsample + protect mix (pipeline.py:463-481)
+            if (MODE == 1) post_store(post, qi, d, c, o, f);   // fused 2x upsample + protect mix (pipeline.py:463-481)
             else o4[c] = o;
         }
         __syncthreads();
@@ -120,10 +120,10 @@ int gather_blend(rvcr_index* h, float* feats, int64_t n, const float* D, const i
     if (threads < 32) threads = 32;
     int64_t grid = (int64_t)h->num_sms * (2048 / threads);
     if (grid > n) grid = n;
-    auto kern = h->fuse.post.out2 ? gather_blend_kernel<true> : gather_blend_kernel<false>;
+    auto kern = h->fuse.post.out2 ? gather_blend_kernel<1> : (h->fuse.push.bases ? gather_blend_kernel<2> : gather_blend_kernel<0>);
     kern<<<(unsigned)grid, threads, 0, s>>>(feats, n, h->d, D, P, assign, h->own_lo, h->own_hi, h->vecs,
                                                             h->last_row_pos, r32, omr32, nullptr, nullptr, nullptr, 0, 0,
-                                                            nullptr, h->fuse.post);
+                                                            nullptr, h->fuse.post, h->fuse.push);
     RVCR_CHECK_LAUNCH();
     count_launch(h);
     return RVCR_OK;
@@ -139,10 +139,10 @@ int gather_blend_range(rvcr_index* h, const float* feats, int64_t n, const float
     if (threads > 256) threads = 256;
     if (threads < 32) threads = 32;
     int64_t grid = max_ctas > 0 ? max_ctas : (int64_t)h->num_sms * (2048 / threads);
-    gather_blend_kernel<false><<<(unsigned)grid, threads, 0, s>>>(const_cast<float*>(feats), n, h->d, D, P, nullptr, h->own_lo, h->own_hi,
+    gather_blend_kernel<0><<<(unsigned)grid, threads, 0, s>>>(const_cast<float*>(feats), n, h->d, D, P, nullptr, h->own_lo, h->own_hi,
                                                             h->vecs, h->last_row_pos, r32, omr32, h->ws_vals2.as<int32_t>(),
                                                             h->ws_items.as<int32_t>(), h->ws_misc.as<int32_t>(), item_begin,
-                                                            item_end, out, PostArgs{});
+                                                            item_end, out, PostArgs{}, PushArgs{});
     RVCR_CHECK_LAUNCH();
     count_launch(h);
     return RVCR_OK;

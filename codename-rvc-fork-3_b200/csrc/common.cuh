@@ -78,6 +78,15 @@ struct PostArgs {
     float protect = 0.f;
 };
 
+// Multi-GPU combine fused into the blend epilogue: the owner shard writes each blended row straight into the HOME rank's
+// feature buffer over NVLink (peer-mapped memory, cudaIpc), instead of a local write + NCCL all-to-all + scatter.
+// Row qi of the local batch goes to bases[rank[qi]] + row[qi] * d.
+struct PushArgs {
+    float* const* bases = nullptr;   // device array of G peer-mapped base pointers (own buffer included); nullptr = off
+    const int32_t* rank = nullptr;   // per local row: home rank
+    const int32_t* row = nullptr;    // per local row: row index inside the home rank's buffer
+};
+
 }  // namespace rvcr
 
 // The handle behind the C ABI.
@@ -149,6 +158,7 @@ struct rvcr_index {
         float* out = nullptr;
         float r32 = 0.f, omr32 = 0.f;
         rvcr::PostArgs post;   // rvcr_retrieve_blend_upsample: rows go to post.out2 (2n x d), feats stay untouched
+        rvcr::PushArgs push;   // rvcr_retrieve_blend_assigned_push: rows go to their home rank's buffer (peer memory)
     } fuse;
 
     bool tc_counters_dirty = false;
@@ -190,6 +200,9 @@ int gather_blend_range(rvcr_index* h, const float* feats, int64_t n, const float
 int gather_blend(rvcr_index* h, float* feats, int64_t n, const float* D, const int32_t* P,
                  const int32_t* assign /*nullable: restrict to owned*/, double index_rate,
                  cudaStream_t s);
+// peer.cu : peer-memory (cudaIpc over NVLink) plumbing of the sharded path
+int peer_pull_rows(const float* const* bases, const int32_t* src_rank, const int32_t* src_row, int64_t m, int d, float* out,
+                   cudaStream_t s);
 // post.cu : standalone 2x upsample + protect mix (pipeline.py:463-481) for callers that skipped retrieval
 int upsample_protect(const float* feats, const float* feats0, const float* pitchf, int64_t n, int d, double protect, float* out,
                      cudaStream_t s);
@@ -271,6 +284,11 @@ __device__ __forceinline__ void post_store(const PostArgs& pa, int64_t qi, int d
         *r0 = o;
         *r1 = o;
     }
+}
+
+// destination of the blended row of local query qi when the epilogue pushes to peer memory
+__device__ __forceinline__ float4* push_row_ptr(const PushArgs& pa, int64_t qi, int d) {
+    return reinterpret_cast<float4*>(pa.bases[pa.rank[qi]] + (int64_t)pa.row[qi] * d);
 }
 
 // (dist, pos) strict total order used everywhere a top-k decision is made: distance ascending,

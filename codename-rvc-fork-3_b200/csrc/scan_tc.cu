@@ -548,6 +548,7 @@ struct BlendArgs {
     int64_t last_row_pos;   // numpy's big_npy[-1] for (FLT_MAX, -1) padding
     float r32, omr32;
     PostArgs post;          // optional fused 2x upsample + protect mix: rows go to post.out2 instead of `out`
+    PushArgs push;          // optional fused multi-GPU combine: rows go to their home rank's buffer (peer memory)
 };
 
 __device__ __forceinline__ void blend_weights(float td, int tp, int lane, int64_t last_row_pos, float& wn, int& spos) {
@@ -593,8 +594,9 @@ __device__ __forceinline__ float4 blend_vec(const float4 (&v)[RVCR_K], const flo
 // BLEND: the warp that has just found a query's exact top-8 also gathers those 8 rows (it read them a moment ago:
 // L1 / L2 hits instead of a second trip to HBM), applies the 1/score^2 weights and the index_rate blend and writes
 // the output row -- rvc/infer/pipeline.py:500-506 without a separate gather kernel.
-// BLEND: 0 = search only, 1 = + fused tail in place, 2 = + fused tail + 2x upsample / protect mix into post.out2 (a separate
-// instantiation so the default kernel's code and register count stay exactly as profiled).
+// BLEND: 0 = search only, 1 = + fused tail in place, 2 = + fused tail + 2x upsample / protect mix into post.out2, 3 = + fused
+// tail pushed to the home rank's buffer over NVLink (separate instantiations so the default kernel's code and register
+// count stay exactly as profiled).
 template <int BLEND>
 __global__ void __launch_bounds__(RC_WARPS * 32)
 scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qorder, const uint32_t* __restrict__ keys,
@@ -668,7 +670,7 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
                 const int pk = __shfl_sync(0xffffffffu, spos, k);
                 rows[k] = pk >= 0 ? reinterpret_cast<const float4*>(vecs + (int64_t)pk * d) : nullptr;
             }
-            float4* o4 = reinterpret_cast<float4*>(ba.out + qi * d);
+            float4* o4 = BLEND == 3 ? push_row_ptr(ba.push, qi, d) : reinterpret_cast<float4*>(ba.out + qi * d);
             for (int c = lane; c < nvec; c += 32) {
                 float4 v[RVCR_K];
 #pragma unroll
@@ -755,7 +757,7 @@ scan_exact_fallback_kernel(const float* __restrict__ q, const int32_t* __restric
                 wk[k] = sw[k];
                 rows[k] = sp[k] >= 0 ? reinterpret_cast<const float4*>(vecs + (int64_t)sp[k] * d) : nullptr;
             }
-            float4* o4 = reinterpret_cast<float4*>(ba.out + qi * d);
+            float4* o4 = BLEND == 3 ? push_row_ptr(ba.push, qi, d) : reinterpret_cast<float4*>(ba.out + qi * d);
             for (int c = tid; c < (d >> 2); c += 256) {
                 float4 v[RVCR_K];
 #pragma unroll
@@ -899,7 +901,8 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     RVCR_CHECK_LAUNCH();
     // fused tail (search_device sets h->fuse for rvcr_retrieve_blend*): the re-check / fallback kernels also blend
     const bool blend = h->fuse.active;
-    BlendArgs ba{h->fuse.out, h->last_row_pos, h->fuse.r32, h->fuse.omr32, h->fuse.post};
+    BlendArgs ba{h->fuse.out, h->last_row_pos, h->fuse.r32, h->fuse.omr32, h->fuse.post, h->fuse.push};
+    const int bmode = !blend ? 0 : (ba.post.out2 ? 2 : (ba.push.bases ? 3 : 1));
     {
         PhaseTimer pt(h, RVCR_PHASE_SCAN_RECHECK, s);
         // One warp per query, 32 warps per SM.  A variant that staged the candidate rows in shared memory with
@@ -912,7 +915,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
             if (const char* e = getenv("RVCR_RC_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // tuning knob
             int64_t rgrid = (int64_t)h->num_sms * per_sm;
             if (rgrid * RC_WARPS > n) rgrid = (n + RC_WARPS - 1) / RC_WARPS;
-            auto kern = !blend ? scan_recheck_kernel<0> : (ba.post.out2 ? scan_recheck_kernel<2> : scan_recheck_kernel<1>);
+            auto kern = bmode == 0 ? scan_recheck_kernel<0> : bmode == 1 ? scan_recheck_kernel<1> : bmode == 2 ? scan_recheck_kernel<2> : scan_recheck_kernel<3>;
             kern<<<(unsigned)rgrid, RC_WARPS * 32, rsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), (uint32_t)h->nlist,
                                                              h->ws_items.as<int32_t>(), h->ws_misc.as<int32_t>(), item_begin, item_end, n,
                                                              d, h->vecs, h->ids, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
@@ -923,7 +926,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     {
         PhaseTimer pt(h, RVCR_PHASE_SCAN_FALLBACK, s);
         const size_t fsm = (size_t)(d + 48) * 4;
-        auto kern = !blend ? scan_exact_fallback_kernel<0> : (ba.post.out2 ? scan_exact_fallback_kernel<2> : scan_exact_fallback_kernel<1>);
+        auto kern = bmode == 0 ? scan_exact_fallback_kernel<0> : bmode == 1 ? scan_exact_fallback_kernel<1> : bmode == 2 ? scan_exact_fallback_kernel<2> : scan_exact_fallback_kernel<3>;
         kern<<<h->num_sms * 2, 256, fsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), h->ws_fb.as<int32_t>(), fb_count,
                                               (uint32_t)h->nlist, d, h->vecs, h->ids, h->offsets, D, P, I, ba);
         RVCR_CHECK_LAUNCH();

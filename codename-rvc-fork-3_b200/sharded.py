@@ -21,6 +21,13 @@ One retrieve_blend step, queries sharded by "home" rank (each rank brings its ow
 (real candidates only for the lists it owns), the candidates are all-gathered (96 B / query / shard)
 and merged by (distance, id).
 
+With peer memory enabled (`ShardedIndex.enable_peer`: every rank's feature buffer is a cudaMalloc allocation mapped
+into all other ranks with cudaIpc over NVLink / NVSwitch) steps 2 and 4 need no collective: after a 4-byte-per-query
+all-gather of the list ids (which is also the barrier that says every rank finished step 1), the owner PULLS its
+rows out of their home ranks' buffers (one gather kernel over peer pointers) and the blend epilogue of step 3 PUSHES
+each blended row straight into its home rank's buffer -- compute and combine in one kernel, no send / recv staging,
+no scatter pass.  The NCCL all-to-all transport stays for tensors outside the peer buffer.
+
 No floating-point reduction crosses ranks, so G-GPU results equal 1-GPU results bit for bit.
 """
 from __future__ import annotations
@@ -66,6 +73,17 @@ class CudaShardBackend:
                 C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()), self._stream(feats)))
         return D, I
 
+    def scan_assigned_push(self, rows, assign, index_rate, peer, dst_rank, dst_row):
+        """Step 3 + 4 fused: scan + top-8 + gather + blend of the pulled rows; the blend epilogue writes row i to
+        peer buffer dst_rank[i], row dst_row[i] (NVLink stores) instead of `rows`."""
+        m = rows.shape[0]
+        if m == 0:
+            return
+        self._check(self._lib().rvcr_retrieve_blend_assigned_push(
+            self.index.handle, C.c_void_p(rows.data_ptr()), m, C.c_void_p(assign.data_ptr()), float(index_rate),
+            C.c_void_p(peer.bases_dev.data_ptr()), C.c_void_p(dst_rank.data_ptr()), C.c_void_p(dst_row.data_ptr()),
+            self._stream(rows)))
+
     def merge_topk(self, D_all, I_all):
         import torch
         G, n, k = D_all.shape
@@ -78,8 +96,106 @@ class CudaShardBackend:
         return D, I
 
 
+class CudaPeer:
+    """One feature buffer per rank (rvcr_peer_alloc), IPC-mapped into every other rank of the group.
+
+    `rows(n, slot)` hands out (n, d) float32 tensors inside the own buffer; `pull_rows` gathers rows out of any
+    rank's buffer through the peer mapping.  Construction is collective; it raises on every rank if any rank cannot
+    map its peers (no NVLink / P2P between the GPUs, IPC disabled), so the caller can stay on the NCCL transport."""
+
+    def __init__(self, capacity_rows: int, d: int, device: int, group=None):
+        import torch
+        import torch.distributed as dist
+        from ._ffi import check, lib
+        from .faiss_compat import _view
+        self._lib, self._check, self._view = lib, check, _view
+        self.d, self.device, self.group = int(d), int(device), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.capacity_rows = int(capacity_rows)
+        self.nbytes = self.capacity_rows * self.d * 4
+        self._own = C.c_void_p()
+        self._opened = []
+        handle = (C.c_ubyte * 64)()
+        err = None
+        try:
+            check(lib().rvcr_peer_alloc(self.device, self.nbytes, C.byref(self._own), handle))
+        except Exception as ex:                                    # keep the collective below in step on every rank
+            err = ex
+        mine = (bytes(handle), self.nbytes, err is None)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self.ptrs = [0] * self.world
+        if err is None and all(e[2] for e in everyone):
+            for r, (hd, nb, _) in enumerate(everyone):
+                if r == self.rank:
+                    self.ptrs[r] = self._own.value
+                    continue
+                p = C.c_void_p()
+                try:
+                    check(lib().rvcr_peer_open(self.device, (C.c_ubyte * 64).from_buffer_copy(hd), C.byref(p)))
+                    self._opened.append(p)
+                    self.ptrs[r] = p.value
+                except Exception as ex:
+                    err = ex
+                    break
+        elif err is None:
+            err = RuntimeError("a peer rank could not allocate its buffer")
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=f"cuda:{self.device}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise RuntimeError(f"peer memory unavailable: {err if err else 'another rank failed to map its peers'}")
+        self.sizes = [e[1] for e in everyone]
+        self.bases_dev = torch.tensor(self.ptrs, dtype=torch.int64, device=f"cuda:{self.device}")
+        self._flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{self.device}")
+
+    def rows(self, n: int, row0: int = 0):
+        """(n, d) float32 tensor over rows [row0, row0 + n) of this rank's buffer (no copy)."""
+        if row0 < 0 or n < 0 or row0 + n > self.capacity_rows:
+            raise ValueError(f"rows [{row0}, {row0 + n}) outside the peer buffer of {self.capacity_rows} rows")
+        return self._view(self.ptrs[self.rank] + row0 * self.d * 4, (n, self.d), "<f4", self.device)
+
+    def row_offset(self, t):
+        """Row index of tensor t inside this rank's buffer, or None if t lives elsewhere."""
+        if not (t.is_cuda and t.dim() == 2 and t.shape[1] == self.d and t.is_contiguous()):
+            return None
+        off = t.data_ptr() - self.ptrs[self.rank]
+        if off < 0 or off % (self.d * 4) or off + t.shape[0] * self.d * 4 > self.nbytes:
+            return None
+        return off // (self.d * 4)
+
+    def pull_rows(self, src_rank, src_row):
+        """rows[i] = buffer[src_rank[i]][src_row[i]] (int32 device tensors) -> new local (m, d) tensor."""
+        import torch
+        m = src_rank.shape[0]
+        out = torch.empty((m, self.d), dtype=torch.float32, device=src_rank.device)
+        if m:
+            st = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
+            self._check(self._lib().rvcr_peer_pull_rows(C.c_void_p(self.bases_dev.data_ptr()), C.c_void_p(src_rank.data_ptr()),
+                                                        C.c_void_p(src_row.data_ptr()), m, self.d, C.c_void_p(out.data_ptr()),
+                                                        self.device, st))
+        return out
+
+    def fence(self, dist):
+        """Stream-ordered cross-rank barrier: when it completes, every rank's pushes issued before its own fence
+        have landed (kernel completion makes peer stores visible)."""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        for p in self._opened:
+            try:
+                self._lib().rvcr_peer_close(self.device, p)
+            except Exception:
+                pass
+        self._opened = []
+        if self._own.value:
+            self._lib().rvcr_peer_free(self.device, self._own)
+            self._own = C.c_void_p()
+
+
 class ShardedIndex:
     """A shard of an IVF-Flat index plus the collectives that make G shards answer as one index."""
+    peer = None
 
     def __init__(self, backend, group=None):
         import torch
@@ -129,13 +245,57 @@ class ShardedIndex:
             assign, _ = self.be.assign(feats)                                            # 1
         else:
             assign = torch.empty(0, dtype=torch.int32, device=feats.device)
+        if self.peer is not None:
+            row0 = None if want_neighbours else (0 if n == 0 else self.peer.row_offset(feats))   # an empty batch fits anywhere
+            return self._peer_scan_push(feats, assign, -1 if row0 is None else row0, index_rate, want_neighbours)
         return self._route_scan_combine(feats, assign, index_rate, want_neighbours)
 
-    def retrieve_blend_host_(self, host, index_rate: float, chunk_rows: int = 131072):
+    def enable_peer(self, capacity_rows: int, d: int | None = None, transport=None):
+        """Collective.  Allocate a peer-mapped feature buffer of `capacity_rows` rows on every rank; tensors handed out
+        by `self.peer.rows(n, row0)` then take the pull / push path in `retrieve_blend_`.  Raises (on every rank) when
+        the GPUs cannot map each other's memory."""
+        self.peer = transport if transport is not None else CudaPeer(capacity_rows, d or self.be.d, self.be.device, self.group)
+        return self.peer
+
+    def _peer_scan_push(self, feats, assign, row0, index_rate, want_neighbours=False):
+        """Steps 2-4 over peer memory.  feats = rows [row0, row0 + n) of this rank's peer buffer, blended in place by
+        whichever ranks own the lists.  row0 = -1 (tensor outside the peer buffer, or neighbours wanted) on ANY rank
+        sends every rank down the NCCL all-to-all route: the transport choice is collective."""
+        import torch
+        G, me, dev = self.world, self.rank, feats.device
+        n = feats.shape[0]
+        meta = torch.tensor([n, row0], dtype=torch.int64, device=dev)
+        metas = torch.empty((G, 2), dtype=torch.int64, device=dev)
+        self.dist.all_gather_into_tensor(metas.view(-1), meta, group=self.group)
+        metas_h = metas.tolist()                                   # host waits here for the coarse step (nothing else to do)
+        if any(int(x[1]) < 0 for x in metas_h):
+            return self._route_scan_combine(feats, assign, index_rate, want_neighbours)
+        nmax = max(int(x[0]) for x in metas_h)
+        if nmax == 0:
+            return feats
+        apad = torch.full((nmax,), -2, dtype=torch.int32, device=dev)              # -2 = padding, -1 = invalid (NaN) query
+        apad[:n] = assign
+        a_all = torch.empty((G, nmax), dtype=torch.int32, device=dev)
+        # 4 bytes per query; also the barrier: nobody scans (and pushes into a home buffer) before everyone's coarse is done
+        self.dist.all_gather_into_tensor(a_all.view(-1), apad, group=self.group)
+        mine = (self._owner(a_all.view(-1)).view(G, nmax) == me) & (a_all != -2)
+        sel = mine.nonzero()                                        # (m, 2): (home rank, row in the home batch), home-major
+        src_rank = sel[:, 0].to(torch.int32)
+        base = torch.tensor([int(x[1]) for x in metas_h], dtype=torch.int64, device=dev)
+        src_row = (sel[:, 1] + base[sel[:, 0]]).to(torch.int32)
+        rows = self.peer.pull_rows(src_rank, src_row)                                # 2: pull over NVLink
+        rows_assign = a_all[sel[:, 0], sel[:, 1]].contiguous()
+        self.be.scan_assigned_push(rows, rows_assign, index_rate, self.peer, src_rank, src_row)   # 3 + 4 fused
+        self.peer.fence(self.dist)                                  # all pushes into my buffer have landed
+        return feats
+
+    def retrieve_blend_host_(self, host, index_rate: float, chunk_rows: int = 131072, device_rows=None):
         """Same step on this rank's HOST rows (a pinned (n_r, d) float32 torch tensor), in place: the rows go up in
         chunks on a copy stream while the tensor cores already assign the previous chunk (the coarse step is
         per-query independent, rvcr_retrieve_blend_host does the same on one GPU); dispatch / scan / combine run on
-        the whole batch; one device -> host copy brings the blended rows back.  Every rank must call it."""
+        the whole batch; one device -> host copy brings the blended rows back.  Every rank must call it.
+        `device_rows`: optional (n, d) device staging tensor -- rows of the peer buffer (`self.peer.rows`) make the
+        step take the pull / push transport."""
         import torch
         n, d = host.shape
         dev = self._device()
@@ -144,7 +304,8 @@ class ShardedIndex:
             self.retrieve_blend_(feats, index_rate)
             host.copy_(feats)
             return host
-        feats = torch.empty((n, d), dtype=torch.float32, device=dev)
+        feats = device_rows if device_rows is not None else torch.empty((n, d), dtype=torch.float32, device=dev)
+        assert tuple(feats.shape) == (n, d)
         main = torch.cuda.current_stream(dev)
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(dev)
@@ -166,7 +327,11 @@ class ShardedIndex:
             main.wait_event(ev)
             parts.append(self.be.assign(feats[a:b])[0])                                  # 1, chunk by chunk
         assign = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int32, device=dev)
-        self._route_scan_combine(feats, assign, index_rate, False)
+        if self.peer is not None:
+            row0 = 0 if n == 0 else self.peer.row_offset(feats)
+            self._peer_scan_push(feats, assign, -1 if row0 is None else row0, index_rate)
+        else:
+            self._route_scan_combine(feats, assign, index_rate, False)
         host.copy_(feats, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         return host

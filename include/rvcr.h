@@ -196,6 +196,23 @@ RVCR_API int rvcr_retrieve_blend_assigned(rvcr_index* h, float* feats_dev, int64
 /* The search half of the above: local top-8 (D, I) for owned queries, (FLT_MAX, -1) rows for the rest. */
 RVCR_API int rvcr_search_assigned(rvcr_index* h, const float* q_dev, int64_t n, const int32_t* assign_dev, float* D_dev,
                                   int64_t* I_dev, void* stream);
+/* ---- peer memory (NVLink / NVSwitch): the two bulk exchanges of a sharded step without a collective ----
+ * Every rank allocates its feature buffer with rvcr_peer_alloc (cudaMalloc + cudaIpcGetMemHandle), exchanges the
+ * 64-byte handles out of band (torch.distributed) and maps the others' buffers with rvcr_peer_open.  The owner
+ * shard then PULLS the query rows assigned to its lists out of their home ranks' buffers (rvcr_peer_pull_rows:
+ * row r of out_dev = bases[src_rank[r]] + src_row[r] * d), and rvcr_retrieve_blend_assigned_push is
+ * rvcr_retrieve_blend_assigned whose blend epilogue PUSHES each blended row into its home rank's buffer
+ * (dst_bases[dst_rank[r]] + dst_row[r] * d) instead of writing rows_dev -- compute and combine in one kernel.
+ * bases arrays are device arrays of G pointers (own buffer included). */
+RVCR_API int rvcr_peer_alloc(int device, int64_t bytes, void** ptr_out, unsigned char* handle64_out);
+RVCR_API int rvcr_peer_open(int device, const unsigned char* handle64, void** ptr_out);
+RVCR_API int rvcr_peer_close(int device, void* ptr);
+RVCR_API int rvcr_peer_free(int device, void* ptr);
+RVCR_API int rvcr_peer_pull_rows(const float* const* bases_dev, const int32_t* src_rank_dev, const int32_t* src_row_dev,
+                        int64_t m, int32_t d, float* out_dev, int device, void* stream);
+RVCR_API int rvcr_retrieve_blend_assigned_push(rvcr_index* h, const float* rows_dev, int64_t m, const int32_t* assign_dev,
+                                      double index_rate, float* const* dst_bases_dev, const int32_t* dst_rank_dev,
+                                      const int32_t* dst_row_dev, void* stream);
 /* Merge G shards' top-8 candidate lists (G x n x 8, after an all-gather) into the global
  * top-8 by (distance, id). */
 RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, int32_t G, int64_t n, int32_t k,

@@ -60,15 +60,45 @@ def _worker(rank, world, port, tmp):
         hp = torch.from_numpy(q.copy()).pin_memory()
         sh.retrieve_blend_host_(hp, 0.75, chunk_rows=400)
         assert np.array_equal(hp.numpy(), ref.cpu().numpy(), equal_nan=True)
-    # an empty home batch on one rank
+    # ---- peer memory transport: owner pulls rows over NVLink, blend epilogue pushes them back (sharded.py) ----
+    peer = sh.enable_peer(4096)
+    for mode, scan in ((2, 5), (1, 2), (0, 5)):                  # tcgen05 scan re-check epilogue, gather_blend epilogue
+        for hnd in (shard, full):
+            hnd.set_option("coarse_mode", mode)
+            hnd.set_option("scan_impl", scan)
+        ref = torch.from_numpy(q.copy()).cuda()
+        full.retrieve_blend_(ref, 0.75)
+        feats = peer.rows(len(q), 5 + rank)
+        feats.copy_(torch.from_numpy(q))
+        launched = shard.stats()["kernels_launched"]
+        out = sh.retrieve_blend_(feats, 0.75)
+        torch.cuda.synchronize()
+        assert out.data_ptr() == feats.data_ptr() and peer.row_offset(feats) == 5 + rank
+        assert np.array_equal(feats.cpu().numpy(), ref.cpu().numpy(), equal_nan=True), (mode, scan)
+        assert shard.stats()["kernels_launched"] > launched
+        # host rows staged in the peer buffer
+        hp = torch.from_numpy(q.copy()).pin_memory()
+        sh.retrieve_blend_host_(hp, 0.75, chunk_rows=400, device_rows=peer.rows(len(q), 2000))
+        assert np.array_equal(hp.numpy(), ref.cpu().numpy(), equal_nan=True)
+    # a tensor outside the peer buffer still works (every rank falls back to the all-to-all route together)
+    got = torch.from_numpy(q.copy()).cuda()
+    sh.retrieve_blend_(got, 0.75)
+    assert np.array_equal(got.cpu().numpy(), ref.cpu().numpy(), equal_nan=True)
+    # an empty home batch on one rank, over both transports
     q2 = q[:0] if rank == world - 1 else q[:7]
+    fp = peer.rows(len(q2), 100)
+    fp.copy_(torch.from_numpy(q2))
+    sh.retrieve_blend_(fp, 0.3)
     f2 = torch.from_numpy(q2.copy()).cuda()
     sh.retrieve_blend_(f2, 0.3)
+    torch.cuda.synchronize()
+    assert np.array_equal(fp.cpu().numpy(), f2.cpu().numpy(), equal_nan=True)
     if len(q2):
         r2 = torch.from_numpy(q2.copy()).cuda()
         full.retrieve_blend_(r2, 0.3)
         assert np.array_equal(f2.cpu().numpy(), r2.cpu().numpy(), equal_nan=True)
     dist.barrier()
+    sh.peer.close()
     dist.destroy_process_group()
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
 

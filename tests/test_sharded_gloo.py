@@ -54,6 +54,11 @@ class OracleShardBackend:
                     q[own] = self.o.tail(Do, Io, self.x, index_rate, q[own])
         return torch.from_numpy(D), torch.from_numpy(I)
 
+    def scan_assigned_push(self, rows, assign, index_rate, peer, dst_rank, dst_row):
+        """what rvcr_retrieve_blend_assigned_push does in its epilogue: blended row i -> buffer[dst_rank[i]][dst_row[i]]"""
+        self.scan_assigned(rows, assign, index_rate, blend=True)
+        peer.push_rows(dst_rank, dst_row, rows)
+
     def merge_topk(self, D_all, I_all):
         D, I = D_all.numpy(), I_all.numpy()
         G, n, k = D.shape
@@ -62,6 +67,96 @@ class OracleShardBackend:
         key_i = np.where(Ic < 0, np.iinfo(np.int64).max, Ic)
         order = np.lexsort((key_i, Dc), axis=1)[:, :k]
         return torch.from_numpy(np.take_along_axis(Dc, order, 1)), torch.from_numpy(np.take_along_axis(Ic, order, 1))
+
+
+class SharedMemoryPeer:
+    """Stand-in for sharded.CudaPeer on CPU: the per-rank feature buffers are torch shared-memory tensors that every
+    process maps (what cudaIpc does for device memory), so the pull / push bookkeeping of the peer step runs for real."""
+
+    def __init__(self, buffers, rank):
+        self.buffers, self.rank = buffers, rank
+        self.d = buffers[0].shape[1]
+        self.pulled = self.pushed = 0
+
+    def rows(self, n, row0=0):
+        return self.buffers[self.rank][row0:row0 + n]
+
+    def row_offset(self, t):
+        own = self.buffers[self.rank]
+        off = t.data_ptr() - own.data_ptr()
+        if t.dim() != 2 or off < 0 or off % (self.d * 4) or off + t.numel() * 4 > own.numel() * 4:
+            return None
+        return off // (self.d * 4)
+
+    def pull_rows(self, src_rank, src_row):
+        self.pulled += len(src_rank)
+        if len(src_rank) == 0:
+            return torch.empty((0, self.d), dtype=torch.float32)
+        return torch.stack([self.buffers[int(r)][int(i)].clone() for r, i in zip(src_rank, src_row)])
+
+    def push_rows(self, dst_rank, dst_row, rows):
+        self.pushed += len(dst_rank)
+        for k, (r, i) in enumerate(zip(dst_rank, dst_row)):
+            self.buffers[int(r)][int(i)] = rows[k]
+
+    def fence(self, d):
+        d.barrier()
+
+
+def _peer_worker(rank, world, port, tmp, buffers):
+    sys.path.insert(0, ROOT)
+    import importlib
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sharded = importlib.import_module("codename-rvc-fork-3_b200.sharded")
+    synth = importlib.import_module("codename-rvc-fork-3_b200.synth")
+    pr = synth.make_host_problem(3000, 64, 0, 48, seed=5, dup_frac=0.01)
+    x, cent = pr.x, pr.centroids
+    full = oracle.OracleIndex.from_vectors(x, cent)
+    lo, hi = synth.shard_ranges(np.diff(full.list_off), world)[rank]
+    sh = sharded.ShardedIndex(OracleShardBackend(oracle, x, cent, lo, hi))
+    peer = sh.enable_peer(0, transport=SharedMemoryPeer(buffers, rank))
+    rng = np.random.default_rng(100 + rank)
+    for step, row0 in enumerate((0, 7 + rank)):                   # ragged batches at different offsets of the buffers
+        n_r = 0 if (step == 1 and rank == world - 1) else 40 + 13 * rank
+        q = (x[rng.integers(0, len(x), n_r)] + rng.standard_normal((n_r, 64)).astype(np.float32) * 0.05).astype(np.float32)
+        if rank == 0:
+            q[3, 0] = np.nan                                        # invalid assignment (-1): answered by shard 0
+        feats = peer.rows(n_r, row0)
+        feats.copy_(torch.from_numpy(q))
+        assert n_r == 0 or peer.row_offset(feats) == row0
+        dist.barrier()
+        before = (peer.pulled, peer.pushed)
+        out = sh.retrieve_blend_(feats, 0.75)
+        assert out.data_ptr() == feats.data_ptr()
+        with np.errstate(all="ignore"):
+            want = oracle.tail(*full.search(q), x, 0.75, q) if n_r else q
+        assert np.array_equal(feats.numpy(), want, equal_nan=True)
+        assert peer.pulled - before[0] == peer.pushed - before[1]  # every pulled row was pushed back exactly once
+        tot = torch.tensor([peer.pulled - before[0], n_r])
+        dist.all_reduce(tot)
+        assert int(tot[0]) == int(tot[1])                           # and every query of every rank was served once
+    # a tensor outside the peer buffer on ONE rank sends every rank down the all-to-all route (collective choice)
+    q = (x[rng.integers(0, len(x), 20)]).astype(np.float32) + np.float32(0.01)
+    feats = torch.from_numpy(q.copy()) if rank == 0 else peer.rows(20, 0).copy_(torch.from_numpy(q))
+    before = peer.pulled
+    sh.retrieve_blend_(feats, 0.75)
+    with np.errstate(all="ignore"):
+        assert np.array_equal(feats.numpy(), oracle.tail(*full.search(q), x, 0.75, q), equal_nan=True)
+    assert peer.pulled == before
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(tmp, f"peer_ok{rank}"), "w").write("ok")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_pull_push_step_on_gloo(world, tmp_path, oracle):
+    """The peer-memory step (owner pulls rows from the home buffers, blends, pushes them back) == single index."""
+    buffers = [torch.zeros((128, 64), dtype=torch.float32).share_memory_() for _ in range(world)]
+    mp.spawn(_peer_worker, args=(world, _free_port(), str(tmp_path), buffers), nprocs=world, join=True)
+    assert all((tmp_path / f"peer_ok{r}").exists() for r in range(world))
 
 
 def _free_port():
