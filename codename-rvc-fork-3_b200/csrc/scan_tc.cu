@@ -911,7 +911,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
         // blend is serial inside a warp) and was removed.
         {
             const size_t rsm = (size_t)RC_WARPS * d * 4;
-            int per_sm = 8;
+            int per_sm = 10;   // = the register-limited occupancy (48 regs x 128 threads); measured r01 C5: 6 -> 16.5, 8 -> 14.6, 10 -> 12.5 ms
             if (const char* e = getenv("RVCR_RC_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // tuning knob
             int64_t rgrid = (int64_t)h->num_sms * per_sm;
             if (rgrid * RC_WARPS > n) rgrid = (n + RC_WARPS - 1) / RC_WARPS;
