@@ -94,9 +94,9 @@ int coarse_dispatch(rvcr_index* h, const float* q, int64_t n, int32_t* list_out,
     int64_t mode = h->opt.coarse_mode;
     if (mode == 0) {
         // the tensor-core path pays a fixed conversion + re-check cost; use it once the
-        // contraction is large enough to matter (>= ~64 MFLOP)
+        // contraction is large enough to matter (Options::coarse_tc_min_flops)
         const double flops = 2.0 * (double)n * (double)h->nlist * (double)h->d;
-        mode = (coarse_tc_available() && flops >= 6.4e7 && h->nlist >= 64 && n >= 1) ? 2 : 1;
+        mode = (coarse_tc_available() && flops >= (double)h->opt.coarse_tc_min_flops && h->nlist >= 64 && n >= 1) ? 2 : 1;
     }
     if (mode >= 2) {
         if (!coarse_tc_available()) {
@@ -629,7 +629,7 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     // on a second stream, so the PCIe write-back of wave k overlaps the scan of wave k+1.
     cudaPointerAttributes pat;
     const bool mapped = cudaPointerGetAttributes(&pat, feats_host) == cudaSuccess && pat.type == cudaMemoryTypeHost &&
-                        pat.devicePointer != nullptr && (h->opt.scan_impl == 4 || h->opt.scan_impl == 5);
+                        pat.devicePointer != nullptr && (h->opt.scan_impl == 0 || h->opt.scan_impl == 4 || h->opt.scan_impl == 5);
     cudaGetLastError();
     if (!mapped) {
         RVCR_TRY(search_device(h, h->ws_q.as<float>(), n, h->ws_assign.as<int32_t>(), true, index_rate, nullptr, nullptr, s));
@@ -860,7 +860,7 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "profile")) {
         h->opt.profile = value ? 1 : 0;
     } else if (!strcmp(key, "scan_impl")) {
-        if (value < 1 || value > 5) return RVCR_ERR_INVALID;
+        if (value < 0 || value > 5) return RVCR_ERR_INVALID;
         h->opt.scan_impl = value;
     } else if (!strcmp(key, "tc_cluster")) {
         if (value != 1 && value != 2) return RVCR_ERR_INVALID;
@@ -868,6 +868,12 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "tc_resident")) {
         if (value != 0 && value != 6 && value != 8 && value != 9 && value != 10) return RVCR_ERR_INVALID;
         h->opt.tc_resident = value;
+    } else if (!strcmp(key, "coarse_tc_min_flops")) {
+        if (value < 0) return RVCR_ERR_INVALID;
+        h->opt.coarse_tc_min_flops = value;
+    } else if (!strcmp(key, "scan_tc_min_queries")) {
+        if (value < 0) return RVCR_ERR_INVALID;
+        h->opt.scan_tc_min_queries = value;
     } else if (!strcmp(key, "kmeans_niter")) {
         if (value < 0 || value > 1000) return RVCR_ERR_INVALID;
         h->opt.kmeans_niter = value;
@@ -897,6 +903,8 @@ int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out) {
     else if (!strcmp(key, "tc_resident")) *value_out = h->opt.tc_resident;
     else if (!strcmp(key, "fused_blend")) *value_out = h->opt.fused_blend;
     else if (!strcmp(key, "kmeans_niter")) *value_out = h->opt.kmeans_niter;
+    else if (!strcmp(key, "coarse_tc_min_flops")) *value_out = h->opt.coarse_tc_min_flops;
+    else if (!strcmp(key, "scan_tc_min_queries")) *value_out = h->opt.scan_tc_min_queries;
     else if (!strcmp(key, "coarse_tc_available")) *value_out = coarse_tc_available() ? 1 : 0;
     else {
         set_error("unknown option '%s'", key);

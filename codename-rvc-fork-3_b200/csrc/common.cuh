@@ -61,10 +61,16 @@ struct Options {
     int64_t coarse_mode = 0;  // 0 auto, 1 exact FFMA, 2 tcgen05 bf16, 3 tcgen05 3-way split
     int64_t nan_on_zero_score = 1;
     int64_t profile = 0;      // record CUDA events around each phase's kernels
-    int64_t scan_impl = 5;    // 5 tcgen05 tf32 + exact re-check (default); exact FFMA scans: 1 scalar 8-lane, 2 packed f32x2
+    int64_t scan_impl = 0;    // 0 auto (default): 5 for batches of >= scan_tc_min_queries, else 4; 5 tcgen05 tf32 + exact
+                              // re-check; exact FFMA scans: 1 scalar 8-lane, 2 packed f32x2
                               // TQx4, 3 same with 16 warps, 4 packed TQx8 tile
     int64_t tc_cluster = 2;   // tcgen05 path: 1 = one CTA per SM, 2 = CTA pairs (cta_group::2)
     int64_t fused_blend = 1;  // scan_impl 5: re-check kernel also does the gather + weights + blend
+    // Size rules of the auto modes.  The tensor-core kernels have fixed costs (TMEM allocation, operand conversion, a
+    // re-check launch, whole 128-row TMA tiles even for 39-row lists) that the exact FFMA kernels do not: a 10 s clip
+    // (C1: 500 frames, 1 GFLOP of coarse work) is served faster by the latter.  Both give identical bits.
+    int64_t coarse_tc_min_flops = 2000000000;   // coarse_mode 0: tcgen05 path from 2 GFLOP per call (C2 and up)
+    int64_t scan_tc_min_queries = 16384;        // scan_impl 0: tcgen05 scan from 16 Ki queries per call (C3 and up)
     int64_t kmeans_niter = 10; // index.train: Lloyd iterations (faiss ClusteringParameters::niter of the Level1Quantizer)
     int64_t tc_resident = 9;  // coarse tcgen05 kernel: query-operand k-blocks pinned in shared memory per work item (0, 6, 8, 9, 10)
 };

@@ -220,16 +220,18 @@ RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, i
 
 /* --------------------------------------------------------------------- options / stats ---- */
 
-/* keys: "coarse_mode" 0 = auto, 1 = exact FFMA kernel, 2 = tcgen05 bf16 + exact re-check,
+/* keys: "coarse_mode" 0 = auto (tcgen05 from "coarse_tc_min_flops" = 2e9 flop per call, else the exact FFMA kernel:
+ *                     same bits, lower fixed cost), 1 = exact FFMA kernel, 2 = tcgen05 bf16 + exact re-check,
  *                     3 = tcgen05 3-way split bf16 + exact re-check
  *       "nan_on_zero_score" 1 (default, reference behaviour: exact-match query -> NaN row)
  *       "profile" 0/1 record per-phase CUDA events (see rvcr_get_phase_ms)
  *       "tc_cluster" 1 = one CTA per SM, 2 (default) = CTA pairs issuing tcgen05.mma.cta_group::2
  *       "tc_resident" 0 / 6 / 8 / 9 (default) / 10: 64-element k-blocks of the query operand the coarse tcgen05 kernel pins
  *                     in shared memory per work item (0 streams both operands through the L2)
- *       "fused_blend" 1 (default): with scan_impl 5 the exact re-check kernel also applies the 1/score^2 weights and
+ *       "fused_blend" 1 (default): with the tcgen05 scan the exact re-check kernel also applies the 1/score^2 weights and
  *                     the index_rate blend (the 8 neighbour rows are still in cache); 0 = separate gather_blend kernel
- *       "scan_impl" 5 (default) tcgen05 tf32 scan + exact re-check; 1-4 exact FFMA scans
+ *       "scan_impl" 0 (default) auto: 5 for calls of >= "scan_tc_min_queries" (16384) queries, else 4;
+ *                   5 tcgen05 tf32 scan + exact re-check; 1-4 exact FFMA scans
  *       "kmeans_niter" 10 (default): Lloyd iterations of rvcr_index_train (0 = the initial centroids only) */
 RVCR_API int rvcr_set_option(rvcr_index* h, const char* key, int64_t value);
 RVCR_API int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out);

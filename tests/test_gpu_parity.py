@@ -144,12 +144,22 @@ def test_config_parity_with_oracle(rvcr, oracle, tmp_path, cfg):
         hp = torch.from_numpy(q.copy()).pin_memory()                  # pinned host path: multi-wave write-back
         index.retrieve_blend_host_(hp.numpy(), rate)
         assert np.array_equal(hp.numpy(), want, equal_nan=True)
-    assert index.get_option("scan_impl") == 5                         # default: tcgen05 tf32 scan + exact re-check
-    for impl in (1, 2, 3, 4):                                         # the exact FFMA scan kernels stay bit-identical
+    assert index.get_option("scan_impl") == 0                         # default: auto (these batches: exact FFMA scan)
+    for impl in (1, 2, 3, 4, 5):                                      # every scan kernel, tcgen05 included, is bit-identical
         index.set_option("scan_impl", impl)
         Dk, Ik = index.search(q, k=8)
         assert np.array_equal(Ik, Io) and np.array_equal(Dk, Do)
-    index.set_option("scan_impl", 5)
+        f = torch.from_numpy(q.copy()).cuda()
+        index.retrieve_blend_(f, rate)
+        assert np.array_equal(f.cpu().numpy(), want, equal_nan=True)
+    # and the coarse step: forced tcgen05 vs forced exact FFMA vs auto
+    la, da = index.assign(torch.from_numpy(q).cuda())
+    for mode in (1, 2):
+        index.set_option("coarse_mode", mode)
+        lm, dm = index.assign(torch.from_numpy(q).cuda())
+        assert torch.equal(lm, la) and torch.equal(dm, da)
+    index.set_option("coarse_mode", 0)
+    index.set_option("scan_impl", 0)
 
 
 def test_coarse_splits_and_ties(rvcr, oracle):
