@@ -66,11 +66,12 @@ struct Options {
                               // TQx4, 3 same with 16 warps, 4 packed TQx8 tile
     int64_t tc_cluster = 2;   // tcgen05 path: 1 = one CTA per SM, 2 = CTA pairs (cta_group::2)
     int64_t fused_blend = 1;  // scan_impl 5: re-check kernel also does the gather + weights + blend
-    // Size rules of the auto modes.  The tensor-core kernels have fixed costs (TMEM allocation, operand conversion, a
-    // re-check launch, whole 128-row TMA tiles even for 39-row lists) that the exact FFMA kernels do not: a 10 s clip
-    // (C1: 500 frames, 1 GFLOP of coarse work) is served faster by the latter.  Both give identical bits.
-    int64_t coarse_tc_min_flops = 2000000000;   // coarse_mode 0: tcgen05 path from 2 GFLOP per call (C2 and up)
-    int64_t scan_tc_min_queries = 16384;        // scan_impl 0: tcgen05 scan from 16 Ki queries per call (C3 and up)
+    // Size rules of the auto modes, set from measurements (profiles/r01_small_dispatch.json, B200).  The tensor-core scan has
+    // fixed costs (TMEM allocation, a re-check launch, whole 128-row TMA tiles even for 39-row lists) that the exact FFMA
+    // scan does not: at C1 (500 frames) exact scan + blend take 75 us against 93 us, at C2 (3 000 frames) 175 us against
+    // 117 us.  The tensor-core coarse step wins already at C1 (94 us against 116 us for 1 GFLOP).  All give identical bits.
+    int64_t coarse_tc_min_flops = 64000000;     // coarse_mode 0: tcgen05 path from 64 MFLOP per call
+    int64_t scan_tc_min_queries = 1024;         // scan_impl 0: tcgen05 scan from 1 Ki queries per call
     int64_t kmeans_niter = 10; // index.train: Lloyd iterations (faiss ClusteringParameters::niter of the Level1Quantizer)
     int64_t tc_resident = 9;  // coarse tcgen05 kernel: query-operand k-blocks pinned in shared memory per work item (0, 6, 8, 9, 10)
 };

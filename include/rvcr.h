@@ -220,7 +220,7 @@ RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, i
 
 /* --------------------------------------------------------------------- options / stats ---- */
 
-/* keys: "coarse_mode" 0 = auto (tcgen05 from "coarse_tc_min_flops" = 2e9 flop per call, else the exact FFMA kernel:
+/* keys: "coarse_mode" 0 = auto (tcgen05 from "coarse_tc_min_flops" = 6.4e7 flop per call, else the exact FFMA kernel:
  *                     same bits, lower fixed cost), 1 = exact FFMA kernel, 2 = tcgen05 bf16 + exact re-check,
  *                     3 = tcgen05 3-way split bf16 + exact re-check
  *       "nan_on_zero_score" 1 (default, reference behaviour: exact-match query -> NaN row)
@@ -230,7 +230,7 @@ RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, i
  *                     in shared memory per work item (0 streams both operands through the L2)
  *       "fused_blend" 1 (default): with the tcgen05 scan the exact re-check kernel also applies the 1/score^2 weights and
  *                     the index_rate blend (the 8 neighbour rows are still in cache); 0 = separate gather_blend kernel
- *       "scan_impl" 0 (default) auto: 5 for calls of >= "scan_tc_min_queries" (16384) queries, else 4;
+ *       "scan_impl" 0 (default) auto: 5 for calls of >= "scan_tc_min_queries" (1024) queries, else 4;
  *                   5 tcgen05 tf32 scan + exact re-check; 1-4 exact FFMA scans
  *       "kmeans_niter" 10 (default): Lloyd iterations of rvcr_index_train (0 = the initial centroids only) */
 RVCR_API int rvcr_set_option(rvcr_index* h, const char* key, int64_t value);

@@ -144,7 +144,7 @@ def test_config_parity_with_oracle(rvcr, oracle, tmp_path, cfg):
         hp = torch.from_numpy(q.copy()).pin_memory()                  # pinned host path: multi-wave write-back
         index.retrieve_blend_host_(hp.numpy(), rate)
         assert np.array_equal(hp.numpy(), want, equal_nan=True)
-    assert index.get_option("scan_impl") == 0                         # default: auto (these batches: exact FFMA scan)
+    assert index.get_option("scan_impl") == 0                         # default: auto (exact FFMA scan for C1's 500 queries, tcgen05 for C2's 3 000)
     for impl in (1, 2, 3, 4, 5):                                      # every scan kernel, tcgen05 included, is bit-identical
         index.set_option("scan_impl", impl)
         Dk, Ik = index.search(q, k=8)

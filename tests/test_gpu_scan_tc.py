@@ -16,7 +16,7 @@ def _build(rvcr, x, cent):
     index.set_centroids(cent)
     for i in range(0, len(x), 65536):
         index.add(x[i:i + 65536])
-    assert index.get_option("scan_impl") == 0            # library default: auto (exact FFMA scan below 16 Ki queries)
+    assert index.get_option("scan_impl") == 0            # library default: auto (exact FFMA scan below 1 Ki queries)
     index.set_option("scan_impl", 5)                     # this file tests the tensor-core scan at every size
     return index
 
