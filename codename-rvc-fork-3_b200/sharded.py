@@ -181,6 +181,12 @@ class CudaPeer:
         have landed (kernel completion makes peer stores visible)."""
         dist.all_reduce(self._flag, group=self.group)
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def close(self):
         for p in self._opened:
             try:
