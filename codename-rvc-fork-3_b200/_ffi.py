@@ -85,6 +85,8 @@ SIGNATURES = {
     "rvcr_get_option": (C.c_int, [_H, C.c_char_p, C.POINTER(_I64)]),
     "rvcr_get_stats": (C.c_int, [_H, C.POINTER(Stats)]),
     "rvcr_get_phase_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "rvcr_debug_rand_perm": (C.c_int, [_I64, _I64, _P]),
+    "rvcr_debug_split_clusters": (C.c_int, [_I32, _I64, _I64, _P, _P, C.POINTER(_I32)]),
     "rvcr_debug_coarse_tc": (C.c_int, [_H, _P, _I64, _I32, _I32, _I32, _P, _P, C.POINTER(_I32), _P,
                                        C.POINTER(C.c_float), _P]),
 }

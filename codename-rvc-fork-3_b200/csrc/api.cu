@@ -392,6 +392,25 @@ int rvcr_index_train(rvcr_index* h, const float* x_host, int64_t n) {
     return kmeans_train(h, x_host, n, nullptr);
 }
 
+int rvcr_debug_rand_perm(int64_t n, int64_t seed, int64_t* perm_out_host) {
+    if (n < 0 || (n > 0 && !perm_out_host)) return RVCR_ERR_INVALID;
+    kmeans_debug_rand_perm(n, seed, perm_out_host);
+    return RVCR_OK;
+}
+
+int rvcr_debug_split_clusters(int32_t d, int64_t k, int64_t n, float* hassign_host, float* centroids_host, int32_t* nsplit_out) {
+    if (d < 1 || k < 1 || n <= k || !hassign_host || !centroids_host) return RVCR_ERR_INVALID;
+    bool any_donor = false;
+    for (int64_t c = 0; c < k; ++c) any_donor = any_donor || hassign_host[c] > 1.f;
+    if (!any_donor) {
+        set_error("split_clusters: no cluster with more than one point to split");
+        return RVCR_ERR_INVALID;
+    }
+    const int ns = kmeans_debug_split_clusters(d, k, n, hassign_host, centroids_host);
+    if (nsplit_out) *nsplit_out = ns;
+    return RVCR_OK;
+}
+
 int rvcr_index_add_preassigned(rvcr_index* h, const float* x_dev, int64_t n, const int32_t* assign_dev, void* stream) {
     RVCR_ENTER(h);
     if (n < 0 || (n > 0 && (!x_dev || !assign_dev))) return RVCR_ERR_INVALID;

@@ -219,6 +219,8 @@ int merge_topk(const float* D_all, const int64_t* I_all, int G, int64_t n, int k
                cudaStream_t s);
 // kmeans.cu : index.train (faiss Clustering::train), assignment on the coarse kernels above
 int kmeans_train(rvcr_index* h, const float* x_host, int64_t n, cudaStream_t s);
+void kmeans_debug_rand_perm(int64_t n, int64_t seed, int64_t* out);
+int kmeans_debug_split_clusters(int d, int64_t k, int64_t n, float* hassign, float* centroids);
 // lists.cu
 int finalize_pending(rvcr_index* h, cudaStream_t s);
 int reconstruct(rvcr_index* h, int64_t i0, int64_t ni, float* out_dev, cudaStream_t s);

@@ -148,6 +148,20 @@ int split_clusters_host(int d, int64_t k, int64_t n, std::vector<float>& hassign
 
 }  // namespace
 
+// Host-only pieces of the k-means, reachable from CPU tests (no CUDA call inside): see rvcr_debug_rand_perm /
+// rvcr_debug_split_clusters in include/rvcr.h.
+void kmeans_debug_rand_perm(int64_t n, int64_t seed, int64_t* out) {
+    const std::vector<int64_t> p = faiss_rand_perm(n, seed);
+    if (n > 0) memcpy(out, p.data(), sizeof(int64_t) * (size_t)n);
+}
+int kmeans_debug_split_clusters(int d, int64_t k, int64_t n, float* hassign, float* centroids) {
+    std::vector<float> h(hassign, hassign + k), c(centroids, centroids + (size_t)k * d);
+    const int ns = split_clusters_host(d, k, n, h, c);
+    memcpy(hassign, h.data(), sizeof(float) * (size_t)k);
+    memcpy(centroids, c.data(), sizeof(float) * (size_t)k * d);
+    return ns;
+}
+
 // Caller holds the handle lock and has selected the device.
 int kmeans_train(rvcr_index* h, const float* x_host, int64_t n, cudaStream_t s) {
     const int64_t k = h->nlist;

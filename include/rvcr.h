@@ -248,6 +248,14 @@ RVCR_API int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, 
                                   int32_t cap_pairs, float* v_host, int32_t* j_host, int32_t* pairs_out,
                                   float* qnorm2_host, float* cmax_out, void* stream);
 
+/* Host-only pieces of rvcr_index_train, exposed so that they can be checked without a GPU: faiss rand_perm
+ * (identity, then swap(perm[i], perm[i + mt() % (n - i)]) with std::mt19937(seed)) and faiss split_clusters
+ * (empty clusters re-seeded from donors picked by RandomGenerator(1234), copies perturbed by 1 +- 1/1024;
+ * hassign: k floats, centroids: k x d, both updated in place; *nsplit_out = clusters re-seeded). */
+RVCR_API int rvcr_debug_rand_perm(int64_t n, int64_t seed, int64_t* perm_out_host);
+RVCR_API int rvcr_debug_split_clusters(int32_t d, int64_t k, int64_t n, float* hassign_host, float* centroids_host,
+                                       int32_t* nsplit_out);
+
 #ifdef __cplusplus
 }
 #endif

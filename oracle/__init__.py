@@ -172,6 +172,34 @@ def rand_perm(n: int, seed: int) -> np.ndarray:
     return np.asarray(perm, np.int64)
 
 
+def split_clusters(hass, cent, n: int) -> int:
+    """faiss Clustering.cpp split_clusters [EXT, SURVEY A9] in place on hass (k float32 counts) and cent (k, d) float32:
+    every empty cluster ci takes a copy of a donor cj drawn with probability (hass[cj] - 1) / (n - k) by walking
+    cj = 0, 1, ... with one rand_float() per step; the copy and the donor are perturbed by 1 +- 1/1024 with alternating
+    sign per dimension; the donor's count is halved.  `RandomGenerator rng(1234)` is a local of the function, i.e.
+    re-seeded on every call; rand_float() = mt() / float(mt.max()) in fp32."""
+    k, d = cent.shape
+    eps = np.float32(1.0 / 1024.0)
+    sign = np.where(np.arange(d) % 2 == 0, eps, -eps).astype(np.float32)
+    rs = np.random.RandomState(1234)
+    nsplit = 0
+    for ci in np.nonzero(hass == 0)[0]:
+        cj = 0
+        while True:
+            p = np.float32((np.float64(hass[cj]) - 1.0) / np.float64(np.float32(n - k)))
+            r = np.float32(rs._bit_generator.random_raw(1)[0]) / np.float32(4294967295.0)   # mt() / float(mt.max())
+            if r < p:
+                break
+            cj = (cj + 1) % k
+        cent[ci] = cent[cj]
+        cent[ci] *= (np.float32(1) + sign)
+        cent[cj] *= (np.float32(1) - sign)
+        hass[ci] = hass[cj] / np.float32(2)
+        hass[cj] -= hass[ci]
+        nsplit += 1
+    return nsplit
+
+
 def kmeans_train(x, k: int, niter: int = 10, seed: int = 1234, max_points_per_centroid: int = 256):
     """faiss 1.7.3 Clustering::train as IndexIVF::train runs it (SURVEY A9) [EXT -- PARITY UNPINNED: restated
     from the published algorithm, faiss is not installable here].  Returns (centroids (k, d) f32, assign of the
@@ -185,7 +213,6 @@ def kmeans_train(x, k: int, niter: int = 10, seed: int = 1234, max_points_per_ce
         x = np.ascontiguousarray(x[rand_perm(n, seed)[: k * max_points_per_centroid]])
         n = x.shape[0]
     cent = np.ascontiguousarray(x[rand_perm(n, seed + 1)[:k]])
-    eps = np.float32(1.0 / 1024.0)
     obj = []
     a = None
     for _ in range(niter):
@@ -197,22 +224,7 @@ def kmeans_train(x, k: int, niter: int = 10, seed: int = 1234, max_points_per_ce
         nz = hass > 0
         cent = cent.copy()
         cent[nz] = sums[nz] * (np.float32(1.0) / hass[nz])[:, None]       # faiss: norm = 1 / hassign; c *= norm
-        # split_clusters: `RandomGenerator rng(1234)` is a local of the function, i.e. re-seeded on every call
-        sign = np.where(np.arange(d) % 2 == 0, eps, -eps).astype(np.float32)
-        rs = np.random.RandomState(1234)
-        for ci in np.nonzero(~nz)[0]:
-            cj = 0
-            while True:
-                p = np.float32((np.float64(hass[cj]) - 1.0) / np.float64(np.float32(n - k)))
-                r = np.float32(rs._bit_generator.random_raw(1)[0]) / np.float32(4294967295.0)   # mt() / float(mt.max())
-                if r < p:
-                    break
-                cj = (cj + 1) % k
-            cent[ci] = cent[cj]
-            cent[ci] *= (np.float32(1) + sign)
-            cent[cj] *= (np.float32(1) - sign)
-            hass[ci] = hass[cj] / np.float32(2)
-            hass[cj] -= hass[ci]
+        split_clusters(hass, cent, n)
     return cent.astype(np.float32), a, obj
 
 

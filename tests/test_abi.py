@@ -67,3 +67,32 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
                 assert "rvc_oracle" not in txt, f
+
+
+def test_native_kmeans_host_pieces_match_oracle(rvcr, oracle):
+    """rvcr_index_train's host-only parts (csrc/kmeans.cu) against the oracle's independent restatement -- no GPU
+    needed: faiss rand_perm on std::mt19937 vs numpy's legacy MT19937 stream, and split_clusters bit for bit."""
+    import ctypes as C
+
+    import numpy as np
+    L = rvcr.lib()
+    for n, seed in ((0, 1), (1, 1), (2, 7), (17, 1234), (1000, 1235), (65537, 99)):
+        out = np.empty(n, np.int64)
+        assert L.rvcr_debug_rand_perm(n, seed, out.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(out, oracle.rand_perm(n, seed)), (n, seed)
+    rng = np.random.default_rng(3)
+    for k, d, n_empty in ((8, 6, 3), (64, 33, 20), (5, 4, 4)):
+        hass = rng.integers(2, 60, k).astype(np.float32)
+        hass[rng.choice(k, n_empty, replace=False)] = 0
+        n = int(hass.sum())
+        cent = rng.standard_normal((k, d)).astype(np.float32)
+        h_o, c_o = hass.copy(), cent.copy()
+        ns_o = oracle.split_clusters(h_o, c_o, n)
+        h_n, c_n = hass.copy(), cent.copy()
+        ns = C.c_int32(0)
+        rc = L.rvcr_debug_split_clusters(d, k, n, h_n.ctypes.data_as(C.c_void_p), c_n.ctypes.data_as(C.c_void_p), C.byref(ns))
+        assert rc == 0 and ns.value == ns_o == n_empty
+        assert np.array_equal(h_n, h_o) and np.array_equal(c_n, c_o)
+        assert (h_n > 0).all() and abs(float(h_n.sum()) - n) < 1e-3
+    bad = np.zeros(4, np.float32)
+    assert L.rvcr_debug_split_clusters(2, 4, 10, bad.ctypes.data_as(C.c_void_p), np.zeros((4, 2), np.float32).ctypes.data_as(C.c_void_p), None) == -1
