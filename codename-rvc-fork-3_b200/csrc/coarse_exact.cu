@@ -170,11 +170,8 @@ static int ce_prepare(rvcr_index* h, size_t* smem_out) {
         set_error("d=%d needs %zu B of shared memory", h->d, smem);
         return RVCR_ERR_UNSUPPORTED;
     }
-    static size_t attr_smem = 0;  // largest dynamic shared memory size opted into so far
-    if (smem > attr_smem) {
-        RVCR_CUDA(cudaFuncSetAttribute(coarse_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    static SmemOptIn opt_in;   // zero-initialised (static storage)
+    RVCR_TRY(opt_in.ensure(coarse_exact_kernel, smem, h->device));
     *smem_out = smem;
     return RVCR_OK;
 }

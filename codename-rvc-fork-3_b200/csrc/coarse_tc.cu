@@ -553,12 +553,8 @@ template <int CLUSTER, int NRES, int SB, int SA, int P>
 int launch_tc(rvcr_index* h, const CUtensorMap& ta, const CUtensorMap& tb, int num_mblocks, int num_ntiles, int nsplit,
               int tps, int nkb, float* topv, int* topj, cudaStream_t s) {
     using C = tc::Cfg<CLUSTER, NRES, SB, SA, P>;
-    static bool attr = false;
-    if (!attr) {
-        RVCR_CUDA(cudaFuncSetAttribute(tc::coarse_tc_kernel<CLUSTER, NRES, SB, SA, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       C::SMEM_BYTES));
-        attr = true;
-    }
+    static SmemOptIn opt_in;   // one per template instantiation
+    RVCR_TRY(opt_in.ensure(tc::coarse_tc_kernel<CLUSTER, NRES, SB, SA, P>, (size_t)C::SMEM_BYTES, h->device));
     const int nitems = num_mblocks * nsplit;
     int nclusters = h->num_sms / CLUSTER;
     if (nclusters > nitems) nclusters = nitems;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -44,6 +45,26 @@ const char* get_error();
             return RVCR_ERR_CUDA;                                                             \
         }                                                                                     \
     } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only, and one process may hold handles on
+// several devices (a server with one index per GPU): remember per device the largest size a kernel has been opted into.
+// One static instance per kernel at its launch site; concurrent callers at worst repeat the (idempotent) call.
+constexpr int RVCR_MAX_DEVICES = 64;
+struct SmemOptIn {
+    std::atomic<size_t> bytes[RVCR_MAX_DEVICES];
+    template <class Kernel>
+    int ensure(Kernel kernel, size_t smem, int device) {
+        if (device < 0 || device >= RVCR_MAX_DEVICES) {
+            set_error("device ordinal %d outside [0, %d)", device, RVCR_MAX_DEVICES);
+            return RVCR_ERR_INVALID;
+        }
+        if (smem > bytes[device].load(std::memory_order_relaxed)) {
+            RVCR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bytes[device].store(smem, std::memory_order_relaxed);
+        }
+        return RVCR_OK;
+    }
+};
 
 // Device buffer grown on demand; never shrinks.  Growth synchronises the device (rare).
 struct DevBuf {

@@ -872,11 +872,8 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
         return RVCR_ERR_UNSUPPORTED;
     }
     const size_t smem = fixed + (size_t)nstage * stc::STAGE_BYTES;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        RVCR_CUDA(cudaFuncSetAttribute(stc::scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    static SmemOptIn opt_in;
+    RVCR_TRY(opt_in.ensure(stc::scan_tc_kernel, smem, h->device));
     RVCR_TRY(h->ws_cand.reserve((size_t)n * stc::CCAP * 4));
     RVCR_TRY(h->ws_candcnt.reserve((size_t)n * 4));
     RVCR_TRY(h->ws_fb.reserve((size_t)n * 4 + 64));

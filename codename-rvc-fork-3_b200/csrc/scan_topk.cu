@@ -934,18 +934,15 @@ int scan_topk_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t*
         set_error("d=%d needs %zu B of shared memory", h->d, smem);
         return RVCR_ERR_UNSUPPORTED;
     }
-    static size_t attr_smem[5] = {0, 0, 0, 0, 0};  // largest dynamic shared memory size opted into so far
-    if (smem > attr_smem[impl]) {
-        if (impl == 1)
-            RVCR_CUDA(cudaFuncSetAttribute(scan_topk_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else if (impl == 2)
-            RVCR_CUDA(cudaFuncSetAttribute(scan_topk_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else if (impl == 3)
-            RVCR_CUDA(cudaFuncSetAttribute(scan_topk_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else
-            RVCR_CUDA(cudaFuncSetAttribute(scan_topk_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem[impl] = smem;
-    }
+    static SmemOptIn opt_in[5];   // per kernel version
+    if (impl == 1)
+        RVCR_TRY(opt_in[1].ensure(scan_topk_kernel_v1, smem, h->device));
+    else if (impl == 2)
+        RVCR_TRY(opt_in[2].ensure(scan_topk_kernel_v2, smem, h->device));
+    else if (impl == 3)
+        RVCR_TRY(opt_in[3].ensure(scan_topk_kernel_v3, smem, h->device));
+    else
+        RVCR_TRY(opt_in[4].ensure(scan_topk_kernel_v4, smem, h->device));
     if (fill) {
         const int64_t nk = n * RVCR_K;
         fill_pad_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, s>>>(D, P, I, nk);
