@@ -29,6 +29,15 @@ class Info(C.Structure):
                 ("owned_end", C.c_int64), ("device", C.c_int32), ("metric", C.c_int32)]
 
 
+class FileInfo(C.Structure):
+    _fields_ = [("d", C.c_int32), ("is_trained", C.c_int32), ("ntotal", C.c_int64), ("nlist", C.c_int64),
+                ("nprobe", C.c_int64), ("metric", C.c_int32), ("layout", C.c_int32), ("direct_map_type", C.c_int32),
+                ("list_encoding", C.c_int32), ("nvectors", C.c_int64), ("max_list_size", C.c_int64),
+                ("nonempty_lists", C.c_int64), ("file_bytes", C.c_int64), ("payload_offset", C.c_int64),
+                ("searchable", C.c_int32), ("fourcc", C.c_char * 8), ("quantizer_fourcc", C.c_char * 8),
+                ("reserved32", C.c_int32), ("reserved", C.c_int64 * 4)]
+
+
 class Stats(C.Structure):
     _fields_ = [("calls_search", C.c_int64), ("queries", C.c_int64), ("kernels_launched", C.c_int64),
                 ("coarse_tc_queries", C.c_int64), ("coarse_candidates", C.c_int64),
@@ -48,6 +57,8 @@ SIGNATURES = {
     "rvcr_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "rvcr_index_create": (C.c_int, [_I32, _I64, C.c_int, C.POINTER(_H)]),
     "rvcr_index_read": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_H)]),
+    "rvcr_index_probe": (C.c_int, [C.c_char_p, C.POINTER(FileInfo), _P, _I64]),
+    "rvcr_shard_range": (C.c_int, [_P, _I64, C.c_int, C.c_int, C.POINTER(_I64), C.POINTER(_I64)]),
     "rvcr_index_read_shard": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_H)]),
     "rvcr_index_set_shard": (C.c_int, [_H, _I64, _I64]),
     "rvcr_index_write": (C.c_int, [_H, C.c_char_p]),

@@ -26,6 +26,8 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 
 int read_index_file(const char* path, int device, int rank, int world, rvcr_index** out);
+int probe_index_file(const char* path, rvcr_file_info* out, int64_t* sizes_out, int64_t sizes_cap);
+void shard_range(const std::vector<int64_t>& sizes, int rank, int world, int64_t& lo, int64_t& hi);
 int write_index_file(rvcr_index* h, const char* path);
 
 namespace {
@@ -265,6 +267,34 @@ int rvcr_index_create(int32_t d, int64_t nlist, int device, rvcr_index** out) {
 int rvcr_index_read(const char* path, int device, rvcr_index** out) {
     if (!path || !out) return RVCR_ERR_INVALID;
     return read_index_file(path, device, 0, 1, out);
+}
+
+int rvcr_index_probe(const char* path, rvcr_file_info* info_out, int64_t* list_sizes_host, int64_t nlist_cap) {
+    if (!path || (!info_out && !list_sizes_host) || (list_sizes_host && nlist_cap < 0)) {
+        set_error("rvcr_index_probe: bad arguments");
+        return RVCR_ERR_INVALID;
+    }
+    return probe_index_file(path, info_out, list_sizes_host, nlist_cap);
+}
+
+int rvcr_shard_range(const int64_t* list_sizes_host, int64_t nlist, int rank, int world, int64_t* lo_out, int64_t* hi_out) {
+    if (!list_sizes_host || nlist <= 0 || world < 1 || rank < 0 || rank >= world || !lo_out || !hi_out) {
+        set_error("rvcr_shard_range: bad arguments");
+        return RVCR_ERR_INVALID;
+    }
+    for (int64_t l = 0; l < nlist; ++l)
+        if (list_sizes_host[l] < 0) {
+            set_error("rvcr_shard_range: negative list size");
+            return RVCR_ERR_INVALID;
+        }
+    try {
+        std::vector<int64_t> sizes(list_sizes_host, list_sizes_host + nlist);
+        shard_range(sizes, rank, world, *lo_out, *hi_out);
+    } catch (const std::exception& e) {
+        set_error("rvcr_shard_range: %s", e.what());
+        return RVCR_ERR_OOM;
+    }
+    return RVCR_OK;
 }
 
 int rvcr_index_read_shard(const char* path, int device, int rank, int world, rvcr_index** out) {

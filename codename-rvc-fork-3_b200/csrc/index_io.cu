@@ -1,5 +1,5 @@
 // index_io.cu -- faiss `.index` (IndexIVFFlat over IndexFlat) reader / writer, straight to / from
-// list-ordered device storage.
+// list-ordered device storage; host-only file probe (rvcr_index_probe).
 //
 // Replaces faiss.read_index (rvc/infer/pipeline.py:555) and faiss.write_index
 // (rvc/train/process/extract_index.py:71).  Byte layout: SURVEY Appendix B (little-endian, no
@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
 
 #include "common.cuh"
 
@@ -19,12 +20,44 @@ namespace rvcr {
 
 namespace {
 
+// Bounded reader: the file length is taken once, every read / skip is checked against it BEFORE any allocation, so a
+// corrupt or hostile header (users download .index files, tabs/download/download.py) can make the parse fail with
+// RVCR_ERR_FORMAT but never allocate from an untrusted count, seek out of range, or abort.
 struct FileReader {
     FILE* f = nullptr;
+    int64_t size = 0, pos = 0;
     ~FileReader() {
         if (f) fclose(f);
     }
-    bool rd(void* dst, size_t n) { return fread(dst, 1, n, f) == n; }
+    bool open(const char* path) {
+        f = fopen(path, "rb");
+        if (!f) return false;
+        if (fseeko(f, 0, SEEK_END) != 0) return false;
+        size = (int64_t)ftello(f);
+        if (size < 0 || fseeko(f, 0, SEEK_SET) != 0) return false;
+        pos = 0;
+        return true;
+    }
+    int64_t left() const { return size - pos; }
+    // n * unit <= bytes left, without overflow
+    bool fits(uint64_t n, uint64_t unit) const { return unit == 0 || n <= (uint64_t)left() / unit; }
+    bool rd(void* dst, size_t n) {
+        if ((uint64_t)n > (uint64_t)left()) return false;
+        if (fread(dst, 1, n, f) != n) return false;
+        pos += (int64_t)n;
+        return true;
+    }
+    bool skip(uint64_t n) {
+        if (n > (uint64_t)left()) return false;
+        if (n && fseeko(f, (off_t)n, SEEK_CUR) != 0) return false;
+        pos += (int64_t)n;
+        return true;
+    }
+    bool seek(int64_t to) {
+        if (to < 0 || to > size || fseeko(f, (off_t)to, SEEK_SET) != 0) return false;
+        pos = to;
+        return true;
+    }
     template <class T>
     bool get(T& v) {
         return rd(&v, sizeof(T));
@@ -47,6 +80,183 @@ bool read_index_header(FileReader& r, Header& h) {
         if (!r.get(arg)) return false;
     }
     return true;
+}
+
+// Everything of an IndexIVFFlat file except the list payload, which stays in the file: where each list's vectors and
+// ids sit is enough to stream them to the device (read_index_file) or to describe the file (rvcr_index_probe).
+//   layout 0  "IwFl"  faiss >= 1.5: ArrayInvertedLists object ("ilar" / "il00"), per list [n x d fp32][n x int64], contiguous
+//   layout 1  "IvFL"  legacy: nlist id vectors before the direct map, then nlist byte vectors of codes
+//   layout 2  "IvFl"  oldest: same, the codes stored as float vectors (faiss impl/index_read.cpp, legacy branch)
+struct ParsedIndex {
+    Header ih;
+    uint64_t nlist = 0, nprobe = 0;
+    int layout = 0;
+    char fourcc[5] = {0}, qfourcc[5] = {0};
+    int dm_type = 0;
+    int list_encoding = 0;                    // 0 "full", 1 "sprs", 2 "il00" (no lists), 3 legacy per-list vectors
+    std::vector<float> cent;                  // nlist x d (empty when the caller does not want them)
+    std::vector<int64_t> sizes;               // nlist
+    int64_t nvec = 0;                         // sum of sizes
+    int64_t payload_off = 0;                  // layout 0: offset of the first list's vectors
+    std::vector<int64_t> ids_off, codes_off;  // legacy layouts: offset of each list's id / code data (past the length prefix)
+    int64_t file_bytes = 0;
+};
+
+#define PARSE_FAIL(code, ...)   \
+    do {                        \
+        set_error(__VA_ARGS__); \
+        return code;            \
+    } while (0)
+
+void printable(char* four) {
+    for (int i = 0; i < 4; ++i)
+        if (four[i] < 32 || four[i] > 126) four[i] = '?';
+}
+
+int parse_index_impl(FileReader& r, const char* path, bool want_centroids, ParsedIndex& p) {
+    p.file_bytes = r.size;
+    if (!r.rd(p.fourcc, 4)) PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated", path);
+    if (memcmp(p.fourcc, "IwFl", 4) == 0) {
+        p.layout = 0;
+    } else if (memcmp(p.fourcc, "IvFL", 4) == 0) {
+        p.layout = 1;
+    } else if (memcmp(p.fourcc, "IvFl", 4) == 0) {
+        p.layout = 2;
+    } else {
+        printable(p.fourcc);
+        PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': fourcc '%.4s' is not an IndexIVFFlat ('IwFl', legacy 'IvFL' / 'IvFl') file", path,
+                   p.fourcc);
+    }
+    Header& ih = p.ih;
+    if (!read_index_header(r, ih) || !r.get(p.nlist) || !r.get(p.nprobe))
+        PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated header", path);
+    if (ih.metric != 1) PARSE_FAIL(RVCR_ERR_UNSUPPORTED, "'%s': metric_type %d unsupported (only METRIC_L2)", path, ih.metric);
+    const uint64_t nlist = p.nlist;
+    if (ih.d <= 0 || ih.ntotal < 0 || nlist == 0 || nlist > (1ull << 31))
+        PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': implausible header (d=%d ntotal=%lld nlist=%llu)", path, ih.d, (long long)ih.ntotal,
+                   (unsigned long long)nlist);
+    if (!r.rd(p.qfourcc, 4) || (memcmp(p.qfourcc, "IxF2", 4) != 0 && memcmp(p.qfourcc, "IxFl", 4) != 0)) {
+        printable(p.qfourcc);
+        PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': quantizer fourcc '%.4s' unsupported (need IndexFlatL2)", path, p.qfourcc);
+    }
+    Header qh;
+    uint64_t count = 0;
+    if (!read_index_header(r, qh) || !r.get(count) || qh.d != ih.d || (uint64_t)qh.ntotal != nlist ||
+        count != nlist * (uint64_t)ih.d)
+        PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': inconsistent quantizer header", path);
+    if (!r.fits(count, 4)) PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated centroids", path);
+    if (want_centroids) {
+        p.cent.resize((size_t)count);
+        if (!r.rd(p.cent.data(), (size_t)count * 4)) PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated centroids", path);
+    } else if (!r.skip(count * 4)) {
+        PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated centroids", path);
+    }
+    // nlist * 4 d bytes of centroids were just found in the file, so nlist-sized host arrays are bounded by its length
+    p.sizes.assign((size_t)nlist, 0);
+    const uint64_t rowb = 4ull * (uint64_t)ih.d;
+    if (p.layout != 0) {
+        // legacy: the id vectors of all lists come first (read_ivf_header(ivf, f, &ids))
+        p.ids_off.assign((size_t)nlist, 0);
+        p.codes_off.assign((size_t)nlist, 0);
+        for (uint64_t l = 0; l < nlist; ++l) {
+            uint64_t n = 0;
+            if (!r.get(n) || !r.fits(n, 8))
+                PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated id vector of list %llu", path, (unsigned long long)l);
+            p.ids_off[l] = r.pos;
+            p.sizes[l] = (int64_t)n;
+            r.skip(n * 8);
+        }
+    }
+    uint8_t dm_type = 0;
+    uint64_t dm_n = 0;
+    if (!r.get(dm_type) || !r.get(dm_n) || !r.fits(dm_n, 8) || !r.skip(dm_n * 8))
+        PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated direct map", path);
+    p.dm_type = dm_type;
+    if (dm_type == 2) {
+        uint64_t hn = 0;
+        if (!r.get(hn) || !r.fits(hn, 16) || !r.skip(hn * 16)) PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated direct map", path);
+    } else if (dm_type > 2) {
+        PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': direct map type %d unknown", path, (int)dm_type);
+    }
+    if (p.layout != 0) {
+        p.list_encoding = 3;
+        const uint64_t unit = p.layout == 1 ? 1 : 4;   // "IvFL": std::vector<uint8_t>, "IvFl": std::vector<float>
+        for (uint64_t l = 0; l < nlist; ++l) {
+            uint64_t m = 0;
+            if (!r.get(m) || !r.fits(m, unit))
+                PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated code vector of list %llu", path, (unsigned long long)l);
+            if (m * unit != (uint64_t)p.sizes[l] * rowb)
+                PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': list %llu holds %lld ids but %llu code bytes (d=%d)", path, (unsigned long long)l,
+                           (long long)p.sizes[l], (unsigned long long)(m * unit), ih.d);
+            p.codes_off[l] = r.pos;
+            r.skip(m * unit);
+        }
+    } else {
+        char four[4];
+        if (!r.rd(four, 4)) PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated inverted-list header", path);
+        if (memcmp(four, "il00", 4) == 0) {
+            uint64_t a, b;
+            if (!r.get(a) || !r.get(b)) PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated inverted-list header", path);
+            p.list_encoding = 2;
+        } else if (memcmp(four, "ilar", 4) == 0) {
+            uint64_t il_nlist = 0, code_size = 0, cnt = 0;
+            char lt[4];
+            if (!r.get(il_nlist) || !r.get(code_size) || !r.rd(lt, 4) || !r.get(cnt))
+                PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated inverted-list header", path);
+            if (il_nlist != nlist || code_size != rowb)
+                PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': inverted lists do not match the header (nlist %llu, code_size %llu)", path,
+                           (unsigned long long)il_nlist, (unsigned long long)code_size);
+            if (!r.fits(cnt, 8)) PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated list-size table", path);
+            std::vector<uint64_t> raw((size_t)cnt);
+            if (cnt && !r.rd(raw.data(), (size_t)cnt * 8)) PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated list-size table", path);
+            if (memcmp(lt, "full", 4) == 0) {
+                if (cnt != nlist)
+                    PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': 'full' list-size table has %llu entries for %llu lists", path,
+                               (unsigned long long)cnt, (unsigned long long)nlist);
+                for (uint64_t l = 0; l < nlist; ++l) p.sizes[l] = (int64_t)raw[l];
+                p.list_encoding = 0;
+            } else if (memcmp(lt, "sprs", 4) == 0) {
+                if (cnt & 1) PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': odd 'sprs' list-size table", path);
+                for (uint64_t i = 0; i + 1 < cnt; i += 2) {
+                    if (raw[i] >= nlist)
+                        PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': 'sprs' entry names list %llu of %llu", path, (unsigned long long)raw[i],
+                                   (unsigned long long)nlist);
+                    p.sizes[raw[i]] = (int64_t)raw[i + 1];
+                }
+                p.list_encoding = 1;
+            } else {
+                PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': list encoding unsupported (need 'full' or 'sprs')", path);
+            }
+        } else {
+            PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': inverted lists fourcc unsupported (need 'ilar' or 'il00')", path);
+        }
+        p.payload_off = r.pos;
+    }
+    // list sizes are untrusted too: non-negative, their payload inside the file (trailing bytes are ignored, like faiss)
+    uint64_t tot = 0;
+    const uint64_t cap = (uint64_t)r.size / (rowb + 8) + 1;
+    for (uint64_t l = 0; l < nlist; ++l) {
+        if (p.sizes[l] < 0 || (uint64_t)p.sizes[l] > cap)
+            PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': list %llu claims %lld vectors", path, (unsigned long long)l, (long long)p.sizes[l]);
+        tot += (uint64_t)p.sizes[l];
+        if (tot > cap)
+            PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated list payload (the size table claims more vectors than the file holds)",
+                       path);
+    }
+    p.nvec = (int64_t)tot;
+    if (p.layout == 0 && !r.fits(tot, rowb + 8))
+        PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated list payload (%llu vectors x %llu bytes expected, %lld bytes left)", path,
+                   (unsigned long long)tot, (unsigned long long)(rowb + 8), (long long)r.left());
+    return RVCR_OK;
+}
+
+int parse_index(FileReader& r, const char* path, bool want_centroids, ParsedIndex& p) {
+    try {
+        return parse_index_impl(r, path, want_centroids, p);
+    } catch (const std::exception& e) {   // std::bad_alloc on a huge but self-consistent file: report, never abort
+        set_error("'%s': out of host memory while parsing (%s)", path, e.what());
+        return RVCR_ERR_OOM;
+    }
 }
 
 }  // namespace
@@ -78,97 +288,68 @@ void shard_range(const std::vector<int64_t>& sizes, int rank, int world, int64_t
     if (hi < lo) hi = lo;
 }
 
-int read_index_file(const char* path, int device, int rank, int world, rvcr_index** out) {
+// Host-only description of an index file (no CUDA call): rvcr_index_probe.  sizes_out (nullable) receives the nlist
+// list sizes; world > 0 additionally reports the list range read_index_shard(rank, world) would load.
+int probe_index_file(const char* path, rvcr_file_info* out, int64_t* sizes_out, int64_t sizes_cap) {
     FileReader r;
-    r.f = fopen(path, "rb");
-    if (!r.f) {
+    if (!r.open(path)) {
         set_error("cannot open index file '%s'", path);
         return RVCR_ERR_IO;
     }
-    char four[4];
-    if (!r.rd(four, 4)) {
-        set_error("'%s': truncated", path);
-        return RVCR_ERR_FORMAT;
-    }
-    if (memcmp(four, "IwFl", 4) != 0) {
-        set_error("'%s': fourcc '%.4s' is not an IndexIVFFlat ('IwFl') file", path, four);
-        return RVCR_ERR_FORMAT;
-    }
-    Header ih;
-    uint64_t nlist = 0, nprobe = 0;
-    if (!read_index_header(r, ih) || !r.get(nlist) || !r.get(nprobe)) {
-        set_error("'%s': truncated header", path);
-        return RVCR_ERR_FORMAT;
-    }
-    if (ih.metric != 1) {
-        set_error("'%s': metric_type %d unsupported (only METRIC_L2)", path, ih.metric);
-        return RVCR_ERR_UNSUPPORTED;
-    }
-    if (ih.d <= 0 || nlist == 0 || nlist > (1ull << 31)) {
-        set_error("'%s': implausible header (d=%d nlist=%llu)", path, ih.d, (unsigned long long)nlist);
-        return RVCR_ERR_FORMAT;
-    }
-    if (!r.rd(four, 4) || (memcmp(four, "IxF2", 4) != 0 && memcmp(four, "IxFl", 4) != 0)) {
-        set_error("'%s': quantizer fourcc '%.4s' unsupported (need IndexFlatL2)", path, four);
-        return RVCR_ERR_FORMAT;
-    }
-    Header qh;
-    uint64_t count = 0;
-    if (!read_index_header(r, qh) || !r.get(count) || qh.d != ih.d || (uint64_t)qh.ntotal != nlist ||
-        count != nlist * (uint64_t)ih.d) {
-        set_error("'%s': inconsistent quantizer header", path);
-        return RVCR_ERR_FORMAT;
-    }
-    std::vector<float> cent((size_t)count);
-    if (!r.rd(cent.data(), (size_t)count * 4)) {
-        set_error("'%s': truncated centroids", path);
-        return RVCR_ERR_FORMAT;
-    }
-    uint8_t dm_type = 0;
-    uint64_t dm_n = 0;
-    if (!r.get(dm_type) || !r.get(dm_n)) {
-        set_error("'%s': truncated direct map", path);
-        return RVCR_ERR_FORMAT;
-    }
-    if (dm_n && fseek(r.f, (long)(dm_n * 8), SEEK_CUR) != 0) return RVCR_ERR_FORMAT;
-    if (dm_type == 2) {
-        uint64_t hn = 0;
-        if (!r.get(hn) || fseek(r.f, (long)(hn * 16), SEEK_CUR) != 0) return RVCR_ERR_FORMAT;
-    }
-    std::vector<int64_t> sizes((size_t)nlist, 0);
-    if (!r.rd(four, 4)) return RVCR_ERR_FORMAT;
-    if (memcmp(four, "il00", 4) == 0) {
-        uint64_t a, b;
-        if (!r.get(a) || !r.get(b)) return RVCR_ERR_FORMAT;
-    } else if (memcmp(four, "ilar", 4) == 0) {
-        uint64_t il_nlist = 0, code_size = 0, cnt = 0;
-        char lt[4];
-        if (!r.get(il_nlist) || !r.get(code_size) || !r.rd(lt, 4) || !r.get(cnt)) {
-            set_error("'%s': truncated inverted-list header", path);
-            return RVCR_ERR_FORMAT;
+    ParsedIndex p;
+    RVCR_TRY(parse_index(r, path, false, p));
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        out->d = p.ih.d;
+        out->is_trained = p.ih.trained ? 1 : 0;
+        out->ntotal = p.ih.ntotal;
+        out->nlist = (int64_t)p.nlist;
+        out->nprobe = (int64_t)p.nprobe;
+        out->metric = p.ih.metric;
+        out->layout = p.layout;
+        out->direct_map_type = p.dm_type;
+        out->list_encoding = p.list_encoding;
+        out->nvectors = p.nvec;
+        int64_t mx = 0, non0 = 0;
+        for (int64_t s : p.sizes) {
+            mx = std::max(mx, s);
+            non0 += s > 0;
         }
-        if (il_nlist != nlist || code_size != 4ull * ih.d) {
-            set_error("'%s': inverted lists do not match the header (nlist %llu, code_size %llu)", path,
-                      (unsigned long long)il_nlist, (unsigned long long)code_size);
-            return RVCR_ERR_FORMAT;
+        out->max_list_size = mx;
+        out->nonempty_lists = non0;
+        out->file_bytes = p.file_bytes;
+        out->payload_offset = p.layout == 0 ? p.payload_off : -1;
+        // what rvcr_index_read + rvcr_search accept: the kernels tile the dimension by 128 and implement nprobe = 1
+        out->searchable = (p.ih.d % 128 == 0 && p.ih.trained && p.nprobe == 1) ? 1 : 0;
+        memcpy(out->fourcc, p.fourcc, 4);
+        memcpy(out->quantizer_fourcc, p.qfourcc, 4);
+    }
+    if (sizes_out) {
+        if (sizes_cap < (int64_t)p.nlist) {
+            set_error("list-size buffer holds %lld entries, the index has %llu lists", (long long)sizes_cap,
+                      (unsigned long long)p.nlist);
+            return RVCR_ERR_INVALID;
         }
-        std::vector<uint64_t> raw((size_t)cnt);
-        if (cnt && !r.rd(raw.data(), (size_t)cnt * 8)) return RVCR_ERR_FORMAT;
-        if (memcmp(lt, "full", 4) == 0) {
-            if (cnt != nlist) return RVCR_ERR_FORMAT;
-            for (uint64_t l = 0; l < nlist; ++l) sizes[l] = (int64_t)raw[l];
-        } else if (memcmp(lt, "sprs", 4) == 0) {
-            for (uint64_t i = 0; i + 1 < cnt; i += 2) {
-                if (raw[i] >= nlist) return RVCR_ERR_FORMAT;
-                sizes[raw[i]] = (int64_t)raw[i + 1];
-            }
-        } else {
-            set_error("'%s': list encoding '%.4s' unsupported", path, lt);
-            return RVCR_ERR_FORMAT;
-        }
-    } else {
-        set_error("'%s': inverted lists fourcc '%.4s' unsupported", path, four);
-        return RVCR_ERR_FORMAT;
+        for (uint64_t l = 0; l < p.nlist; ++l) sizes_out[l] = p.sizes[l];
+    }
+    return RVCR_OK;
+}
+
+int read_index_file(const char* path, int device, int rank, int world, rvcr_index** out) {
+    FileReader r;
+    if (!r.open(path)) {
+        set_error("cannot open index file '%s'", path);
+        return RVCR_ERR_IO;
+    }
+    ParsedIndex pi;
+    RVCR_TRY(parse_index(r, path, true, pi));
+    const Header& ih = pi.ih;
+    const uint64_t nlist = pi.nlist, nprobe = pi.nprobe;
+    const std::vector<float>& cent = pi.cent;
+    const std::vector<int64_t>& sizes = pi.sizes;
+    if (pi.layout == 0 && !r.seek(pi.payload_off)) {
+        set_error("'%s': seek failed", path);
+        return RVCR_ERR_IO;
     }
 
     int64_t lo = 0, hi = (int64_t)nlist;
@@ -239,13 +420,22 @@ int read_index_file(const char* path, int device, int rank, int world, rvcr_inde
             const int64_t n = sizes[l];
             if (n == 0) continue;
             if (l < lo || l >= hi) {
-                if (fseeko(r.f, (off_t)((size_t)n * (rowb + 8)), SEEK_CUR) != 0) {
+                if (pi.layout == 0 && !r.skip((uint64_t)n * (rowb + 8))) {
                     set_error("'%s': truncated list payload", path);
                     rc = RVCR_ERR_FORMAT;
                 }
                 continue;
             }
             const int64_t off = h->offsets_host[l];
+            if (pi.layout != 0) {
+                // legacy files keep a list's ids and its vectors in two different places
+                if (!r.seek(pi.codes_off[l]) || !copy_piece(reinterpret_cast<char*>(h->vecs) + (size_t)off * rowb, (size_t)n * rowb) ||
+                    !r.seek(pi.ids_off[l]) || !copy_piece(reinterpret_cast<char*>(h->ids) + (size_t)off * 8, (size_t)n * 8)) {
+                    set_error("'%s': truncated list payload or copy failure (list %lld)", path, (long long)l);
+                    rc = RVCR_ERR_FORMAT;
+                }
+                continue;
+            }
             if (!copy_piece(reinterpret_cast<char*>(h->vecs) + (size_t)off * rowb, (size_t)n * rowb) ||
                 !copy_piece(reinterpret_cast<char*>(h->ids) + (size_t)off * 8, (size_t)n * 8)) {
                 set_error("'%s': truncated list payload or copy failure (list %lld)", path, (long long)l);

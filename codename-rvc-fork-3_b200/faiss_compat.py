@@ -533,6 +533,32 @@ def read_index(path: str, device: int | None = None, shard: tuple[int, int] | No
     return _open_index(path, dev, shard)
 
 
+def probe_index(path: str, list_sizes: bool = False) -> dict:
+    """Describe an `.index` file on the host, no GPU involved (rvcr_index_probe): d, ntotal, nlist, nprobe, layout
+    ('IwFl' or the legacy 'IvFL' / 'IvFl'), list-size statistics, `searchable`.  Raises RvcrError exactly where
+    `read_index` would refuse the file.  With `list_sizes=True` the dict also holds the (nlist,) int64 vector counts."""
+    from ._ffi import FileInfo
+    inf = FileInfo()
+    p = os.fsencode(path)
+    check(lib().rvcr_index_probe(p, C.byref(inf), None, 0))
+    out = {k: getattr(inf, k) for k, _ in FileInfo._fields_ if not k.startswith("reserved")}
+    out["fourcc"] = inf.fourcc.decode("ascii", "replace")
+    out["quantizer_fourcc"] = inf.quantizer_fourcc.decode("ascii", "replace")
+    if list_sizes:
+        sizes = np.zeros(inf.nlist, np.int64)
+        check(lib().rvcr_index_probe(p, None, C.c_void_p(sizes.ctypes.data), sizes.size))
+        out["list_sizes"] = sizes
+    return out
+
+
+def shard_range(list_sizes, rank: int, world: int) -> tuple[int, int]:
+    """List range [lo, hi) that `read_index(path, shard=(rank, world))` loads: contiguous, balanced by vector count."""
+    sizes = np.ascontiguousarray(list_sizes, np.int64)
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    check(lib().rvcr_shard_range(C.c_void_p(sizes.ctypes.data), sizes.size, rank, world, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
 def write_index(index: IndexIVFFlat, path: str) -> None:
     """faiss.write_index(index, path) (extract_index.py:71)."""
     check(lib().rvcr_index_write(index.handle, str(path).encode()))

@@ -71,6 +71,29 @@ typedef struct rvcr_info {
     int32_t metric;       /* 1 = METRIC_L2                                                      */
 } rvcr_info;
 
+/* What an .index file holds, read on the host without touching a GPU (rvcr_index_probe). */
+typedef struct rvcr_file_info {
+    int32_t d;
+    int32_t is_trained;
+    int64_t ntotal;
+    int64_t nlist;
+    int64_t nprobe;           /* as persisted (extract_index.py:64 writes 1)                                   */
+    int32_t metric;           /* 1 = METRIC_L2 (anything else is refused)                                      */
+    int32_t layout;           /* 0 = "IwFl" (faiss >= 1.5), 1 = legacy "IvFL", 2 = legacy "IvFl"               */
+    int32_t direct_map_type;  /* 0 none, 1 array, 2 hash table (skipped by the reader)                         */
+    int32_t list_encoding;    /* 0 "full", 1 "sprs", 2 "il00" (no lists), 3 legacy per-list vectors            */
+    int64_t nvectors;         /* sum of the list sizes                                                         */
+    int64_t max_list_size;
+    int64_t nonempty_lists;
+    int64_t file_bytes;
+    int64_t payload_offset;   /* layout 0: offset of the first list's vectors; -1 for the legacy layouts         */
+    int32_t searchable;       /* 1 if rvcr_index_read + rvcr_search accept it as is (L2, d % 128 == 0, nprobe 1) */
+    char fourcc[8];           /* NUL-terminated                                                                */
+    char quantizer_fourcc[8];
+    int32_t reserved32;
+    int64_t reserved[4];
+} rvcr_file_info;
+
 typedef struct rvcr_stats {
     int64_t calls_search;       /* search / retrieve_blend calls served                          */
     int64_t queries;            /* queries processed                                             */
@@ -96,6 +119,15 @@ RVCR_API int rvcr_index_create(int32_t d, int64_t nlist, int device, rvcr_index*
 /* faiss.read_index(path)                                rvc/infer/pipeline.py:555
  * Streams the file straight into list-ordered device storage; no host copy of the vectors. */
 RVCR_API int rvcr_index_read(const char* path, int device, rvcr_index** out);
+/* Describe an .index file without a GPU: header fields, layout, list-size statistics; `list_sizes_host` (nullable, room for
+ * `nlist_cap` entries) receives the per-list vector counts, e.g. to plan shard ranges before loading.  Parses exactly what
+ * rvcr_index_read parses (same refusals, same codes); every count in the file is checked against the file length before it
+ * is trusted, so a corrupt or hostile file yields RVCR_ERR_FORMAT, never a crash.  faiss.read_index, pipeline.py:555. */
+RVCR_API int rvcr_index_probe(const char* path, rvcr_file_info* info_out, int64_t* list_sizes_host, int64_t nlist_cap);
+/* List range [*lo_out, *hi_out) that shard `rank` of `world` loads (rvcr_index_read_shard): contiguous, balanced by
+ * vector count.  Host only. */
+RVCR_API int rvcr_shard_range(const int64_t* list_sizes_host, int64_t nlist, int rank, int world, int64_t* lo_out,
+                              int64_t* hi_out);
 /* Same file, but stores only the lists of shard `rank` of `world` (contiguous list-id ranges balanced
  * by vector count).  The quantizer (all centroids, a few hundred MB at most) is replicated on every
  * shard, so rvcr_assign on any shard gives the global assignment; list ids are global. */

@@ -28,7 +28,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import build as _build
-from .index_io import IVFFlatData, read_index, write_index  # noqa: F401
+from .index_io import IVFFlatData, read_index, write_index, write_index_legacy  # noqa: F401
 
 FLT_MAX = np.float32(3.4028234663852886e38)
 

@@ -88,6 +88,42 @@ def write_index(data: IVFFlatData, path_or_file) -> None:
             f.close()
 
 
+def write_index_legacy(data: IVFFlatData, path_or_file, fourcc: bytes = b"IvFL") -> None:
+    """The pre-1.5 IndexIVFFlat layouts faiss 1.7.3 still reads (impl/index_read.cpp, `h == fourcc("IvFl") ||
+    h == fourcc("IvFL")` branch): ivf header, quantizer, then `READVECTOR(ids[i])` for every list
+    (read_ivf_header with `ids`), the direct map, then one vector of codes per list -- bytes for b"IvFL",
+    floats for the oldest b"IvFl".  faiss no longer WRITES these; this writer exists to test readers."""
+    assert fourcc in (b"IvFL", b"IvFl")
+    own = isinstance(path_or_file, (str, bytes))
+    f = open(path_or_file, "wb") if own else path_or_file
+    try:
+        nlist, d = data.nlist, data.d
+        f.write(fourcc)
+        _write_header(f, d, data.ntotal, data.is_trained, data.metric_type)
+        f.write(struct.pack("<QQ", nlist, data.nprobe))
+        f.write(b"IxF2" if data.metric_type == METRIC_L2 else b"IxFI")
+        _write_header(f, d, nlist, True, data.metric_type)
+        f.write(struct.pack("<Q", nlist * d))
+        f.write(np.ascontiguousarray(data.centroids, "<f4").tobytes())
+        sizes = [int(n) for n in np.asarray(data.list_sizes, np.int64)]
+        ids = np.ascontiguousarray(data.ids, "<i8")
+        vecs = np.ascontiguousarray(data.vecs, "<f4")
+        off = 0
+        for n in sizes:
+            f.write(struct.pack("<Q", n))
+            f.write(ids[off:off + n].tobytes())
+            off += n
+        f.write(struct.pack("<BQ", 0, 0))                      # maintain_direct_map = false, empty array
+        off = 0
+        for n in sizes:
+            f.write(struct.pack("<Q", n * d * (4 if fourcc == b"IvFL" else 1)))   # byte count / float count
+            f.write(vecs[off:off + n].tobytes())
+            off += n
+    finally:
+        if own:
+            f.close()
+
+
 def _rd(f, fmt):
     n = struct.calcsize(fmt)
     b = f.read(n)
@@ -103,6 +139,38 @@ def _read_header(f):
     return d, ntotal, bool(trained), metric
 
 
+def _read_legacy_lists(f, four, d, ntotal, nprobe, cent, metric, trained) -> IVFFlatData:
+    nlist = cent.shape[0]
+    id_parts = []
+    for _ in range(nlist):
+        (n,) = _rd(f, "<Q")
+        b = f.read(8 * n)
+        if len(b) != 8 * n:
+            raise ValueError("truncated index file")
+        id_parts.append(np.frombuffer(b, "<i8"))
+    (dm_type,) = _rd(f, "<B")
+    (dm_n,) = _rd(f, "<Q")
+    f.read(8 * dm_n)
+    if dm_type == 2:
+        (hn,) = _rd(f, "<Q")
+        f.read(16 * hn)
+    unit = 1 if four == b"IvFL" else 4
+    vec_parts = []
+    for l in range(nlist):
+        (m,) = _rd(f, "<Q")
+        if m * unit != len(id_parts[l]) * 4 * d:
+            raise ValueError("legacy list: id / code counts disagree")
+        b = f.read(m * unit)
+        if len(b) != m * unit:
+            raise ValueError("truncated index file")
+        vec_parts.append(np.frombuffer(b, "<f4").reshape(-1, d))
+    sizes = np.array([len(i) for i in id_parts], np.int64)
+    return IVFFlatData(d=d, ntotal=ntotal, nprobe=nprobe, centroids=cent, list_sizes=sizes,
+                       vecs=np.concatenate(vec_parts).astype(np.float32) if nlist else np.empty((0, d), np.float32),
+                       ids=np.concatenate(id_parts).astype(np.int64) if nlist else np.empty(0, np.int64),
+                       metric_type=metric, is_trained=trained)
+
+
 def read_index(path_or_bytes) -> IVFFlatData:
     if isinstance(path_or_bytes, (bytes, bytearray)):
         f = io.BytesIO(path_or_bytes)
@@ -112,8 +180,8 @@ def read_index(path_or_bytes) -> IVFFlatData:
         own = True
     try:
         four = f.read(4)
-        if four != b"IwFl":
-            raise ValueError(f"unsupported index fourcc {four!r} (expected b'IwFl')")
+        if four not in (b"IwFl", b"IvFL", b"IvFl"):
+            raise ValueError(f"unsupported index fourcc {four!r} (expected b'IwFl' or legacy b'IvFL' / b'IvFl')")
         d, ntotal, trained, metric = _read_header(f)
         nlist, nprobe = _rd(f, "<QQ")
         qf = f.read(4)
@@ -124,6 +192,8 @@ def read_index(path_or_bytes) -> IVFFlatData:
         if qd != d or qn != nlist or count != nlist * d:
             raise ValueError("inconsistent quantizer header")
         cent = np.frombuffer(f.read(4 * count), "<f4").reshape(nlist, d).copy()
+        if four != b"IwFl":
+            return _read_legacy_lists(f, four, d, ntotal, nprobe, cent, metric, trained)
         (dm_type,) = _rd(f, "<B")
         (dm_n,) = _rd(f, "<Q")
         f.read(8 * dm_n)

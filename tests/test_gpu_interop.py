@@ -3,7 +3,9 @@
 
 Files are assembled from the oracle writer's bytes by editing the header fields a different faiss build / fork
 would write: the legacy flat-quantizer fourcc `IxFl`, a populated array direct map, a populated hash direct map,
-nprobe != 1 in the header.  The legacy index fourcc `IvFl` and a non-L2 metric must be refused loudly."""
+nprobe != 1 in the header.  A non-L2 metric and a legacy index fourcc `IvFl` stamped on a current-layout body (it does not
+parse as the legacy layout) must be refused loudly; genuine legacy files are covered by tests/test_gpu_zz_legacy_index.py
+and, at the parser, by tests/test_index_probe.py."""
 import struct
 import threading
 
@@ -73,7 +75,7 @@ def test_files_from_other_writers(rvcr, oracle, tmp_path):
     idx.nprobe = 1
     D, I = idx.search(b["q"], k=8)
     assert np.array_equal(I, b["oidx"].search(b["q"], k=8)[1])
-    # refused loudly: legacy IndexIVFFlat fourcc, inner-product metric, truncated payload
+    # refused loudly: legacy IndexIVFFlat fourcc on a current-layout body, inner-product metric, truncated payload
     f5 = bytearray(raw)
     f5[0:4] = b"IvFl"
     (tmp_path / "ivfl.index").write_bytes(f5)
