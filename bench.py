@@ -218,6 +218,79 @@ def run_reference_arm(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def build_roofline(phase_acc, coarse_on_tensor_cores, pk, *, nst, n_home, owned_q, nlist, d, scan_impl, workload, world):
+    """Per-phase rooflines from the library's CUDA-event phase times (ms) and the ALGORITHMIC work of SURVEY 8d.
+    nst = vectors stored on this rank, n_home = queries whose coarse step runs here, owned_q = queries whose list lives
+    here (uniform queries: nq / world).  Returns (dict by phase, name of the dominant phase)."""
+    coarse_flops = 2.0 * n_home * nlist * d     # home queries x all centroids (replicated quantizer)
+    scan_bytes = nst * (4 * d + 8) + owned_q * 4 * d + owned_q * K * 12      # B_s (SURVEY 8d): every list probed at these sizes
+    blend_bytes = owned_q * (K * 4 * d + 8 * d) + owned_q * K * 12           # B_g
+    roof = {}
+    if "coarse_main" in phase_acc:
+        tf = coarse_flops / (phase_acc["coarse_main"] * 1e-3) / 1e12
+        tc = coarse_on_tensor_cores
+        # MEASURED_PEAKS.json holds two cuBLAS bf16 figures: the burst one (best of ten 0.7 ms GEMMs) for a kernel timed
+        # alone, the sustained one (back to back for 4 s, power-capped clocks) for a kernel timed inside a long step.  A
+        # launch that runs for tens of milliseconds inside back-to-back steps is in the sustained regime (the clocks
+        # line shows sw_power_cap); microsecond launches (C1 / C2) are compared with the burst figure.  Both fractions
+        # are reported.
+        sustained = tc and phase_acc["coarse_main"] >= 20.0
+        peak = (pk["bf16_tflops_sustained"] if sustained else pk["bf16_tflops"]) if tc else 72.5
+        roof["coarse"] = {"bound": "tensor" if tc else "fp32-ffma", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+                          "frac": tf / peak, "traffic": None,
+                          "kernel": "coarse_tc_kernel<2> (tcgen05 bf16, fp32 accumulate)" if tc else "coarse_exact_kernel",
+                          "ms": phase_acc["coarse_main"], "flops_per_launch": coarse_flops,
+                          "peak_source": (pk["source"] + (" cuBLAS bf16 sustained (the launch runs %.0f ms inside back-to-back steps)"
+                                                          % phase_acc["coarse_main"] if sustained else " cuBLAS bf16 burst"))
+                          if tc else "measured FFMA micro-peak (profiles/)"}
+        if tc:
+            roof["coarse"]["frac_vs_burst"] = tf / pk["bf16_tflops"]
+            roof["coarse"]["frac_vs_sustained"] = tf / pk["bf16_tflops_sustained"]
+    fused = "scan" in phase_acc and "blend" not in phase_acc      # the re-check kernel also gathered + blended
+    if "scan" in phase_acc:
+        sb = scan_bytes + (blend_bytes if fused else 0)
+        gb = sb / (phase_acc["scan"] * 1e-3) / 1e9
+        roof["scan"] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / pk["hbm_gbs"],
+                        "traffic": None, "kernel": ("scan_tc_kernel (tcgen05 tf32 + TMA) + scan_recheck_kernel (exact fp32"
+                                                    + (" + gather/weights/blend)" if fused else ")")) if "scan_recheck" in phase_acc
+                        else f"scan_topk_kernel_v{scan_impl or 4}", "ms": phase_acc["scan"], "bytes_per_launch": sb,
+                        "bytes_note": "B_s + B_g (SURVEY 8d): scan and fused tail" if fused else "B_s (SURVEY 8d)",
+                        "peak_source": pk["source"]}
+    if "blend" in phase_acc:
+        gb = blend_bytes / (phase_acc["blend"] * 1e-3) / 1e9
+        roof["blend"] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / pk["hbm_gbs"],
+                         "traffic": None, "kernel": "gather_blend_kernel", "ms": phase_acc["blend"],
+                         "bytes_per_launch": blend_bytes, "peak_source": pk["source"]}
+    dominant = max(roof, key=lambda k: roof[k]["ms"]) if roof else None
+    # the scan phase split into its two kernels (not candidates for `dominant`): the streaming tensor-core scan against
+    # B_s (the north star's "list-scan HBM roofline") and the exact re-check + fused tail against B_g
+    if fused and "scan_recheck" in phase_acc and phase_acc["scan_recheck"] > 0:
+        t_tail = phase_acc["scan_recheck"] + phase_acc.get("scan_fallback", 0.0)
+        t_stream = phase_acc["scan"] - t_tail
+        if t_stream > 0:
+            gb = scan_bytes / (t_stream * 1e-3) / 1e9
+            roof["scan_stream"] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / pk["hbm_gbs"],
+                                   "traffic": None, "kernel": "scan_tc_kernel (tcgen05 tf32 + TMA), incl. pad fill / counters",
+                                   "ms": t_stream, "bytes_per_launch": scan_bytes, "bytes_note": "B_s (SURVEY 8d)",
+                                   "peak_source": pk["source"]}
+        gb = blend_bytes / (t_tail * 1e-3) / 1e9
+        roof["scan_tail"] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / pk["hbm_gbs"],
+                             "traffic": None, "kernel": "scan_recheck_kernel (exact fp32 re-check + gather/weights/blend)",
+                             "ms": t_tail, "bytes_per_launch": blend_bytes, "bytes_note": "B_g (SURVEY 8d)",
+                             "peak_source": pk["source"]}
+    traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if dominant and world == 1 and os.path.exists(traffic_file):   # the capture is of the 1-GPU step
+        try:
+            tr = json.load(open(traffic_file))
+            for k in roof:
+                w = tr.get(workload, {})
+                roof[k]["traffic"] = w.get(k, w.get(roof[k]["kernel"].split(" ")[0].split("<")[0]) if k in ("coarse", "scan") else None)
+        except Exception:
+            pass
+
+    return roof, dominant
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -365,46 +438,9 @@ def main():
             phase_acc[k] = phase_acc.get(k, 0.0) + v / reps
         del b
     st = index.stats()
-    pk = peaks()
-    nst = int(sizes[lo:hi].sum())
-    owned_q = nq / world                        # uniform queries: each shard owns ~1/world of them
-    coarse_flops = 2.0 * n_home * nlist * d     # home queries x all centroids (replicated quantizer)
-    scan_bytes = nst * (4 * d + 8) + owned_q * 4 * d + owned_q * K * 12      # B_s: every list probed at these sizes
-    blend_bytes = owned_q * (K * 4 * d + 8 * d) + owned_q * K * 12           # B_g
-    roof = {}
-    if "coarse_main" in phase_acc:
-        tf = coarse_flops / (phase_acc["coarse_main"] * 1e-3) / 1e12
-        tc = st["coarse_tc_queries"] > 0
-        roof["coarse"] = {"bound": "tensor" if tc else "fp32-ffma", "achieved": tf,
-                          "peak": pk["bf16_tflops"] if tc else 72.5, "unit": "TFLOP/s",
-                          "frac": tf / (pk["bf16_tflops"] if tc else 72.5), "traffic": None,
-                          "kernel": "coarse_tc_kernel<2> (tcgen05 bf16, fp32 accumulate)" if tc else "coarse_exact_kernel",
-                          "ms": phase_acc["coarse_main"], "flops_per_launch": coarse_flops,
-                          "peak_source": pk["source"] + " cuBLAS bf16 burst" if tc else "measured FFMA micro-peak (profiles/)"}
-    fused = "scan" in phase_acc and "blend" not in phase_acc      # the re-check kernel also gathered + blended
-    if "scan" in phase_acc:
-        sb = scan_bytes + (blend_bytes if fused else 0)
-        gb = sb / (phase_acc["scan"] * 1e-3) / 1e9
-        roof["scan"] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / pk["hbm_gbs"],
-                        "traffic": None, "kernel": ("scan_tc_kernel (tcgen05 tf32 + TMA) + scan_recheck_kernel (exact fp32"
-                                                    + (" + gather/weights/blend)" if fused else ")")) if "scan_recheck" in phase_acc
-                        else f"scan_topk_kernel_v{args.scan_impl or 4}", "ms": phase_acc["scan"], "bytes_per_launch": sb,
-                        "bytes_note": "B_s + B_g (SURVEY 8d): scan and fused tail" if fused else "B_s (SURVEY 8d)",
-                        "peak_source": pk["source"]}
-    if "blend" in phase_acc:
-        gb = blend_bytes / (phase_acc["blend"] * 1e-3) / 1e9
-        roof["blend"] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / pk["hbm_gbs"],
-                         "traffic": None, "kernel": "gather_blend_kernel", "ms": phase_acc["blend"],
-                         "bytes_per_launch": blend_bytes, "peak_source": pk["source"]}
-    dominant = max(roof, key=lambda k: roof[k]["ms"]) if roof else None
-    traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if dominant and world == 1 and os.path.exists(traffic_file):   # the capture is of the 1-GPU step
-        try:
-            tr = json.load(open(traffic_file))
-            for k in roof:
-                roof[k]["traffic"] = tr.get(args.workload, {}).get(roof[k]["kernel"].split(" ")[0].split("<")[0])
-        except Exception:
-            pass
+    roof, dominant = build_roofline(phase_acc, st["coarse_tc_queries"] > 0, peaks(), nst=int(sizes[lo:hi].sum()), n_home=n_home,
+                                    owned_q=nq / world, nlist=nlist, d=d, scan_impl=args.scan_impl, workload=args.workload,
+                                    world=world)
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region --------------
     e2e = None
@@ -456,13 +492,19 @@ def main():
         sub_ids = np.arange(len(sub_vecs), dtype=np.int64)
         cpu_path(oracle, qs[:256], cent_h, sub_off, sub_vecs, sub_ids)      # warm-up (thread pools, page faults)
         t0 = time.perf_counter()
-        out_cpu, _ = cpu_path(oracle, qs, cent_h, sub_off, sub_vecs, sub_ids)
-        sec = time.perf_counter() - t0
+        passes = 0
+        while True:                                                         # about 10 s of CPU work, at most 8 passes
+            out_cpu, _ = cpu_path(oracle, qs, cent_h, sub_off, sub_vecs, sub_ids)
+            passes += 1
+            if time.perf_counter() - t0 >= 10.0 or passes >= 8:
+                break
+        total_s = time.perf_counter() - t0
+        sec = total_s / passes
         import torch as _t
         cpu = {"value": sample / sec, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
                "sample": f"first {sample} of {nq} query frames of this workload, all {nlist} centroids, the {len(probed)} lists "
-                         f"they probe staged on the host; {sec:.2f} s of CPU work; oracle port of faiss 1.7.3 + numpy "
-                         f"(omp_threads={oracle.num_threads()}, torch_threads={_t.get_num_threads()})"}
+                         f"they probe staged on the host; {passes} passes, {total_s:.1f} s of CPU work; oracle port of faiss "
+                         f"1.7.3 + numpy (omp_threads={oracle.num_threads()}, torch_threads={_t.get_num_threads()})"}
         del sub_vecs
 
     if rank == 0:
