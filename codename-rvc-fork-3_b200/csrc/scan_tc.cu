@@ -597,7 +597,8 @@ __device__ __forceinline__ float4 blend_vec(const float4 (&v)[RVCR_K], const flo
 // BLEND: 0 = search only, 1 = + fused tail in place, 2 = + fused tail + 2x upsample / protect mix into post.out2, 3 = + fused
 // tail pushed to the home rank's buffer over NVLink (separate instantiations so the default kernel's code and register
 // count stay exactly as profiled).
-template <int BLEND>
+// UNR: float4 loads in flight per lane in the distance loop (8 as profiled in round 1; 16 is a tuning variant, RVCR_RC_UNROLL).
+template <int BLEND, int UNR = 8>
 __global__ void __launch_bounds__(RC_WARPS * 32)
 scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qorder, const uint32_t* __restrict__ keys,
                     uint32_t nlist, const int32_t* __restrict__ items, const int32_t* __restrict__ nitems_ptr, int item_begin,
@@ -633,7 +634,7 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
                 const float4* y4 = reinterpret_cast<const float4*>(vecs + (int64_t)pos * d) + h;
                 const float4* x4 = reinterpret_cast<const float4*>(sq) + h;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
+#pragma unroll UNR
                 for (int i = 0; i < (d >> 3); ++i) {
                     const float4 y = __ldg(y4 + 2 * i);
                     const float4 x = x4[2 * i];
@@ -913,6 +914,9 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
             int64_t rgrid = (int64_t)h->num_sms * per_sm;
             if (rgrid * RC_WARPS > n) rgrid = (n + RC_WARPS - 1) / RC_WARPS;
             auto kern = bmode == 0 ? scan_recheck_kernel<0> : bmode == 1 ? scan_recheck_kernel<1> : bmode == 2 ? scan_recheck_kernel<2> : scan_recheck_kernel<3>;
+            if (const char* e = getenv("RVCR_RC_UNROLL"))   // tuning knob: fewer CTAs per SM (RVCR_RC_CTAS) with more loads in flight per lane
+                if (atoi(e) == 16)
+                    kern = bmode == 0 ? scan_recheck_kernel<0, 16> : bmode == 1 ? scan_recheck_kernel<1, 16> : bmode == 2 ? scan_recheck_kernel<2, 16> : scan_recheck_kernel<3, 16>;
             kern<<<(unsigned)rgrid, RC_WARPS * 32, rsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), (uint32_t)h->nlist,
                                                              h->ws_items.as<int32_t>(), h->ws_misc.as<int32_t>(), item_begin, item_end, n,
                                                              d, h->vecs, h->ids, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
