@@ -6,7 +6,9 @@
 
 Why: there is no GPU in the build container, so a kernel that was validated on a B200 must not change by accident when
 host code, headers or OTHER template instantiations are edited.  The fingerprint is the sha1 of `cuobjdump -sass` of one
-function with the address / encoding comments stripped."""
+function with the address / encoding comments stripped.  ptxas does not always number (uniform) registers the same way in
+two runs over the same source, so a second fingerprint with register numbers masked is kept: a kernel whose exact hash
+differs but whose masked hash is equal is reported as RENAMED (same instruction stream), not CHANGED."""
 import glob
 import hashlib
 import json
@@ -29,16 +31,18 @@ def fingerprints():
         def flush():
             if name is not None:
                 body = "\n".join(lines)
-                out[f"{os.path.basename(obj)}:{name}"] = {"sha1": hashlib.sha1(body.encode()).hexdigest(), "lines": len(lines)}
+                masked = re.sub(r"\b(U?R|U?P)\d+\b", r"\1#", body)
+                out[f"{os.path.basename(obj)}:{name}"] = {"sha1": hashlib.sha1(body.encode()).hexdigest(),
+                                                         "sha1_masked": hashlib.sha1(masked.encode()).hexdigest(), "lines": len(lines)}
 
         for ln in txt.splitlines():
             m = re.search(r"Function : (\S+)", ln)
             if m:
                 flush()
-                name, lines = m.group(1), []
+                name, lines = re.sub(r"_GLOBAL__N__[0-9a-f]+_", "_GLOBAL__N__", m.group(1)), []   # path-dependent hash
             elif name is not None:
-                ln = re.sub(r"/\*[0-9a-fx]+\*/", "", ln).strip()
-                if ln:
+                ln = re.sub(r"/\*.*?\*/", "", ln).strip()          # addresses and encodings
+                if ln and not ln.startswith("identifier ="):
                     lines.append(ln)
         flush()
     return out
@@ -54,13 +58,15 @@ def main():
         print(f"{len(cur)} kernels -> {path}")
         return 0
     old = json.load(open(path))
-    changed = [k for k in cur if k in old and cur[k]["sha1"] != old[k]["sha1"]]
+    differs = [k for k in cur if k in old and cur[k]["sha1"] != old[k]["sha1"]]
+    renamed = [k for k in differs if old[k].get("sha1_masked") == cur[k]["sha1_masked"]]
+    changed = [k for k in differs if k not in renamed]
     new = [k for k in cur if k not in old]
     gone = [k for k in old if k not in cur]
-    for tag, ks in (("CHANGED", changed), ("NEW", new), ("GONE", gone)):
+    for tag, ks in (("CHANGED", changed), ("RENAMED", renamed), ("NEW", new), ("GONE", gone)):
         for k in ks:
             print(tag, k)
-    print(f"{len(cur)} kernels: {len(changed)} changed, {len(new)} new, {len(gone)} gone")
+    print(f"{len(cur)} kernels: {len(changed)} changed, {len(renamed)} with renamed registers only, {len(new)} new, {len(gone)} gone")
     return 1 if changed or gone else 0
 
 
