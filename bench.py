@@ -253,7 +253,8 @@ def build_roofline(phase_acc, coarse_on_tensor_cores, pk, *, nst, n_home, owned_
         roof["scan"] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / pk["hbm_gbs"],
                         "traffic": None, "kernel": ("scan_tc_kernel (tcgen05 tf32 + TMA) + scan_recheck_kernel (exact fp32"
                                                     + (" + gather/weights/blend)" if fused else ")")) if "scan_recheck" in phase_acc
-                        else f"scan_topk_kernel_v{scan_impl or 4}", "ms": phase_acc["scan"], "bytes_per_launch": sb,
+                        else ("scan_tc_fused_kernel (tcgen05 tf32 + TMA; exact re-check + tail as a warp role)" if scan_impl == 6
+                              else f"scan_topk_kernel_v{scan_impl or 4}"), "ms": phase_acc["scan"], "bytes_per_launch": sb,
                         "bytes_note": "B_s + B_g (SURVEY 8d): scan and fused tail" if fused else "B_s (SURVEY 8d)",
                         "peak_source": pk["source"]}
     if "blend" in phase_acc:
@@ -304,7 +305,7 @@ def main():
     ap.add_argument("--workload", default="C5", choices=["C1", "C2", "C3", "C5"])
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--coarse-mode", type=int, default=0)
-    ap.add_argument("--scan-impl", type=int, default=0, help="0 = library default (auto by batch size), 5 = tcgen05 scan, 1-4 exact FFMA scans")
+    ap.add_argument("--scan-impl", type=int, default=0, help="0 = library default (auto by batch size), 5 = tcgen05 scan, 1-4 exact FFMA scans, 6 = experimental fused scan + re-check")
     ap.add_argument("--tc-resident", type=int, default=-1, help="coarse kernel: resident query k-blocks (0/8/9/10; -1 = library default)")
     ap.add_argument("--fused-blend", type=int, default=-1, help="1 = re-check kernel also blends (default), 0 = separate gather_blend kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")

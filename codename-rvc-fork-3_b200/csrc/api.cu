@@ -909,7 +909,7 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "profile")) {
         h->opt.profile = value ? 1 : 0;
     } else if (!strcmp(key, "scan_impl")) {
-        if (value < 0 || value > 5) return RVCR_ERR_INVALID;
+        if (value < 0 || value > 6) return RVCR_ERR_INVALID;   // 6: experimental fused re-check (scan_tc_fused.cu), never auto
         h->opt.scan_impl = value;
     } else if (!strcmp(key, "tc_cluster")) {
         if (value != 1 && value != 2) return RVCR_ERR_INVALID;

@@ -84,7 +84,8 @@ struct Options {
     int64_t profile = 0;      // record CUDA events around each phase's kernels
     int64_t scan_impl = 0;    // 0 auto (default): 5 for batches of >= scan_tc_min_queries, else 4; 5 tcgen05 tf32 + exact
                               // re-check; exact FFMA scans: 1 scalar 8-lane, 2 packed f32x2
-                              // TQx4, 3 same with 16 warps, 4 packed TQx8 tile
+                              // TQx4, 3 same with 16 warps, 4 packed TQx8 tile; 6 = 5 with the re-check folded into the
+                              // scan kernel (scan_tc_fused.cu; experimental, explicit only)
     int64_t tc_cluster = 2;   // tcgen05 path: 1 = one CTA per SM, 2 = CTA pairs (cta_group::2)
     int64_t fused_blend = 1;  // scan_impl 5: re-check kernel also does the gather + weights + blend
     // Size rules of the auto modes, set from measurements (profiles/r01_small_dispatch.json, B200).  The tensor-core scan has

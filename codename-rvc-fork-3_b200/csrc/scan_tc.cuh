@@ -172,4 +172,9 @@ __device__ __forceinline__ float4 blend_vec(const float4 (&v)[RVCR_K], const flo
     return o;
 }
 
+// scan_tc_fused.cu (scan_impl 6, experimental)
+int launch_scan_tc_fused(rvcr_index* h, const CUtensorMap* tm, const float* q, int64_t n, float rel, float absm, int item_begin,
+                         int item_end, int ticket_slot, int32_t* fb_count, float* D, int32_t* P, int64_t* I,
+                         const BlendArgs& ba, int bmode, cudaStream_t s);
+
 }  // namespace rvcr

@@ -1,28 +1,20 @@
-// scan_tc.cu -- inverted-list scan on the 5th-gen tensor cores (tcgen05 kind::tf32 + TMEM + TMA), made
-// FP32-exact by an exact re-check.  scan_impl = 5 (default).
+// scan_tc_fused.cu -- scan_impl = 6 (EXPERIMENTAL, never chosen by the auto mode): the tensor-core list scan of scan_tc.cu
+// with the exact re-check + gather / weights / blend folded into the same persistent kernel as a fourth warp role.
 //
-// Replaces the same reference stage as scan_topk.cu: index.search(npy, k=8) (rvc/infer/pipeline.py:499)
-// -> IndexIVF::search_preassigned -> IVFFlatScanner<METRIC_L2>::scan_codes + heap.
+// Same reference stage as scan_tc.cu: index.search(npy, k=8) + the numpy tail, rvc/infer/pipeline.py:499-506.
 //
-// Why: the exact FP32 scan needs 2 lane-ops per (query, row, element); with ~11 queries per probed list at
-// C5 that is as much FP32-pipe time as the list bytes take at HBM speed, and in practice
-// the shared-memory pipe saturates first.  Here the streamed list rows never touch the CUDA cores:
+// Why (profiles/r01_ncu_summary.md): with two kernels the re-check runs after ALL lists have been
+// streamed, so its 13 candidate rows per query (and the 8 gathered ones) come from HBM a second time: 64.6 GB of DRAM
+// traffic for 30.8 GB of algorithmic work, 0.38 of the HBM roofline, and the scan phase as a whole stops at 0.62.  Here a
+// list's candidates are re-checked by warps of the same CTA right after the list has been streamed (a 4-deep hand-off ring
+// behind the epilogue warps), while the TMA / MMA / splitter warps are already on the next lists; a list is ~1 MB and
+// 148 CTAs stream ~160 MB through the 126 MB L2 in the time a list takes, so a large part of the candidate reads -- and
+// all of the 8 gather reads, which follow the distance pass within microseconds -- are L2 hits.
 //
-//   TMA      list rows (fp32, row-major, 128 rows x 32 floats = 16 KB boxes, 128B swizzle) HBM -> shared memory
-//   tcgen05  kind::tf32 MMA  acc[row, query] = <y_row, q>  (A = the staged rows, B = the item's <= 16 queries,
-//            both read from shared memory as K-major fp32; the tensor core uses the top 19 bits of each
-//            operand), fp32 accumulation in TMEM
-//   epilogue v = ||y||^2 - 2 acc  (||y||^2 precomputed per stored row) -> shared memory, [query][row] per chunk
-//            of 512 rows
-//   select   per query: U = 8th smallest of the 32 lane minima (an upper bound of the 8th smallest v, and
-//            within a row or two of it); every row with v <= U + margin(q) is a candidate (ballot-compacted)
-//   recheck  canonical fp32 distance (fvec_L2sqr order, pairdist.cuh) of each candidate, top-8 by
-//            (distance, position): bit-identical to the exact scan
-//
-// margin(q) bounds twice the worst-case |v - v_true| (tf32 truncation of both operands, Cauchy-Schwarz;
-// fp32 accumulation of d products; norm roundings), so the true top-8 are always among the candidates
-// (DESIGN.md "Numerics").  If more than 64 rows qualify, the query is re-done by the brute-force exact
-// kernel below.
+// Status: written after the last GPU session of round 1 and NOT yet run on a B200; results must equal scan_impl 5 bit for
+// bit (same candidates, same canonical distances, same tail arithmetic).  tests/test_gpu_scan_tc.py covers it only when
+// RVCR_TEST_EXPERIMENTAL=1.  The 768-thread CTA needs per-role register budgets (setmaxnreg): 65536 / 768 = 85 registers
+// per thread would spill the splitter and epilogue warps (113 in the 512-thread kernel).
 #include <stddef.h>
 #include <stdlib.h>
 
@@ -32,16 +24,117 @@ namespace rvcr {
 
 namespace stc {
 
-__global__ void __launch_bounds__(THREADS, 1)
-scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__ CUtensorMap tm64,
+constexpr int RCW = 8;                          // re-check warps (warpgroups 4 and 5)
+constexpr int RC_WARP0 = THREADS / 32;          // 16
+constexpr int FTHREADS = THREADS + RCW * 32;    // 768
+constexpr int RCRING = 4;                       // items the epilogue may run ahead of the re-check warps
+// Register budgets per warpgroup (setmaxnreg; multiples of 8).  The CTA is launched with 80 per thread (61 440):
+// 128 x 40 + 128 x 104 + 256 x 112 + 256 x 56 = 61 440.
+constexpr int REGS_CTRL = 40;                   // warps 0-3: TMA, MMA, TMEM allocator, scheduler
+constexpr int REGS_EPI = 104;                   // warps 4-7
+constexpr int REGS_SPLIT = 112;                 // warps 8-15
+constexpr int REGS_RC = 56;                     // warps 16-23
+
+struct SmemF : Smem {
+    uint64_t rcfull[RCRING], rcempty[RCRING];   // epilogue -> re-check hand-off ring
+    int rc_p0[RCRING];                          // sorted position of the item's first query
+    int rc_cnt[RCRING];                         // queries in the item; -1 = no more items
+};
+
+template <int N>
+__device__ __forceinline__ void reg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N));
+}
+
+// One query (sorted position p) by one warp: the body of scan_recheck_kernel (scan_tc.cu) without the shared-memory copy
+// of the query -- all 16 lane pairs read the SAME query addresses, so those loads are one broadcast sector per warp
+// instruction from L1 / L2, and this kernel's shared memory is full.  cand / candcnt were written by the epilogue warps of
+// this CTA and published through the hand-off barrier: plain (coherent) loads, not the read-only path.
+template <int BLEND>
+__device__ __forceinline__ void recheck_query(int64_t p, const float* q, const int32_t* __restrict__ qorder, int d,
+                                              const float* __restrict__ vecs, const int64_t* __restrict__ ids,
+                                              const int32_t* cand, const int32_t* candcnt, float* D, int32_t* P, int64_t* I,
+                                              const BlendArgs& ba, int lane) {
+    const int64_t qi = qorder[p];
+    const int nc = *reinterpret_cast<const volatile int32_t*>(candcnt + qi);
+    if (nc < 0) return;   // overflowed: the exact fallback kernel answers this query
+    const int h = lane & 1;
+    const int nvec = d >> 2;
+    const float4* q4 = reinterpret_cast<const float4*>(q + qi * d);
+    float td = RVCR_FLT_MAX;
+    int tp = 0x7fffffff;
+    for (int base = 0; base < nc; base += 16) {
+        const int c = base + (lane >> 1);
+        const bool have = c < nc;
+        const int pos = *reinterpret_cast<const volatile int32_t*>(cand + qi * CCAP + (have ? c : 0));
+        const float4* y4 = reinterpret_cast<const float4*>(vecs + (int64_t)pos * d) + h;
+        const float4* x4 = q4 + h;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < (d >> 3); ++i) {
+            const float4 y = __ldg(y4 + 2 * i);
+            const float4 x = x4[2 * i];
+            const float t0 = __fsub_rn(x.x, y.x), t1 = __fsub_rn(x.y, y.y), t2 = __fsub_rn(x.z, y.z), t3 = __fsub_rn(x.w, y.w);
+            a0 = __fmaf_rn(t0, t0, a0);
+            a1 = __fmaf_rn(t1, t1, a1);
+            a2 = __fmaf_rn(t2, t2, a2);
+            a3 = __fmaf_rn(t3, t3, a3);
+        }
+        // canonical reduction ((a0+a4)+(a1+a5))+((a2+a6)+(a3+a7)); lane h holds a[4h..4h+3]
+        const float s0 = __fadd_rn(a0, __shfl_xor_sync(0xffffffffu, a0, 1));
+        const float s1 = __fadd_rn(a1, __shfl_xor_sync(0xffffffffu, a1, 1));
+        const float s2 = __fadd_rn(a2, __shfl_xor_sync(0xffffffffu, a2, 1));
+        const float s3 = __fadd_rn(a3, __shfl_xor_sync(0xffffffffu, a3, 1));
+        const float dist = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+        top8_update(td, tp, dist, pos, have && h == 0, lane);
+    }
+    if (lane < RVCR_K) {
+        const bool pad = tp == 0x7fffffff;
+        D[qi * RVCR_K + lane] = pad ? RVCR_FLT_MAX : td;
+        P[qi * RVCR_K + lane] = pad ? -1 : tp;
+        if (I) I[qi * RVCR_K + lane] = pad ? (int64_t)-1 : ids[tp];
+    }
+    if (BLEND) {
+        float wn;
+        int spos;
+        blend_weights(td, tp, lane, ba.last_row_pos, wn, spos);
+        float wk[RVCR_K];
+        const float4* rows[RVCR_K];
+#pragma unroll
+        for (int k = 0; k < RVCR_K; ++k) {
+            wk[k] = __shfl_sync(0xffffffffu, wn, k);
+            const int pk = __shfl_sync(0xffffffffu, spos, k);
+            rows[k] = pk >= 0 ? reinterpret_cast<const float4*>(vecs + (int64_t)pk * d) : nullptr;
+        }
+        float4* o4 = BLEND == 3 ? push_row_ptr(ba.push, qi, d) : reinterpret_cast<float4*>(ba.out + qi * d);
+        for (int c = lane; c < nvec; c += 32) {
+            float4 v[RVCR_K];
+#pragma unroll
+            for (int k = 0; k < RVCR_K; ++k) v[k] = rows[k] ? __ldg(rows[k] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 f0 = q4[c];      // read before this lane overwrites the same 16 bytes (in-place blend)
+            const float4 o = blend_vec(v, wk, f0, ba.r32, ba.omr32);
+            if (BLEND == 2) post_store(ba.post, qi, d, c, o, f0);
+            else o4[c] = o;
+        }
+    }
+}
+
+template <int BLEND>
+__global__ void __launch_bounds__(FTHREADS, 1)
+scan_tc_fused_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__ CUtensorMap tm64,
                const __grid_constant__ CUtensorMap tm96, const __grid_constant__ CUtensorMap tm128,
-               const float* __restrict__ q, const int32_t* __restrict__ qorder, const uint32_t* __restrict__ keys,
+               const float* q /* may alias ba.out: blended in place */, const int32_t* __restrict__ qorder, const uint32_t* __restrict__ keys,
                const int32_t* __restrict__ items, const int32_t* __restrict__ nitems_ptr, int32_t* __restrict__ ticket,
                const int64_t* __restrict__ offsets, const float* __restrict__ ynorm, uint32_t nlist, int64_t n, int d,
                int nstage, float ymax, float acc_rel, float abs_margin, int item_begin, int item_end,
-               int32_t* __restrict__ cand, int32_t* __restrict__ candcnt, int32_t* __restrict__ fb_list,
+               int32_t* cand, int32_t* candcnt /* written by the epilogue warps, read by the re-check warps */, int32_t* __restrict__ fb_list,
                int32_t* __restrict__ fb_count, unsigned long long* __restrict__ totals /*[0] fallbacks, [1] candidates*/,
-               float2* __restrict__ stage_buf /*[grid][16][SCAP]*/, int dbg_flags) {
+               float2* __restrict__ stage_buf /*[grid][16][SCAP]*/, int dbg_flags, const float* __restrict__ vecs,
+               const int64_t* __restrict__ ids, float* D, int32_t* P, int64_t* I, BlendArgs ba) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nkb = d / KB;
@@ -49,7 +142,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
     uint8_t* sQ = sR + (size_t)nstage * STAGE_BYTES;            // 2 x nkb x 2 KB
     const int qbuf_bytes = nkb * QKB_BYTES;
     float* sV = reinterpret_cast<float*>(sQ + 2 * (size_t)qbuf_bytes);    // [16][CHUNK_ROWS]
-    Smem* S = reinterpret_cast<Smem*>(reinterpret_cast<uint8_t*>(sV) + SV_BYTES);
+    SmemF* S = reinterpret_cast<SmemF*>(reinterpret_cast<uint8_t*>(sV) + SV_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nitems = min(*nitems_ptr, item_end);
@@ -79,6 +172,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
         }
         tc::mbar_init(&S->qfull[0], EPI_THREADS / 32);
         tc::mbar_init(&S->qfull[1], EPI_THREADS / 32);
+        for (int i = 0; i < RCRING; ++i) {
+            tc::mbar_init(&S->rcfull[i], EPI_THREADS / 32);   // every epilogue warp has published its queries' candidates
+            tc::mbar_init(&S->rcempty[i], RCW);               // every re-check warp is done with the slot
+        }
         tc::fence_mbar_init();
     } else if (warp == 2) {
         tc::tmem_alloc<1>(&S->tmem_ptr, TMEM_COLS);
@@ -88,6 +185,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
     tc::tc_fence_after();
     const uint32_t tmem_base = S->tmem_ptr;
 
+    const int wg = warp >> 2;
+    if (wg == 0) {
+    reg_dec<REGS_CTRL>();
     if (warp == 3) {
         // ================================ work-item scheduler ===========================================
         // runs up to IRING items ahead of the consumers, so the ticket / metadata latency is never on the
@@ -177,7 +277,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                 }
             }
         }
-    } else if (warp >= CONV_WARP0) {
+    }
+    } else if (wg == 2 || wg == 3) {
+        reg_inc<REGS_SPLIT>();
         // ================================ row splitters ================================================
         // thread t owns row t of every staged [128 rows][32 floats] block: y = hi + lo with hi = y's top 19 bits
         // (exactly representable in tf32, so the result does not depend on how the tensor core would cut a raw fp32
@@ -235,12 +337,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                 }
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    } else if (wg == 1) {
+        reg_inc<REGS_EPI>();
         // ================================ epilogue =====================================================
         const int ew = warp - EPI_WARP0;          // == warp % 4: the TMEM lane quarter this warp may read
         const int et = threadIdx.x - EPI_WARP0 * 32;
         uint32_t tile_cnt = 0;
         unsigned long long n_fb = 0, n_cand = 0;    // lane 0: running totals for rvcr_get_stats
+        uint32_t nproc = 0;                         // items this CTA has handed to the re-check warps
         mbar_wait_warp(&S->ifull[0], 0, lane);
         Item cur = S->items[0];
         mbar_arrive_warp(&S->iempty[0], lane);
@@ -410,11 +514,46 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                     }
                 }
             }
+            // ---- hand the item to the re-check warps: its candidate lists (global memory, written above by this
+            // warp's lanes) are published by the arrive (release; the waiters acquire) ----
+            {
+                const uint32_t slot = it % RCRING, use = it / RCRING;
+                mbar_wait_warp(&S->rcempty[slot], (use & 1) ^ 1, lane);     // the re-check warps are done with the slot
+                if (ew == 0 && lane == 0) {
+                    S->rc_p0[slot] = (int)cur.p0;
+                    S->rc_cnt[slot] = cnt;
+                }
+                mbar_arrive_warp(&S->rcfull[slot], lane);
+            }
+            ++nproc;
             cur = nxt;
+        }
+        {   // stop marker after the last item of this CTA
+            const uint32_t slot = nproc % RCRING, use = nproc / RCRING;
+            mbar_wait_warp(&S->rcempty[slot], (use & 1) ^ 1, lane);
+            if (ew == 0 && lane == 0) S->rc_cnt[slot] = -1;
+            mbar_arrive_warp(&S->rcfull[slot], lane);
         }
         if (lane == 0) {
             if (n_fb) atomicAdd(&totals[0], n_fb);
             if (n_cand) atomicAdd(&totals[1], n_cand);
+        }
+    } else {
+        // ================================ exact re-check + tail ========================================
+        // Warps 16..23: as soon as the epilogue has selected an item's candidates, evaluate their canonical fp32
+        // distances, keep the top-8 by (distance, position) and (BLEND) gather / weight / blend -- while the TMA, MMA and
+        // splitter warps stream the next lists.  The candidate rows went through L2 on their way to shared memory a few
+        // microseconds earlier, so most of these reads are L2 hits instead of a second trip to HBM.
+        reg_dec<REGS_RC>();
+        const int rw = warp - RC_WARP0;
+        for (uint32_t seq = 0;; ++seq) {
+            const uint32_t slot = seq % RCRING, use = seq / RCRING;
+            mbar_wait_warp(&S->rcfull[slot], use & 1, lane);
+            const int p0 = S->rc_p0[slot], cnt = S->rc_cnt[slot];
+            if (cnt < 0) break;
+            for (int j = rw; j < cnt; j += RCW)
+                recheck_query<BLEND>((int64_t)p0 + j, q, qorder, d, vecs, ids, cand, candcnt, D, P, I, ba, lane);
+            mbar_arrive_warp(&S->rcempty[slot], lane);
         }
     }
 
@@ -425,288 +564,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
 
 }  // namespace stc
 
-// ------------------------------------------------------------------------- exact re-check ----
-
-// One warp per query (walked in list-sorted order, so neighbouring warps touch the same list): canonical fp32
-// distance of each candidate -- two lanes per candidate, lane h owns accumulators 4h..4h+3 (float4 loads),
-// sequential over the row exactly like fvec_L2sqr -- then top-8 by (distance, position).
-constexpr int RC_WARPS = 4;
-
-// BLEND: the warp that has just found a query's exact top-8 also gathers those 8 rows (it read them a moment ago:
-// L1 / L2 hits instead of a second trip to HBM), applies the 1/score^2 weights and the index_rate blend and writes
-// the output row -- rvc/infer/pipeline.py:500-506 without a separate gather kernel.
-// BLEND: 0 = search only, 1 = + fused tail in place, 2 = + fused tail + 2x upsample / protect mix into post.out2, 3 = + fused
-// tail pushed to the home rank's buffer over NVLink (separate instantiations so the default kernel's code and register
-// count stay exactly as profiled).
-// UNR: float4 loads in flight per lane in the distance loop (8 as profiled in round 1; 16 is a tuning variant, RVCR_RC_UNROLL).
-template <int BLEND, int UNR = 8>
-__global__ void __launch_bounds__(RC_WARPS * 32)
-scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qorder, const uint32_t* __restrict__ keys,
-                    uint32_t nlist, const int32_t* __restrict__ items, const int32_t* __restrict__ nitems_ptr, int item_begin,
-                    int item_end, int64_t n, int d, const float* __restrict__ vecs, const int64_t* __restrict__ ids,
-                    const int32_t* __restrict__ cand, const int32_t* __restrict__ candcnt, float* __restrict__ D,
-                    int32_t* __restrict__ P, int64_t* __restrict__ I, BlendArgs ba) {
-    extern __shared__ __align__(16) float rc_smem[];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    float* sq = rc_smem + (size_t)w * d;
-    const int nit = *nitems_ptr;
-    const int64_t first = item_begin < nit ? (int64_t)items[item_begin] : n;
-    const int64_t last = item_end < nit ? (int64_t)items[item_end] : n;
-    const int h = lane & 1;
-    const int nvec = d >> 2;
-    for (int64_t p = first + (int64_t)blockIdx.x * RC_WARPS + w; p < last; p += (int64_t)gridDim.x * RC_WARPS) {
-        if (keys[p] == nlist + 1u) continue;   // another shard's query (sorted last; forms no work item)
-        const int64_t qi = qorder[p];
-        const int nc = candcnt[qi];
-        if (nc < 0) continue;   // overflowed: the exact fallback kernel answers this query
-        float td = RVCR_FLT_MAX;
-        int tp = 0x7fffffff;
-        if (nc > 0 || BLEND) {
-            __syncwarp();
-            const float4* q4 = reinterpret_cast<const float4*>(q + qi * d);
-            for (int c = lane; c < nvec; c += 32) reinterpret_cast<float4*>(sq)[c] = q4[c];
-            __syncwarp();
-        }
-        if (nc > 0) {
-            for (int base = 0; base < nc; base += 16) {
-                const int c = base + (lane >> 1);
-                const bool have = c < nc;
-                const int pos = cand[qi * stc::CCAP + (have ? c : 0)];
-                const float4* y4 = reinterpret_cast<const float4*>(vecs + (int64_t)pos * d) + h;
-                const float4* x4 = reinterpret_cast<const float4*>(sq) + h;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll UNR
-                for (int i = 0; i < (d >> 3); ++i) {
-                    const float4 y = __ldg(y4 + 2 * i);
-                    const float4 x = x4[2 * i];
-                    const float t0 = __fsub_rn(x.x, y.x), t1 = __fsub_rn(x.y, y.y), t2 = __fsub_rn(x.z, y.z), t3 = __fsub_rn(x.w, y.w);
-                    a0 = __fmaf_rn(t0, t0, a0);
-                    a1 = __fmaf_rn(t1, t1, a1);
-                    a2 = __fmaf_rn(t2, t2, a2);
-                    a3 = __fmaf_rn(t3, t3, a3);
-                }
-                // canonical reduction ((a0+a4)+(a1+a5))+((a2+a6)+(a3+a7)); lane h holds a[4h..4h+3]
-                const float s0 = __fadd_rn(a0, __shfl_xor_sync(0xffffffffu, a0, 1));
-                const float s1 = __fadd_rn(a1, __shfl_xor_sync(0xffffffffu, a1, 1));
-                const float s2 = __fadd_rn(a2, __shfl_xor_sync(0xffffffffu, a2, 1));
-                const float s3 = __fadd_rn(a3, __shfl_xor_sync(0xffffffffu, a3, 1));
-                const float dist = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
-                top8_update(td, tp, dist, pos, have && h == 0, lane);
-            }
-        }
-        if (lane < RVCR_K) {
-            const bool pad = tp == 0x7fffffff;
-            D[qi * RVCR_K + lane] = pad ? RVCR_FLT_MAX : td;
-            P[qi * RVCR_K + lane] = pad ? -1 : tp;
-            if (I) I[qi * RVCR_K + lane] = pad ? (int64_t)-1 : ids[tp];
-        }
-        if (BLEND) {
-            float wn;
-            int spos;
-            blend_weights(td, tp, lane, ba.last_row_pos, wn, spos);
-            float wk[RVCR_K];
-            const float4* rows[RVCR_K];
-#pragma unroll
-            for (int k = 0; k < RVCR_K; ++k) {
-                wk[k] = __shfl_sync(0xffffffffu, wn, k);
-                const int pk = __shfl_sync(0xffffffffu, spos, k);
-                rows[k] = pk >= 0 ? reinterpret_cast<const float4*>(vecs + (int64_t)pk * d) : nullptr;
-            }
-            float4* o4 = BLEND == 3 ? push_row_ptr(ba.push, qi, d) : reinterpret_cast<float4*>(ba.out + qi * d);
-            for (int c = lane; c < nvec; c += 32) {
-                float4 v[RVCR_K];
-#pragma unroll
-                for (int k = 0; k < RVCR_K; ++k) v[k] = rows[k] ? __ldg(rows[k] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 f0 = reinterpret_cast<const float4*>(sq)[c];
-                const float4 o = blend_vec(v, wk, f0, ba.r32, ba.omr32);
-                if (BLEND == 2) post_store(ba.post, qi, d, c, o, f0);
-                else o4[c] = o;
-            }
-        }
-    }
-}
-
-// Brute-force exact scan of one list for the queries the tensor-core pass could not bound (rare): one CTA
-// per query, 8 lanes per row (canonical order), 32 rows per step.
-template <int BLEND>
-__global__ void __launch_bounds__(256)
-scan_exact_fallback_kernel(const float* __restrict__ q, const int32_t* __restrict__ qorder, const uint32_t* __restrict__ keys,
-                           const int32_t* __restrict__ fb_list, const int32_t* __restrict__ fb_count, uint32_t nlist, int d,
-                           const float* __restrict__ vecs, const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
-                           float* __restrict__ D, int32_t* __restrict__ P, int64_t* __restrict__ I, BlendArgs ba) {
-    extern __shared__ __align__(16) float fb_smem[];
-    float* sq = fb_smem;          // d
-    float* sd = fb_smem + d;      // 32
-    float* sw = fb_smem + d + 32; // 8 weights
-    int* sp = reinterpret_cast<int*>(fb_smem + d + 40);   // 8 gather positions
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int l8 = tid & 7, grp = tid >> 3;   // 32 groups of 8 lanes
-    const int nfb = *fb_count;
-    for (int f = blockIdx.x; f < nfb; f += gridDim.x) {
-        const int64_t p = fb_list[f];
-        const int64_t qi = qorder[p];
-        const uint32_t key = keys[p];
-        int64_t lb = 0, len = 0;
-        if (key < nlist) {
-            lb = offsets[key];
-            len = offsets[key + 1] - lb;
-        }
-        __syncthreads();
-        for (int c = tid; c < d; c += 256) sq[c] = q[qi * d + c];
-        __syncthreads();
-        float td = RVCR_FLT_MAX;
-        int tp = 0x7fffffff;
-        for (int64_t r0 = 0; r0 < len; r0 += 32) {
-            const int64_t r = r0 + grp;
-            float acc = 0.f;
-            if (r < len) {
-                const float* y = vecs + (lb + r) * d;
-                for (int i = 0; i < d; i += 8) {
-                    const float t = __fsub_rn(sq[i + l8], y[i + l8]);
-                    acc = __fmaf_rn(t, t, acc);
-                }
-            }
-            acc = reduce8_canonical(acc);
-            if (l8 == 0) sd[grp] = acc;
-            __syncthreads();
-            if (w == 0) {
-                const int64_t rr = r0 + lane;
-                top8_update(td, tp, sd[lane], (int)(lb + rr), rr < len, lane);
-            }
-            __syncthreads();
-        }
-        if (w == 0 && lane < RVCR_K) {
-            const bool pad = tp == 0x7fffffff;
-            D[qi * RVCR_K + lane] = pad ? RVCR_FLT_MAX : td;
-            P[qi * RVCR_K + lane] = pad ? -1 : tp;
-            if (I) I[qi * RVCR_K + lane] = pad ? (int64_t)-1 : ids[tp];
-        }
-        if (BLEND) {
-            if (w == 0) {
-                float wn;
-                int spos;
-                blend_weights(td, tp, lane, ba.last_row_pos, wn, spos);
-                if (lane < RVCR_K) {
-                    sw[lane] = wn;
-                    sp[lane] = spos;
-                }
-            }
-            __syncthreads();
-            float wk[RVCR_K];
-            const float4* rows[RVCR_K];
-#pragma unroll
-            for (int k = 0; k < RVCR_K; ++k) {
-                wk[k] = sw[k];
-                rows[k] = sp[k] >= 0 ? reinterpret_cast<const float4*>(vecs + (int64_t)sp[k] * d) : nullptr;
-            }
-            float4* o4 = BLEND == 3 ? push_row_ptr(ba.push, qi, d) : reinterpret_cast<float4*>(ba.out + qi * d);
-            for (int c = tid; c < (d >> 2); c += 256) {
-                float4 v[RVCR_K];
-#pragma unroll
-                for (int k = 0; k < RVCR_K; ++k) v[k] = rows[k] ? __ldg(rows[k] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 f0 = reinterpret_cast<const float4*>(sq)[c];
-                const float4 o = blend_vec(v, wk, f0, ba.r32, ba.omr32);
-                if (BLEND == 2) post_store(ba.post, qi, d, c, o, f0);
-                else o4[c] = o;
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------- row norms ------
-
-// one warp per stored row: ||y||^2 (fp32) and the running maximum (as uint bits; non-negative floats order as uints)
-__global__ void row_norm_kernel(const float* __restrict__ vecs, int64_t nrows, int d, float* __restrict__ norm2,
-                                unsigned int* __restrict__ max_bits) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (r >= nrows) return;
-    const float4* y4 = reinterpret_cast<const float4*>(vecs + r * d);
-    float s = 0.f;
-    for (int c = lane; c < (d >> 2); c += 32) {
-        const float4 v = __ldg(y4 + c);
-        s = fmaf(v.x, v.x, s);
-        s = fmaf(v.y, v.y, s);
-        s = fmaf(v.z, v.z, s);
-        s = fmaf(v.w, v.w, s);
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) {
-        norm2[r] = s;
-        if (s > 0.f && s < __int_as_float(0x7f800000)) atomicMax(max_bits, __float_as_uint(s));
-    }
-}
-
-// ------------------------------------------------------------------------------ host side ----
-
-int scan_tc_invalidate(rvcr_index* h) {
-    h->row_norm_valid = false;
-    h->scan_tmap_valid = false;
-    return RVCR_OK;
-}
-
-static int ensure_row_norms(rvcr_index* h, cudaStream_t s) {
-    if (h->row_norm_valid) return RVCR_OK;
-    RVCR_TRY(h->row_norm.reserve((size_t)(h->nstored > 0 ? h->nstored : 1) * 4));
-    unsigned int* mx = h->ws_misc.as<unsigned int>() + 13;
-    RVCR_CUDA(cudaMemsetAsync(mx, 0, 4, s));
-    if (h->nstored > 0) {
-        const int64_t thr = h->nstored * 32;
-        row_norm_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(h->vecs, h->nstored, h->d, h->row_norm.as<float>(), mx);
-        RVCR_CHECK_LAUNCH();
-        count_launch(h);
-    }
-    unsigned int bits = 0;
-    RVCR_CUDA(cudaMemcpyAsync(&bits, mx, 4, cudaMemcpyDeviceToHost, s));
-    RVCR_CUDA(cudaStreamSynchronize(s));
-    float m2;
-    memcpy(&m2, &bits, 4);
-    h->row_norm_max = sqrtf(m2);
-    h->row_norm_valid = true;
-    return RVCR_OK;
-}
-
-static int ensure_scan_tmaps(rvcr_index* h) {
-    if (h->scan_tmap_valid && h->scan_tmap_base == (const void*)h->vecs && h->scan_tmap_rows == h->nstored) return RVCR_OK;
-    tc::EncodeTiledFn fn = tc::get_encode_fn();
-    if (!fn) {
-        set_error("cuTensorMapEncodeTiled is not available from the driver");
-        return RVCR_ERR_CUDA;
-    }
-    static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
-    for (int i = 0; i < 4; ++i) {
-        cuuint64_t dims[2] = {(cuuint64_t)h->d, (cuuint64_t)h->nstored};
-        cuuint64_t strides[1] = {(cuuint64_t)h->d * 4};
-        cuuint32_t box[2] = {(cuuint32_t)stc::KB, (cuuint32_t)(32 * (i + 1))};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = fn(reinterpret_cast<CUtensorMap*>(h->scan_tmaps[i]), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->vecs, dims, strides,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("cuTensorMapEncodeTiled failed (%d) for the %lld x %d list storage", (int)r, (long long)h->nstored, h->d);
-            return RVCR_ERR_CUDA;
-        }
-    }
-    h->scan_tmap_valid = true;
-    h->scan_tmap_base = h->vecs;
-    h->scan_tmap_rows = h->nstored;
-    return RVCR_OK;
-}
-
-bool scan_tc_supported(const rvcr_index* h) { return h->d % stc::KB == 0 && h->d >= stc::KB && h->d <= 1024 && h->nstored > 0; }
-
-// Same contract as scan_topk_range (scan_topk.cu); requires group_queries() on the same stream.
-int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, int64_t* I, int item_begin, int item_end,
-                  int ticket_slot, bool fill, cudaStream_t s) {
-    if (h->nstored >= (1ll << 31)) {
-        set_error("more than 2^31 stored vectors per shard is unsupported");
-        return RVCR_ERR_UNSUPPORTED;
-    }
-    RVCR_TRY(ensure_row_norms(h, s));
-    RVCR_TRY(ensure_scan_tmaps(h));
+// Launch the fused kernel for work items [item_begin, item_end); called by scan_tc_range (scan_tc.cu) in place of the
+// streaming kernel + scan_recheck_kernel when option scan_impl is 6.  Row norms, tensor maps and scratch are the caller's.
+int launch_scan_tc_fused(rvcr_index* h, const CUtensorMap* tm, const float* q, int64_t n, float rel, float absm, int item_begin,
+                         int item_end, int ticket_slot, int32_t* fb_count, float* D, int32_t* P, int64_t* I,
+                         const BlendArgs& ba, int bmode, cudaStream_t s) {
     const int d = h->d, nkb = d / stc::KB;
-    const size_t fixed = 2 * (size_t)nkb * stc::QKB_BYTES + stc::SV_BYTES + sizeof(stc::Smem) + 1024;
+    const size_t fixed = 2 * (size_t)nkb * stc::QKB_BYTES + stc::SV_BYTES + sizeof(stc::SmemF) + 1024;
     int nstage = (int)((226 * 1024 - fixed) / stc::STAGE_BYTES);
     if (nstage > 8) nstage = 8;
     if (nstage < 2) {
@@ -714,76 +578,24 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
         return RVCR_ERR_UNSUPPORTED;
     }
     const size_t smem = fixed + (size_t)nstage * stc::STAGE_BYTES;
-    static SmemOptIn opt_in;
-    RVCR_TRY(opt_in.ensure(stc::scan_tc_kernel, smem, h->device));
-    RVCR_TRY(h->ws_cand.reserve((size_t)n * stc::CCAP * 4));
-    RVCR_TRY(h->ws_candcnt.reserve((size_t)n * 4));
-    RVCR_TRY(h->ws_fb.reserve((size_t)n * 4 + 64));
-    RVCR_TRY(h->ws_cstage.reserve((size_t)h->num_sms * stc::QT * stc::SCAP * sizeof(float2)));
-    int32_t* fb_count = h->ws_misc.as<int32_t>() + 14;
-    RVCR_CUDA(cudaMemsetAsync(fb_count, 0, 4, s));
-    if (fill) {
-        RVCR_TRY(fill_pad(D, P, I, n * RVCR_K, s));
-    }
-    // relative error of one accumulated dot product beyond the dropped query low part: truncation of the row
-    // low part to tf32 (2^-20) and fp32 accumulation of 2 d products in the tensor core (d 2^-21)
-    const float rel = 1.f / 1048576.f + (float)d / 2097152.f;
-    const float absm = 1.f / 524288.f;
-    int grid = h->num_sms;
-    const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(h->scan_tmaps);
-    const bool fused_recheck = h->opt.scan_impl == 6;   // experimental: re-check + tail as a warp role of the scan kernel
-    if (fused_recheck) {
-        const bool blend_f = h->fuse.active;
-        BlendArgs baf{h->fuse.out, h->last_row_pos, h->fuse.r32, h->fuse.omr32, h->fuse.post, h->fuse.push};
-        const int bmode_f = !blend_f ? 0 : (baf.post.out2 ? 2 : (baf.push.bases ? 3 : 1));
-        RVCR_TRY(launch_scan_tc_fused(h, tm, q, n, rel, absm, item_begin, item_end, ticket_slot, fb_count, D, P, I, baf, bmode_f, s));
-    } else
-    stc::scan_tc_kernel<<<grid, stc::THREADS, smem, s>>>(
-        tm[0], tm[1], tm[2], tm[3], q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), h->ws_items.as<int32_t>(),
-        h->ws_misc.as<int32_t>(), h->ws_misc.as<int32_t>() + ticket_slot, h->offsets, h->row_norm.as<float>(), (uint32_t)h->nlist, n, d,
-        nstage, h->row_norm_max, rel, absm, item_begin, item_end, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
-        h->ws_fb.as<int32_t>(), fb_count, reinterpret_cast<unsigned long long*>(h->ws_misc.as<int32_t>() + 48),
-        h->ws_cstage.as<float2>(), getenv("RVCR_STC_FLAGS") ? atoi(getenv("RVCR_STC_FLAGS")) : 0);
+    static SmemOptIn opt_in[4];
+#define RVCR_LAUNCH_FUSED(B)                                                                                                     \
+    do {                                                                                                                         \
+        RVCR_TRY(opt_in[B].ensure(stc::scan_tc_fused_kernel<B>, smem, h->device));                                               \
+        stc::scan_tc_fused_kernel<B><<<h->num_sms, stc::FTHREADS, smem, s>>>(                                                    \
+            tm[0], tm[1], tm[2], tm[3], q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), h->ws_items.as<int32_t>(),     \
+            h->ws_misc.as<int32_t>(), h->ws_misc.as<int32_t>() + ticket_slot, h->offsets, h->row_norm.as<float>(),               \
+            (uint32_t)h->nlist, n, d, nstage, h->row_norm_max, rel, absm, item_begin, item_end, h->ws_cand.as<int32_t>(),        \
+            h->ws_candcnt.as<int32_t>(), h->ws_fb.as<int32_t>(), fb_count,                                                       \
+            reinterpret_cast<unsigned long long*>(h->ws_misc.as<int32_t>() + 48), h->ws_cstage.as<float2>(),                    \
+            getenv("RVCR_STC_FLAGS") ? atoi(getenv("RVCR_STC_FLAGS")) : 0, h->vecs, h->ids, D, P, I, ba);                        \
+    } while (0)
+    if (bmode == 0) RVCR_LAUNCH_FUSED(0);
+    else if (bmode == 1) RVCR_LAUNCH_FUSED(1);
+    else if (bmode == 2) RVCR_LAUNCH_FUSED(2);
+    else RVCR_LAUNCH_FUSED(3);
+#undef RVCR_LAUNCH_FUSED
     RVCR_CHECK_LAUNCH();
-    // fused tail (search_device sets h->fuse for rvcr_retrieve_blend*): the re-check / fallback kernels also blend
-    const bool blend = h->fuse.active;
-    BlendArgs ba{h->fuse.out, h->last_row_pos, h->fuse.r32, h->fuse.omr32, h->fuse.post, h->fuse.push};
-    const int bmode = !blend ? 0 : (ba.post.out2 ? 2 : (ba.push.bases ? 3 : 1));
-    if (!fused_recheck) {
-        PhaseTimer pt(h, RVCR_PHASE_SCAN_RECHECK, s);
-        // One warp per query, 32 warps per SM.  A variant that staged the candidate rows in shared memory with
-        // cp.async.bulk (so the fused gather never left the SM) was measured slower (r01: 14.2 vs 8.1 ms at C5 -- with
-        // 52 KB per query only 4 warps fit per SM, and the per-query chain header -> copies -> distances -> top-8 ->
-        // blend is serial inside a warp) and was removed.
-        {
-            const size_t rsm = (size_t)RC_WARPS * d * 4;
-            int per_sm = 10;   // = the register-limited occupancy (48 regs x 128 threads); measured r01 C5: 6 -> 16.5, 8 -> 14.6, 10 -> 12.5 ms
-            if (const char* e = getenv("RVCR_RC_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // tuning knob
-            int64_t rgrid = (int64_t)h->num_sms * per_sm;
-            if (rgrid * RC_WARPS > n) rgrid = (n + RC_WARPS - 1) / RC_WARPS;
-            auto kern = bmode == 0 ? scan_recheck_kernel<0> : bmode == 1 ? scan_recheck_kernel<1> : bmode == 2 ? scan_recheck_kernel<2> : scan_recheck_kernel<3>;
-            if (const char* e = getenv("RVCR_RC_UNROLL"))   // tuning knob: fewer CTAs per SM (RVCR_RC_CTAS) with more loads in flight per lane
-                if (atoi(e) == 16)
-                    kern = bmode == 0 ? scan_recheck_kernel<0, 16> : bmode == 1 ? scan_recheck_kernel<1, 16> : bmode == 2 ? scan_recheck_kernel<2, 16> : scan_recheck_kernel<3, 16>;
-            kern<<<(unsigned)rgrid, RC_WARPS * 32, rsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), (uint32_t)h->nlist,
-                                                             h->ws_items.as<int32_t>(), h->ws_misc.as<int32_t>(), item_begin, item_end, n,
-                                                             d, h->vecs, h->ids, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
-                                                             D, P, I, ba);
-        }
-        RVCR_CHECK_LAUNCH();
-    }
-    {
-        PhaseTimer pt(h, RVCR_PHASE_SCAN_FALLBACK, s);
-        const size_t fsm = (size_t)(d + 48) * 4;
-        auto kern = bmode == 0 ? scan_exact_fallback_kernel<0> : bmode == 1 ? scan_exact_fallback_kernel<1> : bmode == 2 ? scan_exact_fallback_kernel<2> : scan_exact_fallback_kernel<3>;
-        kern<<<h->num_sms * 2, 256, fsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), h->ws_fb.as<int32_t>(), fb_count,
-                                              (uint32_t)h->nlist, d, h->vecs, h->ids, h->offsets, D, P, I, ba);
-        RVCR_CHECK_LAUNCH();
-    }
-    if (blend) h->fuse.done = true;
-    // running total of fallback queries (read back lazily by rvcr_get_stats)
-    h->scan_fb_dirty = true;
-    count_launch(h, (fill ? 4 : 3) - (fused_recheck ? 1 : 0));
     return RVCR_OK;
 }
 

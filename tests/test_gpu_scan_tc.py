@@ -2,12 +2,17 @@
 scan (scan_impl = 4).  The tensor-core pass only nominates candidates; the re-check evaluates the canonical
 fp32 distance, so ids AND distances must be bit-identical -- including ties, duplicates, short lists and
 the overflow path that falls back to the brute-force exact kernel."""
+import os
 from importlib import import_module
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+# RVCR_TEST_SCAN_IMPL=6 runs this whole file against the experimental fused scan + re-check kernel (csrc/scan_tc_fused.cu),
+# which must give the same bits; the default suite tests the shipped tensor-core scan (5).
+TC_IMPL = int(os.environ.get("RVCR_TEST_SCAN_IMPL", "5"))
 
 
 def _build(rvcr, x, cent):
@@ -17,7 +22,7 @@ def _build(rvcr, x, cent):
     for i in range(0, len(x), 65536):
         index.add(x[i:i + 65536])
     assert index.get_option("scan_impl") == 0            # library default: auto (exact FFMA scan below 1 Ki queries)
-    index.set_option("scan_impl", 5)                     # this file tests the tensor-core scan at every size
+    index.set_option("scan_impl", TC_IMPL)               # this file tests the tensor-core scan at every size
     return index
 
 
@@ -32,7 +37,7 @@ def test_scan_tc_matches_oracle_and_exact_scan(rvcr, oracle):
     a_q, _ = oracle.coarse_assign(pr.q, pr.centroids)
     Do, Io = oracle.scan_topk(pr.q, a_q, off, vecs, ids)
     s0 = index.stats()
-    assert index.get_option("scan_impl") == 5
+    assert index.get_option("scan_impl") == TC_IMPL
     D5, I5 = index.search(pr.q, k=8)
     s1 = index.stats()
     assert np.array_equal(I5, Io) and np.array_equal(D5, Do)
