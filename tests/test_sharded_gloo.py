@@ -151,10 +151,11 @@ def _peer_worker(rank, world, port, tmp, buffers):
     open(os.path.join(tmp, f"peer_ok{rank}"), "w").write("ok")
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 8])
 def test_peer_pull_push_step_on_gloo(world, tmp_path, oracle):
-    """The peer-memory step (owner pulls rows from the home buffers, blends, pushes them back) == single index."""
-    buffers = [torch.zeros((128, 64), dtype=torch.float32).share_memory_() for _ in range(world)]
+    """The peer-memory step (owner pulls rows from the home buffers, blends, pushes them back) == single index.
+    world 8 = the ranks of one B200 box (48 lists over 8 owners: some shards own very few lists)."""
+    buffers = [torch.zeros((256, 64), dtype=torch.float32).share_memory_() for _ in range(world)]
     mp.spawn(_peer_worker, args=(world, _free_port(), str(tmp_path), buffers), nprocs=world, join=True)
     assert all((tmp_path / f"peer_ok{r}").exists() for r in range(world))
 
