@@ -321,6 +321,7 @@ void rvcr_index_free(rvcr_index* h) {
         if (h->cent) cudaFree(h->cent);
         if (h->cent_bf16) cudaFree(h->cent_bf16);
         if (h->cent_norm) cudaFree(h->cent_norm);
+        if (h->cent_f8) cudaFree(h->cent_f8);
         if (h->vecs) cudaFree(h->vecs);
         if (h->ids) cudaFree(h->ids);
         if (h->offsets) cudaFree(h->offsets);
@@ -328,7 +329,7 @@ void rvcr_index_free(rvcr_index* h) {
         if (h->stage_assign) cudaFree(h->stage_assign);
         DevBuf* bufs[] = {&h->ws_assign, &h->ws_keys, &h->ws_vals, &h->ws_keys2, &h->ws_vals2, &h->ws_cub, &h->ws_items,
                           &h->ws_flags, &h->ws_misc, &h->ws_D, &h->ws_P, &h->ws_I, &h->ws_best, &h->ws_q, &h->ws_tc0,
-                          &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_stage, &h->row_norm, &h->ws_cand, &h->ws_candcnt,
+                          &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_tc4, &h->ws_stage, &h->row_norm, &h->ws_cand, &h->ws_candcnt,
                           &h->ws_fb, &h->ws_cstage};
         for (DevBuf* b : bufs) b->release();
         if (h->last_done) cudaEventDestroy(h->last_done);
@@ -904,7 +905,7 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
     if (!h || !key) return RVCR_ERR_INVALID;
     std::lock_guard<std::mutex> lock(h->mu);
     if (!strcmp(key, "coarse_mode")) {
-        if (value < 0 || value > 3) return RVCR_ERR_INVALID;
+        if (value < 0 || value > 4) return RVCR_ERR_INVALID;   // 4: experimental e4m3 operands, never chosen by auto
         h->opt.coarse_mode = value;
     } else if (!strcmp(key, "profile")) {
         h->opt.profile = value ? 1 : 0;
@@ -1010,7 +1011,7 @@ int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t s
     float *topv, *qnorm;
     int* topj;
     int nsplit = 0;
-    RVCR_TRY(coarse_tc_top8(h, q_dev, n, split ? 1 : 0, cluster, &topv, &topj, &nsplit, &qnorm, s));
+    RVCR_TRY(coarse_tc_top8(h, q_dev, n, split == 2 ? 2 : (split ? 1 : 0), cluster, &topv, &topj, &nsplit, &qnorm, s));   // 2: e4m3
     const int pairs = nsplit * 8;
     *pairs_out = pairs;
     if (pairs > cap_pairs) {

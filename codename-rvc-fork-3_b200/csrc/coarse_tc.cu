@@ -28,6 +28,7 @@
 //            per row in registers; overlaps the next tile's MMAs
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -85,12 +86,18 @@ struct Cfg {
 
 // grid = persistent CTAs (multiple of CLUSTER); work item = (m-block of 128*CLUSTER queries, split
 // of the centroid tiles); item i is taken by cluster (i mod nclusters).
-template <int CLUSTER, int NRES, int SB, int SA, int P>
+//
+// F8 = 1 (coarse_mode 4, experimental): e4m3 operands (kind::f8f6f4).  A 128-byte k-block then holds 128 elements
+// instead of 64, every tile / descriptor / byte count stays as it is, the instruction descriptor and the MMA kind
+// change, and the epilogue multiplies the accumulator by the per-query factor qk[row] = -2 / (s_q(row) s_c) that undoes
+// the power-of-two operand scales (bf16: the constant -2).
+template <int CLUSTER, int NRES, int SB, int SA, int P, int F8 = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const float* __restrict__ cn, int num_mblocks, int num_ntiles, int nsplit, int tiles_per_split,
-                 int num_kblocks, float* __restrict__ topv, int* __restrict__ topj) {
+                 int num_kblocks, float* __restrict__ topv, int* __restrict__ topj, const float* __restrict__ qk) {
     using C = Cfg<CLUSTER, NRES, SB, SA, P>;
+    constexpr int KE = F8 ? 2 * BLOCK_K : BLOCK_K;   // elements per 128-byte k-block (TMA coordinates are in elements)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sAres = smem;                               // NRES resident A k-blocks
@@ -165,7 +172,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     int nres = 0;
                     for (int kb = 0; kb < num_kblocks; ++kb)
                         if (!is_streamed(kb)) {
-                            tma_load_2d_a<CLUSTER>(&tmap_a, ares_full_addr, sAres_addr + (kb - kb / P) * C::A_BYTES, kb * BLOCK_K, m0);
+                            tma_load_2d_a<CLUSTER>(&tmap_a, ares_full_addr, sAres_addr + (kb - kb / P) * C::A_BYTES, kb * KE, m0);
                             ++nres;
                         }
                     if (leader) mbar_arrive_expect_tx_addr(ares_full_addr, (uint32_t)nres * C::A_BYTES * CLUSTER);
@@ -182,8 +189,8 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (elect_one()) {
                         const uint32_t fb = full_addr + stage * 8;
                         const uint32_t aslot = NRES > 0 ? astage : stage;
-                        if (streamed) tma_load_2d_a<CLUSTER>(&tmap_a, fb, sA_addr + aslot * C::A_BYTES, kb * BLOCK_K, m0);
-                        tma_load_2d_a<CLUSTER>(&tmap_b, fb, sB_addr + stage * C::B_BYTES, kb * BLOCK_K, n0);
+                        if (streamed) tma_load_2d_a<CLUSTER>(&tmap_a, fb, sA_addr + aslot * C::A_BYTES, kb * KE, m0);
+                        tma_load_2d_a<CLUSTER>(&tmap_b, fb, sB_addr + stage * C::B_BYTES, kb * KE, n0);
                         if (leader) mbar_arrive_expect_tx_addr(fb, (uint32_t)(C::B_BYTES + (streamed ? C::A_BYTES : 0)) * CLUSTER);
                         else mbar_arrive_cluster_addr(fb, 0);
                     }
@@ -198,7 +205,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp == 1) {
         // ================================ MMA issuer ===================================
         if (leader) {
-            constexpr uint32_t idesc = make_idesc(C::UMMA_M, BLOCK_N);
+            constexpr uint32_t idesc = F8 ? make_idesc_f8(C::UMMA_M, BLOCK_N) : make_idesc(C::UMMA_M, BLOCK_N);
             const uint32_t sAres_addr = tc::warp_uniform(smem_u32(sAres));
             const uint32_t sA_addr = tc::warp_uniform(smem_u32(sA)), sB_addr = tc::warp_uniform(smem_u32(sB));
             const uint32_t empty_addr = tc::warp_uniform(smem_u32(empty_bar)), tfull_addr = tc::warp_uniform(smem_u32(tmem_full_bar));
@@ -229,7 +236,11 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte units
+                                // advance 16 bf16 (32 e4m3) = 32 B inside the 128 B swizzle row: +2 in 16-byte units
+                                if constexpr (F8)
+                                    umma_f8<CLUSTER>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                                     (kb > 0 || k > 0) ? 1u : 0u);
+                                else
                                 umma_bf16<CLUSTER>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                                    (kb > 0 || k > 0) ? 1u : 0u);
                             }
@@ -263,6 +274,8 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int tj[TOPT];
 #pragma unroll
             for (int i = 0; i < TOPT; ++i) { tv[i] = __int_as_float(0x7f800000); tj[i] = -1; }
+            float kr = -2.f;   // v = ||c||^2 + kr * acc
+            if constexpr (F8) kr = __ldg(qk + (int64_t)mb * (BLOCK_M * CLUSTER) + (int64_t)cta_rank * BLOCK_M + row);
             for (int t = t0; t < t1; ++t, ++tile_cnt) {
                 const uint32_t as = tile_cnt & 1, aphase = (tile_cnt >> 1) & 1;
                 mbar_wait_warp(&tmem_full_bar[as], aphase, lane);
@@ -280,10 +293,10 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     tmem_ld_wait();
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
-                        const float x0 = fmaf(-2.f, __uint_as_float(r[4 * g + 0]), nn[g].x);
-                        const float x1 = fmaf(-2.f, __uint_as_float(r[4 * g + 1]), nn[g].y);
-                        const float x2 = fmaf(-2.f, __uint_as_float(r[4 * g + 2]), nn[g].z);
-                        const float x3 = fmaf(-2.f, __uint_as_float(r[4 * g + 3]), nn[g].w);
+                        const float x0 = fmaf(F8 ? kr : -2.f, __uint_as_float(r[4 * g + 0]), nn[g].x);
+                        const float x1 = fmaf(F8 ? kr : -2.f, __uint_as_float(r[4 * g + 1]), nn[g].y);
+                        const float x2 = fmaf(F8 ? kr : -2.f, __uint_as_float(r[4 * g + 2]), nn[g].z);
+                        const float x3 = fmaf(F8 ? kr : -2.f, __uint_as_float(r[4 * g + 3]), nn[g].w);
                         const float m = fminf(fminf(x0, x1), fminf(x2, x3));
                         if (m < tv[TOPT - 1]) {
                             const int jb = n0 + c * 32 + 4 * g;
@@ -354,6 +367,90 @@ __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int6
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0 && norm2) norm2[r] = s;
+}
+
+// ---- e4m3 operands (coarse_mode 4) ----
+// Power-of-two scale s with 128 <= max|x| * s < 256 (e4m3 tops out at 448; a power of two keeps x * s exact), or 0 when no
+// such fp32 scale exists / the row is all zero or not finite (the caller then routes the row to the exact kernel).
+__host__ __device__ inline float f8_scale_for(float mx) {
+    if (!(mx > 0.f) || !(mx < INFINITY)) return 0.f;
+    int e;
+    frexpf(mx, &e);   // mx = m * 2^e, 0.5 <= m < 1
+    e = 8 - e;
+    if (e > 100 || e < -100) return 0.f;
+    return ldexpf(1.f, e);
+}
+
+// max |x| over an array; bit 31 of flags[1] is raised when a value is NaN / inf
+__global__ void tc_maxabs_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__ flags) {
+    float m = 0.f;
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float a = fabsf(x[i]);
+        if (a < INFINITY) m = fmaxf(m, a);
+        else bad = true;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (m > 0.f) atomicMax(&flags[0], __float_as_uint(m));
+        if (bad) atomicOr(&flags[1], 0x80000000u);
+    }
+}
+
+// one warp per row: fp32 row -> e4m3 row scaled by a power of two (`fixed_scale` for the centroids -- one scale for the
+// whole set, so the epilogue needs no per-column factor -- or the row's own scale for a query), the row's squared norm, and
+// for queries kfac[r] = -2 / (s_q(r) * other_scale), the factor that turns the scaled accumulator into -2 <q, c>.  A query
+// row that cannot be scaled (all zero, NaN / inf, exponent out of range) gets kfac = NaN: every v is NaN, no candidate is
+// kept, and the re-check hands the query to the exact kernel.
+__global__ void tc_prep_rows_f8_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d, float fixed_scale,
+                                       float other_scale, uint8_t* __restrict__ out, float* __restrict__ norm2,
+                                       float* __restrict__ kfac, float pad_norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_pad) return;
+    uint8_t* o = out + r * d;
+    if (r >= n) {
+        for (int c = lane; c < d; c += 32) o[c] = 0;
+        if (lane == 0) {
+            if (norm2) norm2[r] = pad_norm;
+            if (kfac) kfac[r] = -2.f;
+        }
+        return;
+    }
+    const float* xr = x + r * d;
+    float s = 0.f, mx = 0.f;
+    bool bad = false;
+    for (int c = lane; c < d; c += 32) {
+        const float v = xr[c];
+        s = fmaf(v, v, s);
+        const float a = fabsf(v);
+        if (a < INFINITY) mx = fmaxf(mx, a);
+        else bad = true;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    float scale = fixed_scale > 0.f ? fixed_scale : f8_scale_for(mx);
+    if (!(scale > 0.f)) {
+        bad = true;
+        scale = 1.f;
+    }
+    for (int c = lane; c < d; c += 32)
+        o[c] = (uint8_t)__nv_cvt_float_to_fp8(xr[c] * scale, __NV_SATFINITE, __NV_E4M3);
+    if (lane == 0) {
+        if (norm2) norm2[r] = s;
+        if (kfac) {
+            const double p = (double)scale * (double)other_scale;
+            float k = (float)(-2.0 / p);
+            if (bad || !(fabsf(k) >= 1.17549435e-38f) || !(fabsf(k) < INFINITY)) k = __int_as_float(0x7fc00000);
+            kfac[r] = k;
+        }
+    }
 }
 
 __global__ void tc_max_kernel(const float* __restrict__ v, int64_t n, unsigned int* __restrict__ out_bits) {
@@ -513,6 +610,27 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int kdim, int box_
     return RVCR_OK;
 }
 
+// row-major e4m3 matrix [rows][kdim] (one byte per element) -> tensor map with a [box_rows][128] box, 128B swizzle
+int make_tmap_u8(CUtensorMap* m, const void* base, int64_t rows, int kdim, int box_rows) {
+    tc::EncodeTiledFn fn = tc::get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return RVCR_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kdim};
+    cuuint32_t box[2] = {(cuuint32_t)(2 * tc::BLOCK_K), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for a %lld x %d e4m3 matrix", (int)r, (long long)rows, kdim);
+        return RVCR_ERR_CUDA;
+    }
+    return RVCR_OK;
+}
+
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 // centroid operands are built once per (centroid set, split mode)
@@ -549,12 +667,40 @@ int ensure_centroid_operands(rvcr_index* h, int split, cudaStream_t s) {
     return RVCR_OK;
 }
 
-template <int CLUSTER, int NRES, int SB, int SA, int P>
+// e4m3 centroid operand (coarse_mode 4): one power-of-two scale for the whole set; needs the norms of the bf16 build
+int ensure_centroid_operands_f8(rvcr_index* h, cudaStream_t s) {
+    RVCR_TRY(ensure_centroid_operands(h, 0, s));   // ||c||^2 (+inf for pad rows) and max ||c||
+    if (h->cent_f8) return RVCR_OK;
+    unsigned int* fl = h->ws_misc.as<unsigned int>() + 56;   // [56] max |c| bits, [57] non-finite flag
+    RVCR_CUDA(cudaMemsetAsync(fl, 0, 8, s));
+    tc_maxabs_kernel<<<h->num_sms * 8, 256, 0, s>>>(h->cent, h->nlist * (int64_t)h->d, fl);
+    RVCR_CHECK_LAUNCH();
+    unsigned int got[2] = {0, 0};
+    RVCR_CUDA(cudaMemcpyAsync(got, fl, 8, cudaMemcpyDeviceToHost, s));
+    RVCR_CUDA(cudaStreamSynchronize(s));
+    float mx;
+    memcpy(&mx, &got[0], 4);
+    const float sc = f8_scale_for(mx);
+    if (got[1] || !(sc > 0.f)) {
+        set_error("coarse_mode 4 (e4m3 operands) needs finite, non-zero centroids; use coarse_mode 2");
+        return RVCR_ERR_UNSUPPORTED;
+    }
+    RVCR_CUDA(cudaMalloc(&h->cent_f8, (size_t)h->cent_pad * h->d));
+    const int64_t thr = h->cent_pad * 32;
+    tc_prep_rows_f8_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(h->cent, h->nlist, h->cent_pad, h->d, sc, 1.f,
+                                                                          reinterpret_cast<uint8_t*>(h->cent_f8), nullptr, nullptr, 0.f);
+    RVCR_CHECK_LAUNCH();
+    h->cent_f8_scale = sc;
+    count_launch(h, 2);
+    return RVCR_OK;
+}
+
+template <int CLUSTER, int NRES, int SB, int SA, int P, int F8 = 0>
 int launch_tc(rvcr_index* h, const CUtensorMap& ta, const CUtensorMap& tb, int num_mblocks, int num_ntiles, int nsplit,
-              int tps, int nkb, float* topv, int* topj, cudaStream_t s) {
+              int tps, int nkb, float* topv, int* topj, cudaStream_t s, const float* qk = nullptr) {
     using C = tc::Cfg<CLUSTER, NRES, SB, SA, P>;
     static SmemOptIn opt_in;   // one per template instantiation
-    RVCR_TRY(opt_in.ensure(tc::coarse_tc_kernel<CLUSTER, NRES, SB, SA, P>, (size_t)C::SMEM_BYTES, h->device));
+    RVCR_TRY(opt_in.ensure(tc::coarse_tc_kernel<CLUSTER, NRES, SB, SA, P, F8>, (size_t)C::SMEM_BYTES, h->device));
     const int nitems = num_mblocks * nsplit;
     int nclusters = h->num_sms / CLUSTER;
     if (nclusters > nitems) nclusters = nitems;
@@ -570,8 +716,8 @@ int launch_tc(rvcr_index* h, const CUtensorMap& ta, const CUtensorMap& tb, int n
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    RVCR_CUDA(cudaLaunchKernelEx(&cfg, tc::coarse_tc_kernel<CLUSTER, NRES, SB, SA, P>, ta, tb, (const float*)h->cent_norm,
-                                 num_mblocks, num_ntiles, nsplit, tps, nkb, topv, topj));
+    RVCR_CUDA(cudaLaunchKernelEx(&cfg, tc::coarse_tc_kernel<CLUSTER, NRES, SB, SA, P, F8>, ta, tb, (const float*)h->cent_norm,
+                                 num_mblocks, num_ntiles, nsplit, tps, nkb, topv, topj, qk));
     return RVCR_OK;
 }
 
@@ -582,8 +728,11 @@ bool coarse_tc_available() { return true; }
 int coarse_tc_invalidate(rvcr_index* h) {
     if (h->cent_bf16) cudaFree(h->cent_bf16);
     if (h->cent_norm) cudaFree(h->cent_norm);
+    if (h->cent_f8) cudaFree(h->cent_f8);
     h->cent_bf16 = nullptr;
     h->cent_norm = nullptr;
+    h->cent_f8 = nullptr;
+    h->cent_f8_scale = 0.f;
     h->cent_split = -1;
     return RVCR_OK;
 }
@@ -592,21 +741,38 @@ int coarse_tc_invalidate(rvcr_index* h) {
 // Outputs (device, owned by the handle scratch): topv/topj [n_pad][nsplit][8]; returns nsplit.
 int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int cluster, float** topv_out, int** topj_out,
                    int* nsplit_out, float** qnorm_out, cudaStream_t s) {
-    if (h->d % tc::BLOCK_K != 0) {
-        set_error("d=%d unsupported by the tcgen05 path (must be a multiple of %d)", h->d, tc::BLOCK_K);
+    // split: 0 = bf16, 1 = bf16 3-way split along K, 2 = e4m3 operands (coarse_mode 4)
+    const bool f8 = split == 2;
+    const int kelems = f8 ? 2 * tc::BLOCK_K : tc::BLOCK_K;   // elements per 128-byte k-block
+    if (h->d % kelems != 0) {
+        set_error("d=%d unsupported by the tcgen05 path (must be a multiple of %d)", h->d, kelems);
         return RVCR_ERR_UNSUPPORTED;
     }
-    const int kdim = split ? 3 * h->d : h->d;
+    const int kdim = split == 1 ? 3 * h->d : h->d;
     const int mblk = tc::BLOCK_M * cluster;
     const int64_t n_pad = round_up(n, mblk);
     {
         PhaseTimer pt(h, RVCR_PHASE_COARSE_PREP, s);
+        const int64_t thr = n_pad * 32;
+        if (f8) {
+            if (h->d > 1024) {
+                set_error("coarse_mode 4: d=%d above 1024 (the e4m3 error bound is derived for d <= 1024)", h->d);
+                return RVCR_ERR_UNSUPPORTED;
+            }
+            RVCR_TRY(ensure_centroid_operands_f8(h, s));
+            RVCR_TRY(h->ws_tc0.reserve((size_t)n_pad * kdim));   // e4m3 queries, each row with its own power-of-two scale
+            RVCR_TRY(h->ws_tc1.reserve((size_t)n_pad * 4));      // ||q||^2
+            RVCR_TRY(h->ws_tc4.reserve((size_t)n_pad * 4));      // -2 / (s_q s_c) per query
+            tc_prep_rows_f8_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, n_pad, h->d, 0.f, h->cent_f8_scale,
+                                                                                  h->ws_tc0.as<uint8_t>(), h->ws_tc1.as<float>(),
+                                                                                  h->ws_tc4.as<float>(), 0.f);
+        } else {
         RVCR_TRY(ensure_centroid_operands(h, split, s));
         RVCR_TRY(h->ws_tc0.reserve((size_t)n_pad * kdim * 2));   // bf16 queries
         RVCR_TRY(h->ws_tc1.reserve((size_t)n_pad * 4));          // ||q||^2
-        const int64_t thr = n_pad * 32;
         tc_prep_rows_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, n_pad, h->d, split, 0,
                                                                            h->ws_tc0.as<__nv_bfloat16>(), h->ws_tc1.as<float>(), 0.f);
+        }
         RVCR_CHECK_LAUNCH();
         count_launch(h);
     }
@@ -631,16 +797,25 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
     RVCR_TRY(h->ws_tc2.reserve((size_t)n_pad * nsplit * tc::TOPT * 4));
     RVCR_TRY(h->ws_tc3.reserve((size_t)n_pad * nsplit * tc::TOPT * 4));
     CUtensorMap ta, tb;
+    if (f8) {
+        RVCR_TRY(make_tmap_u8(&ta, h->ws_tc0.p, n_pad, kdim, tc::BLOCK_M));
+        RVCR_TRY(make_tmap_u8(&tb, h->cent_f8, h->cent_pad, kdim, tc::BLOCK_N / cluster));
+    } else {
     RVCR_TRY(make_tmap(&ta, h->ws_tc0.p, n_pad, kdim, tc::BLOCK_M));
     RVCR_TRY(make_tmap(&tb, h->cent_bf16, h->cent_pad, kdim, tc::BLOCK_N / cluster));
+    }
     {
         PhaseTimer pt(h, RVCR_PHASE_COARSE_MAIN, s);
         float* tv = h->ws_tc2.as<float>();
         int* tj = h->ws_tc3.as<int>();
-        const int nkb = kdim / tc::BLOCK_K;
+        const int nkb = kdim / kelems;
         // option "tc_resident": A k-blocks pinned in shared memory (0 = stream both operands, the r01 v1 kernel)
         const int64_t res = h->opt.tc_resident;
-        if (cluster == 2) {
+        if (f8) {   // d / 128 k-blocks (6 at d = 768): the 9-resident configuration keeps all but every 4th in shared memory
+            const float* qk = h->ws_tc4.as<float>();
+            if (cluster == 2) RVCR_TRY((launch_tc<2, 9, 4, 1, 4, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
+            else RVCR_TRY((launch_tc<1, 8, 2, 2, 3, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
+        } else if (cluster == 2) {
             if (res == 0) RVCR_TRY((launch_tc<2, 0, 6, 6, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
             else if (res == 6) RVCR_TRY((launch_tc<2, 6, 5, 3, 2>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
             else if (res == 8) RVCR_TRY((launch_tc<2, 8, 4, 2, 3>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
@@ -663,7 +838,7 @@ int coarse_exact_selected(rvcr_index* h, const float* q, int64_t n, const int32_
                           int32_t* list_out, float* dist_out, cudaStream_t s);
 
 int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out, cudaStream_t s) {
-    const int split = h->opt.coarse_mode == 3 ? 1 : 0;
+    const int split = h->opt.coarse_mode == 3 ? 1 : (h->opt.coarse_mode == 4 ? 2 : 0);
     const int cluster = h->opt.tc_cluster == 1 ? 1 : 2;
     float *topv, *qnorm;
     int* topj;
@@ -673,8 +848,12 @@ int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float
     // error margin between two approximate values (see DESIGN.md "Numerics"):
     //   bf16 rounding of both operands:  2 * 2 * 2^-8 |q||c|          (1-way)   /  2 * 2 * 3 * 2^-18 |q||c| (3-way split)
     //   fp32 accumulation over kdim products and the final fma: kdim * 2^-21 |q||c| + 2^-20 (|q|^2 + |c|^2)
-    const int kdim = split ? 3 * h->d : h->d;
-    const float rel = (split ? 12.f * 1.01f / 262144.f : 1.01f / 64.f) + (float)kdim / 2097152.f;
+    //   e4m3 (coarse_mode 4): rounding to 4 significant bits, 2^-4 relative per element; elements below the normal range
+    //   add at most sqrt(d) 2^-10 / s <= 2.2e-4 of the row maximum (s max >= 128, d <= 1024), saturation cannot happen
+    //   (s max < 256 <= 448):  |<q,c> - <q8,c8>| <= (0.0628 + 1.0628 * 0.0628) |q| c_max = 0.1296 |q| c_max,
+    //   times 2 (v = |c|^2 - 2 <q,c>) times 2 (two approximate values compared) = 0.5184 -> 0.53
+    const int kdim = split == 1 ? 3 * h->d : h->d;
+    const float rel = (split == 2 ? 0.53f : split == 1 ? 12.f * 1.01f / 262144.f : 1.01f / 64.f) + (float)kdim / 2097152.f;
     const float absm = 1.f / 1048576.f;
     RVCR_TRY(h->ws_stage.reserve((size_t)n * 4 + 64));
     int32_t* fb_list = h->ws_stage.as<int32_t>();

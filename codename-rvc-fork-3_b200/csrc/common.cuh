@@ -79,7 +79,8 @@ struct DevBuf {
 };
 
 struct Options {
-    int64_t coarse_mode = 0;  // 0 auto, 1 exact FFMA, 2 tcgen05 bf16, 3 tcgen05 3-way split
+    int64_t coarse_mode = 0;  // 0 auto, 1 exact FFMA, 2 tcgen05 bf16, 3 tcgen05 3-way split, 4 tcgen05 e4m3 (experimental,
+                              // explicit only: wide margin, pays off when few centroids are near the best one)
     int64_t nan_on_zero_score = 1;
     int64_t profile = 0;      // record CUDA events around each phase's kernels
     int64_t scan_impl = 0;    // 0 auto (default): 5 for batches of >= scan_tc_min_queries, else 4; 5 tcgen05 tf32 + exact
@@ -141,6 +142,8 @@ struct rvcr_index {
     int64_t cent_pad = 0;
     int cent_kdim = 0;                 // d (mode 2) or 3d (mode 3)
     int cent_split = 0;
+    void* cent_f8 = nullptr;           // nlist_pad x d e4m3 (coarse_mode 4), scaled by cent_f8_scale (a power of two)
+    float cent_f8_scale = 0.f;
 
     // list-ordered storage
     float* vecs = nullptr;             // nstored x d fp32
@@ -168,7 +171,7 @@ struct rvcr_index {
     bool scan_fb_dirty = false;
 
     rvcr::DevBuf ws_assign, ws_keys, ws_vals, ws_keys2, ws_vals2, ws_cub, ws_items, ws_flags, ws_misc,
-        ws_D, ws_P, ws_I, ws_best, ws_q, ws_tc0, ws_tc1, ws_tc2, ws_tc3, ws_stage;
+        ws_D, ws_P, ws_I, ws_best, ws_q, ws_tc0, ws_tc1, ws_tc2, ws_tc3, ws_tc4, ws_stage;
     cudaStream_t copy_stream = nullptr;          // host-buffer entry points: H2D chunks overlap the coarse step
     cudaStream_t out_stream = nullptr;           // ... and blended rows stream out while later lists are scanned
     std::vector<cudaEvent_t> copy_events;

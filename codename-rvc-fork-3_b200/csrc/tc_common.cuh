@@ -181,6 +181,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
             : "memory");
     }
 }
+// D[tmem] (+)= A[smem] * B[smem]^T, e4m3 x e4m3 -> fp32 (kind::f8f6f4: K = 32 elements = 32 B per instruction, so the
+// shared-memory tiles, descriptors and the +32 B k-advance are byte for byte those of the bf16 path)
+template <int CLUSTER>
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CLUSTER == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(
+                tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(
+                tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
 // all previously issued MMAs of this thread arrive on `bar` when they complete
 template <int CLUSTER>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -215,6 +233,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4)                    // D format: fp32
            | (1u << 7)                  // A format: bf16
            | (1u << 10)                 // B format: bf16
+           | ((uint32_t)(N >> 3) << 17) // N / 8
+           | ((uint32_t)(M >> 4) << 24);// M / 16    (A, B K-major; no negate; dense)
+}
+
+__host__ __device__ constexpr uint32_t make_idesc_f8(int M, int N) {
+    return (1u << 4)                    // D format: fp32
+           | (0u << 7)                  // A format: e4m3 (kind::f8f6f4: 0 = E4M3, 1 = E5M2)
+           | (0u << 10)                 // B format: e4m3
            | ((uint32_t)(N >> 3) << 17) // N / 8
            | ((uint32_t)(M >> 4) << 24);// M / 16    (A, B K-major; no negate; dense)
 }

@@ -255,6 +255,9 @@ RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, i
 /* keys: "coarse_mode" 0 = auto (tcgen05 from "coarse_tc_min_flops" = 6.4e7 flop per call, else the exact FFMA kernel:
  *                     same bits, lower fixed cost), 1 = exact FFMA kernel, 2 = tcgen05 bf16 + exact re-check,
  *                     3 = tcgen05 3-way split bf16 + exact re-check
+ *                     4 = tcgen05 e4m3 operands + exact re-check (experimental, explicit only: twice the tensor rate, a
+ *                         much wider margin -- pays off when few centroids lie near the best one, else queries fall
+ *                         back to the exact kernel; results are identical either way)
  *       "nan_on_zero_score" 1 (default, reference behaviour: exact-match query -> NaN row)
  *       "profile" 0/1 record per-phase CUDA events (see rvcr_get_phase_ms)
  *       "tc_cluster" 1 = one CTA per SM, 2 (default) = CTA pairs issuing tcgen05.mma.cta_group::2
@@ -275,7 +278,7 @@ RVCR_API int rvcr_get_phase_ms(rvcr_index* h, float* ms_out);
 /* Diagnostics for tests: run only the tensor-core stage of the coarse quantizer (coarse_tc.cu) and
  * return its raw output -- per query, `*pairs_out` = 8 * (number of centroid splits) approximate
  * (v = ||c||^2 - 2<q,c>, centroid id) pairs -- to host buffers of capacity cap_pairs per query,
- * plus ||q||^2 per query and max ||c||.  split: 0 = bf16, 1 = 3-way split bf16; cluster: 1 | 2. */
+ * plus ||q||^2 per query and max ||c||.  split: 0 = bf16, 1 = 3-way split bf16, 2 = e4m3; cluster: 1 | 2. */
 RVCR_API int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t split, int32_t cluster,
                                   int32_t cap_pairs, float* v_host, int32_t* j_host, int32_t* pairs_out,
                                   float* qnorm2_host, float* cmax_out, void* stream);

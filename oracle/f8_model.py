@@ -1,0 +1,43 @@
+"""numpy model of the e4m3 operand arithmetic of coarse_mode 4 (csrc/coarse_tc.cu, experimental).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): used by tests to check the kernel's raw values and, on the CPU, that the
+error margin the exact re-check relies on really bounds the e4m3 error.  `e4m3_round` is verified against torch's
+float8_e4m3fn conversion in tests/test_f8_margin_model.py."""
+import numpy as np
+
+
+def e4m3_round(x):
+    """float64 value of round-to-nearest-even e4m3 (bias 7, 3 mantissa bits, subnormal step 2^-9, max 448, saturating)."""
+    x = np.asarray(x, np.float64)
+    a = np.abs(x)
+    e = np.floor(np.log2(np.maximum(a, 2.0 ** -20)))
+    e = np.maximum(e, -6.0)                         # below 2^-6: the subnormal grid of the lowest binade
+    step = 2.0 ** (e - 3)
+    r = np.round(a / step) * step                   # np.round: half to even, like the hardware conversion
+    r = np.minimum(r, 448.0)
+    return np.sign(x) * r
+
+
+def f8_scale(mx):
+    """power-of-two scale s with 128 <= mx * s < 256 (f8_scale_for in coarse_tc.cu)"""
+    m, e = np.frexp(mx)
+    return np.ldexp(1.0, 8 - e)
+
+
+def coarse_values(q, cent):
+    """(v8, vtrue, margin): v8 = what the e4m3 tensor-core pass computes (exact dot of the scaled e4m3 operands, float64),
+    vtrue = ||c||^2 - 2 <q, c> in float64, margin = the per-query re-check margin of coarse_tc() for coarse_mode 4."""
+    q64, c64 = np.asarray(q, np.float64), np.asarray(cent, np.float64)
+    d = q64.shape[1]
+    cn = (c64 ** 2).sum(1)
+    sc = f8_scale(np.abs(c64).max())
+    sq = f8_scale(np.abs(q64).max(axis=1))
+    q8 = e4m3_round(q64 * sq[:, None])
+    c8 = e4m3_round(c64 * sc)
+    v8 = cn[None, :] - 2.0 * (q8 @ c8.T) / (sq[:, None] * sc)
+    vtrue = cn[None, :] - 2.0 * (q64 @ c64.T)
+    qn2 = (q64 ** 2).sum(1)
+    cmax = np.sqrt(cn.max())
+    rel = 0.53 + d / 2097152
+    margin = rel * np.sqrt(qn2) * cmax + (qn2 + cmax * cmax) / 1048576
+    return v8, vtrue, margin

@@ -1,0 +1,118 @@
+"""GPU, opt-in (RVCR_TEST_EXPERIMENTAL=1): the two kernels written after the last GPU session of round 1, which the
+default suite does not run because they have never executed on a B200:
+
+  * coarse_mode 4 -- the tcgen05 coarse step with e4m3 operands (kind::f8f6f4, csrc/coarse_tc.cu): raw values against a
+    float64 restatement of the scaled e4m3 arithmetic, the error margin, and the end result bit-identical to the exact
+    kernel (more fallbacks than bf16 are expected on tie-rich centroids; the answer must not change);
+  * scan_impl 6 -- the list scan with the exact re-check folded in (csrc/scan_tc_fused.cu): covered by running
+    tests/test_gpu_scan_tc.py with RVCR_TEST_SCAN_IMPL=6; here only a smoke comparison against scan_impl 5.
+
+tools/gpu_r02_first.sh runs this file under its own timeout (the kernels' mbarrier waits are bounded: they trap, they do not
+hang)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("RVCR_TEST_EXPERIMENTAL") != "1", reason="set RVCR_TEST_EXPERIMENTAL=1")]
+
+
+from oracle.f8_model import e4m3_round, f8_scale  # noqa: E402  (numpy model of the e4m3 arithmetic; CPU-checked in tests/test_f8_margin_model.py)
+
+
+def clustered_problem(rng, nq, nlist, d, sib=0.03):
+    blobs = (rng.standard_normal((max(4, nlist // 4), d)) * 0.30).astype(np.float32)
+    cent = (blobs[np.arange(nlist) // 4 % len(blobs)] + rng.standard_normal((nlist, d)).astype(np.float32) * sib).astype(np.float32)
+    q = (cent[rng.integers(0, nlist, nq)] + rng.standard_normal((nq, d)).astype(np.float32) * 0.14).astype(np.float32)
+    return q, cent
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("shape", [(300, 1000, 768), (200, 700, 256)])
+def test_f8_raw_values_match_float64(rvcr, cluster, shape):
+    import torch
+    nq, nlist, d = shape
+    rng = np.random.default_rng(nq + d)
+    q, cent = clustered_problem(rng, nq, nlist, d)
+    q[3] *= np.float32(1e-3)                          # a row far below the others: its own scale keeps it accurate
+    index = rvcr.index_factory(d, f"IVF{nlist},Flat")
+    index.set_centroids(cent)
+    v, j, qn2, cmax = index.debug_coarse_tc(torch.from_numpy(q).cuda(), split=2, cluster=cluster)
+    q64, c64 = q.astype(np.float64), cent.astype(np.float64)
+    cn = (c64 ** 2).sum(1)
+    sc = f8_scale(np.abs(c64).max())
+    sq = f8_scale(np.abs(q64).max(axis=1))
+    q8 = e4m3_round(q64 * sq[:, None])
+    c8 = e4m3_round(c64 * sc)
+    assert np.abs(q8).max() < 256 and np.abs(c8).max() < 256
+    vref = cn[None, :] - 2.0 * (q8 @ c8.T) / (sq[:, None] * sc)
+    vtrue = cn[None, :] - 2.0 * (q64 @ c64.T)
+    for i in range(nq):
+        valid = j[i] >= 0
+        assert valid.sum() >= 8 and (j[i][valid] < nlist).all()
+        got = v[i][valid]
+        assert np.abs(got - vref[i, j[i][valid]]).max() <= 4e-3          # fp32 accumulation + the fp32 ||c||^2 only
+        assert np.abs(np.sort(got)[:8] - np.sort(vref[i])[:8]).max() <= 8e-3
+    rel = 0.53 + d / 2097152
+    qn = np.sqrt(qn2.astype(np.float64))
+    margin = rel * qn * cmax + (qn2 + cmax * cmax) / 1048576
+    worst = 0.0
+    for i in range(nq):
+        valid = j[i] >= 0
+        err = np.abs(v[i][valid].astype(np.float64) - vtrue[i, j[i][valid]])
+        assert err.max() <= 0.5 * margin[i], (i, err.max(), margin[i])
+        worst = max(worst, err.max() / margin[i])
+    print(f"e4m3 coarse: worst |v - v_true| / margin = {worst:.3f} (must stay below 0.5)")
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+def test_f8_assign_bit_identical_to_exact_kernel(rvcr, oracle, cluster):
+    import torch
+    rng = np.random.default_rng(98)
+    nq, nlist, d = 6000, 6000, 768
+    q, cent = clustered_problem(rng, nq, nlist, d, sib=0.03)
+    cent[4001] = cent[17]                                         # exact duplicate centroid: lowest id must win
+    q[5] = cent[17] + np.float32(0.01)
+    q[6, 3] = np.nan
+    q[7] = 0                                                      # all-zero row: no scale -> exact kernel
+    q[8, 11] = np.inf
+    index = rvcr.index_factory(d, f"IVF{nlist},Flat")
+    index.set_centroids(cent)
+    qd = torch.from_numpy(q).cuda()
+    index.set_option("coarse_mode", 1)
+    l_ex, d_ex = [t.cpu().numpy() for t in index.assign(qd)]
+    index.set_option("coarse_mode", 4)
+    index.set_option("tc_cluster", cluster)
+    s0 = index.stats()
+    l_tc, d_tc = [t.cpu().numpy() for t in index.assign(qd)]
+    s1 = index.stats()
+    assert np.array_equal(l_tc, l_ex)
+    ok = l_ex >= 0
+    assert np.array_equal(d_tc[ok], d_ex[ok])
+    assert l_tc[5] == 17 and l_tc[6] == -1
+    fb = s1["coarse_fallback"] - s0["coarse_fallback"]
+    cand = s1["coarse_candidates"] - s0["coarse_candidates"]
+    print(f"e4m3 coarse, cluster {cluster}: {cand / max(1, nq - fb):.1f} candidates per query, {fb} of {nq} fell back")
+    assert fb <= nq // 10                                         # 4 siblings inside the margin, the rest ~100 away
+
+
+def test_fused_scan_equals_separate_recheck(rvcr):
+    import torch
+    from importlib import import_module
+    synth = import_module("codename-rvc-fork-3_b200.synth")
+    pr = synth.make_host_problem(150_000, 768, 9_000, 400)
+    index = rvcr.index_factory(768, "IVF400,Flat")
+    index.nprobe = 1
+    index.set_centroids(pr.centroids)
+    for i in range(0, len(pr.x), 65536):
+        index.add(pr.x[i:i + 65536])
+    out = {}
+    for impl in (5, 6):
+        index.set_option("scan_impl", impl)
+        D, I = index.search(pr.q, k=8)
+        f = torch.from_numpy(pr.q.copy()).cuda()
+        index.retrieve_blend_(f, 0.75)
+        out[impl] = (D, I, f.cpu().numpy())
+    assert np.array_equal(out[5][1], out[6][1]) and np.array_equal(out[5][0], out[6][0])
+    assert np.array_equal(out[5][2], out[6][2], equal_nan=True)

@@ -4,7 +4,8 @@
 # 1. the full GPU suite (now with the legacy-layout reader, tests/test_gpu_zz_legacy_index.py) and smoke()
 # 2. the experimental fused scan + re-check kernel (scan_impl 6) against the same tests as scan_impl 5 -- under its own
 #    timeout; its mbarrier waits are bounded (trap, not hang)
-# 3. C5 bench lines: default, scan_impl 6, and the re-check tuning knobs (CTAs per SM x unroll)
+#    and the e4m3 coarse step (coarse_mode 4) against the exact kernel (tests/test_gpu_experimental.py)
+# 3. C5 bench lines: default, scan_impl 6, coarse_mode 4, both, and the re-check tuning knobs (CTAs per SM x unroll)
 set -u
 mkdir -p gpurun_out
 ( time timeout 900 python -m pytest tests -x -q -m gpu ) > gpurun_out/r02_pytest.log 2>&1
@@ -14,6 +15,9 @@ tail -4 gpurun_out/r02_pytest.log
 ( RVCR_TEST_SCAN_IMPL=6 timeout 300 python -m pytest tests/test_gpu_scan_tc.py -x -q ) > gpurun_out/r02_pytest_fused.log 2>&1
 echo "fused rc=$?" >> gpurun_out/r02_pytest_fused.log
 tail -6 gpurun_out/r02_pytest_fused.log
+( RVCR_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -x -q -s ) > gpurun_out/r02_pytest_experimental.log 2>&1
+echo "experimental rc=$?" >> gpurun_out/r02_pytest_experimental.log
+tail -8 gpurun_out/r02_pytest_experimental.log
 nvidia-smi --query-gpu=name,memory.used --format=csv,noheader
 run() {  # name, env..., -- bench args
   local name=$1; shift
@@ -29,6 +33,8 @@ PY
 }
 run default RVCR_NOP=1
 BENCH_ARGS="--scan-impl 6" run fused RVCR_NOP=1
+BENCH_ARGS="--coarse-mode 4" run coarse_e4m3 RVCR_NOP=1
+BENCH_ARGS="--coarse-mode 4 --scan-impl 6" run coarse_e4m3_fused RVCR_NOP=1
 for ctas in 4 6 8 10; do
   for unr in 8 16; do
     run rc_${ctas}_${unr} RVCR_RC_CTAS=$ctas RVCR_RC_UNROLL=$unr
