@@ -57,7 +57,7 @@ def main():
         json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
         print(f"{len(cur)} kernels -> {path}")
         return 0
-    old = json.load(open(path))
+    old = {k: v for k, v in json.load(open(path)).items() if not k.startswith("_")}
     differs = [k for k in cur if k in old and cur[k]["sha1"] != old[k]["sha1"]]
     renamed = [k for k in differs if old[k].get("sha1_masked") == cur[k]["sha1_masked"]]
     changed = [k for k in differs if k not in renamed]
