@@ -218,7 +218,8 @@ def run_reference_arm(args, cfg):
     print(json.dumps(line), flush=True)
 
 
-def build_roofline(phase_acc, coarse_on_tensor_cores, pk, *, nst, n_home, owned_q, nlist, d, scan_impl, workload, world):
+def build_roofline(phase_acc, coarse_on_tensor_cores, pk, *, nst, n_home, owned_q, nlist, d, scan_impl, workload, world,
+                   coarse_e4m3=False):
     """Per-phase rooflines from the library's CUDA-event phase times (ms) and the ALGORITHMIC work of SURVEY 8d.
     nst = vectors stored on this rank, n_home = queries whose coarse step runs here, owned_q = queries whose list lives
     here (uniform queries: nq / world).  Returns (dict by phase, name of the dominant phase)."""
@@ -235,17 +236,22 @@ def build_roofline(phase_acc, coarse_on_tensor_cores, pk, *, nst, n_home, owned_
         # line shows sw_power_cap); microsecond launches (C1 / C2) are compared with the burst figure.  Both fractions
         # are reported.
         sustained = tc and phase_acc["coarse_main"] >= 20.0
-        peak = (pk["bf16_tflops_sustained"] if sustained else pk["bf16_tflops"]) if tc else 72.5
+        # coarse_mode 4 (experimental e4m3 operands): MEASURED_PEAKS.json has no fp8 figure; the tensor cores' e4m3 rate is
+        # twice the bf16 rate, so the denominator is 2 x the measured bf16 figure, and peak_source says so
+        fp8x = 2.0 if (tc and coarse_e4m3) else 1.0
+        peak = fp8x * (pk["bf16_tflops_sustained"] if sustained else pk["bf16_tflops"]) if tc else 72.5
         roof["coarse"] = {"bound": "tensor" if tc else "fp32-ffma", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
                           "frac": tf / peak, "traffic": None,
-                          "kernel": "coarse_tc_kernel<2> (tcgen05 bf16, fp32 accumulate)" if tc else "coarse_exact_kernel",
+                          "kernel": ("coarse_tc_kernel<2> (tcgen05 e4m3, fp32 accumulate)" if coarse_e4m3 else
+                                     "coarse_tc_kernel<2> (tcgen05 bf16, fp32 accumulate)") if tc else "coarse_exact_kernel",
                           "ms": phase_acc["coarse_main"], "flops_per_launch": coarse_flops,
                           "peak_source": (pk["source"] + (" cuBLAS bf16 sustained (the launch runs %.0f ms inside back-to-back steps)"
-                                                          % phase_acc["coarse_main"] if sustained else " cuBLAS bf16 burst"))
+                                                          % phase_acc["coarse_main"] if sustained else " cuBLAS bf16 burst")
+                                          + (" x 2 for e4m3 operands (no measured fp8 figure)" if coarse_e4m3 else ""))
                           if tc else "measured FFMA micro-peak (profiles/)"}
         if tc:
-            roof["coarse"]["frac_vs_burst"] = tf / pk["bf16_tflops"]
-            roof["coarse"]["frac_vs_sustained"] = tf / pk["bf16_tflops_sustained"]
+            roof["coarse"]["frac_vs_burst"] = tf / (fp8x * pk["bf16_tflops"])
+            roof["coarse"]["frac_vs_sustained"] = tf / (fp8x * pk["bf16_tflops_sustained"])
     fused = "scan" in phase_acc and "blend" not in phase_acc      # the re-check kernel also gathered + blended
     if "scan" in phase_acc:
         sb = scan_bytes + (blend_bytes if fused else 0)
@@ -441,7 +447,7 @@ def main():
     st = index.stats()
     roof, dominant = build_roofline(phase_acc, st["coarse_tc_queries"] > 0, peaks(), nst=int(sizes[lo:hi].sum()), n_home=n_home,
                                     owned_q=nq / world, nlist=nlist, d=d, scan_impl=args.scan_impl, workload=args.workload,
-                                    world=world)
+                                    world=world, coarse_e4m3=args.coarse_mode == 4)
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region --------------
     e2e = None
@@ -517,7 +523,8 @@ def main():
                            **({"transport": transport} if transport else {}),
                            "l2": "inputs larger than L2 (fresh 3 KB/query feature buffer per step; lists >> 126 MB)"
                            if nq * d * 4 > (126 << 20) else "inputs smaller than L2",
-                           "coarse": "tcgen05 bf16 + exact fp32 re-check" if st["coarse_tc_queries"] else "exact FFMA",
+                           "coarse": (("tcgen05 e4m3 (experimental coarse_mode 4)" if args.coarse_mode == 4 else "tcgen05 bf16")
+                                      + " + exact fp32 re-check") if st["coarse_tc_queries"] else "exact FFMA",
                            "setup_s": round(setup_s, 1)},
                 "roofline": dict(roof[dominant], dominant=dominant) if dominant else None,
                 "roofline_all": roof, "phase_ms": phase_acc, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,

@@ -92,3 +92,13 @@ def test_peaks_reads_driver_file_or_falls_back(bench, tmp_path, monkeypatch):
     (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps({"hbm_gbs": 6500, "bf16_tflops": 1600}))
     p = bench.peaks()
     assert p == {"hbm_gbs": 6500.0, "bf16_tflops": 1600.0, "bf16_tflops_sustained": 1600.0, "source": "measured"}
+
+
+def test_roofline_e4m3_coarse_uses_twice_the_bf16_figure(bench):
+    ph = {"coarse_main": 55.0, "scan": 32.0, "scan_recheck": 12.0}
+    roof, dom = bench.build_roofline(ph, True, PK, nst=32_000_000, n_home=1_000_000, owned_q=1e6, nlist=90509, d=768,
+                                     scan_impl=0, workload="C5", world=2, coarse_e4m3=True)
+    c = roof["coarse"]
+    assert dom == "coarse" and "e4m3" in c["kernel"] and "x 2" in c["peak_source"]
+    assert c["peak"] == 2 * PK["bf16_tflops_sustained"] and abs(c["frac"] - c["achieved"] / c["peak"]) < 1e-12
+    assert c["frac"] < 1.0 and abs(c["frac_vs_burst"] - c["achieved"] / (2 * PK["bf16_tflops"])) < 1e-12
