@@ -62,3 +62,27 @@ def test_oracle_search_semantics_match_sklearn_brute_force(oracle, d, iid, n, nl
                 padded += 1
             checked += 1
     assert checked == len(q) and (not iid or padded > 0)
+
+
+def test_oracle_kmeans_is_lloyd_from_the_faiss_init_like_sklearn(oracle):
+    """oracle.kmeans_train (faiss Clustering::train restated, SURVEY A9) against scikit-learn's Lloyd iterations started from
+    the SAME initial centroids (the first k rows of faiss's rand_perm(seed + 1)), on data without empty clusters and below
+    the 256-points-per-centroid subsampling threshold: ten plain Lloyd steps, so the centroids agree up to the few points
+    whose two nearest centroids are a rounding-size tie, and the objective decreases monotonically."""
+    sk_cluster = pytest.importorskip("sklearn.cluster")
+    synth = import_module("codename-rvc-fork-3_b200.synth")
+    pr = synth.make_host_problem(6_000, 64, 0, 40, seed=11, dup_frac=0.0)
+    x, k = pr.x, 40
+    cent, a_last, obj = oracle.kmeans_train(x, k, niter=10)
+    assert all(b <= a * (1 + 1e-6) for a, b in zip(obj[:-1], obj[1:]))
+    init = x[oracle.rand_perm(len(x), 1235)[:k]]
+    # 10 assignments + 10 mean updates in faiss == max_iter = 10 in sklearn (tol = 0: it only stops early once the labels
+    # no longer change, after which further faiss iterations change nothing either)
+    km = sk_cluster.KMeans(n_clusters=k, init=init.astype(np.float64), n_init=1, max_iter=10, tol=0.0, algorithm="lloyd")
+    km.fit(x.astype(np.float64))
+    assert np.bincount(a_last, minlength=k).min() > 0                       # no split_clusters involved
+    diff = np.abs(cent.astype(np.float64) - km.cluster_centers_).max(axis=1)
+    assert np.median(diff) <= 1e-5 and (diff <= 1e-3).mean() >= 0.9, (np.median(diff), diff.max())
+    obj_sk = ((x.astype(np.float64) - km.cluster_centers_[km.predict(x.astype(np.float64))]) ** 2).sum()
+    a_fin, d_fin = oracle.coarse_assign(x, cent)
+    assert abs(float(d_fin.astype(np.float64).sum()) - obj_sk) <= 1e-3 * obj_sk
