@@ -5,11 +5,14 @@
 //
 // Why (profiles/r01_ncu_summary.md): with two kernels the re-check runs after ALL lists have been
 // streamed, so its 13 candidate rows per query (and the 8 gathered ones) come from HBM a second time: 64.6 GB of DRAM
-// traffic for 30.8 GB of algorithmic work, 0.38 of the HBM roofline, and the scan phase as a whole stops at 0.62.  Here a
-// list's candidates are re-checked by warps of the same CTA right after the list has been streamed (a 4-deep hand-off ring
-// behind the epilogue warps), while the TMA / MMA / splitter warps are already on the next lists; a list is ~1 MB and
-// 148 CTAs stream ~160 MB through the 126 MB L2 in the time a list takes, so a large part of the candidate reads -- and
-// all of the 8 gather reads, which follow the distance pass within microseconds -- are L2 hits.
+// traffic for 30.8 GB of algorithmic work at 0.38 of the HBM roofline (a latency-bound kernel), and the scan phase as a
+// whole stops at 0.62.  Here a list's candidates are re-checked by warps of the same CTA right after the list has been
+// streamed (a 4-deep hand-off ring behind the epilogue warps), while the TMA / MMA / splitter warps are already on the next
+// lists.  What that can buy: (1) the latency-bound re-check overlaps the bandwidth-bound stream instead of following it;
+// (2) the 8 gather reads follow the distance pass of the same warp within microseconds and should hit L2; (3) SOME of the
+// candidate reads hit L2 -- the chip streams ~6 MB per microsecond through a 126 MB L2, so only rows younger than ~15 us
+// survive, i.e. the tail of the list that has just been streamed.  Honest expectation: phase 32 -> 26-28 ms, not the 22 ms
+// of the roofline; the second read of the candidates is inherent as long as a list (1 MB) does not fit on chip.
 //
 // Status: written after the last GPU session of round 1 and NOT yet run on a B200; results must equal scan_impl 5 bit for
 // bit (same candidates, same canonical distances, same tail arithmetic).  tests/test_gpu_scan_tc.py covers it only when
