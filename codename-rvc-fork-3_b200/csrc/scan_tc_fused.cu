@@ -230,6 +230,14 @@ scan_tc_fused_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_cons
                 const int row0 = lb + t * TILE_M;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait_warp(&S->empty[stage], phase ^ 1, lane);
+                    if ((dbg_flags & 8) && (kb & 1) == 0 && kb + 1 < nkb) {
+                        // tuning variant (RVCR_STC_FLAGS=8): issue k-blocks in pairs -- hold this box until the NEXT stage
+                        // is free too, so that the two 128-byte segments of every row (256 contiguous bytes in HBM) are
+                        // requested back to back instead of a stage time apart (DRAM page locality of the 3 KB rows)
+                        const uint32_t s2 = stage + 1 == (uint32_t)nstage ? 0u : stage + 1;
+                        const uint32_t p2 = s2 == 0u ? phase ^ 1u : phase;
+                        mbar_wait_warp(&S->empty[s2], p2 ^ 1, lane);
+                    }
                     if (tc::elect_one()) {
                         const uint32_t fb = bar_addr + (uint32_t)offsetof(Smem, full) + stage * 8;
                         tc::mbar_arrive_expect_tx_addr(fb, (uint32_t)rows * 128u);
