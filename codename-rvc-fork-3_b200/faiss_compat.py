@@ -467,6 +467,7 @@ class IndexCache:
         self.misses = 0
         self._lock = threading.Lock()
         self._entries: "OrderedDict[tuple, tuple[IndexIVFFlat, int]]" = OrderedDict()
+        self._loading: "dict[tuple, threading.Event]" = {}    # keys being read right now (one reader per key)
 
     @staticmethod
     def key(path: str, dev: int, shard) -> tuple:
@@ -476,16 +477,30 @@ class IndexCache:
 
     def get(self, path: str, dev: int, shard, opener) -> IndexIVFFlat:
         k = self.key(path, dev, shard)
-        with self._lock:
-            hit = self._entries.get(k)
-            if hit is not None:
-                self._entries.move_to_end(k)
-                self.hits += 1
-                return hit[0]
-            # a rewritten file (same path, new mtime / size) supersedes its stale entry
-            for old in [e for e in self._entries if e[0] == k[0] and e[3:] == k[3:]]:
-                del self._entries[old]
-        index = opener(path, dev, shard)                   # outside the lock: may take seconds for a 100 GB file
+        while True:
+            with self._lock:
+                hit = self._entries.get(k)
+                if hit is not None:
+                    self._entries.move_to_end(k)
+                    self.hits += 1
+                    return hit[0]
+                pending = self._loading.get(k)
+                if pending is None:
+                    # a rewritten file (same path, new mtime / size) supersedes its stale entry
+                    for old in [e for e in self._entries if e[0] == k[0] and e[3:] == k[3:]]:
+                        del self._entries[old]
+                    pending = self._loading[k] = threading.Event()
+                    break
+            # another thread (Gradio worker, core.py:38-42 shares one converter) is reading this very file: wait for it
+            # instead of loading a second copy of up to 100 GB; if its read failed, take over
+            pending.wait()
+        try:
+            index = opener(path, dev, shard)               # outside the lock: may take seconds for a 100 GB file
+        except BaseException:
+            with self._lock:
+                del self._loading[k]
+            pending.set()
+            raise
         nbytes = int(k[2])
         with self._lock:
             self.misses += 1
@@ -494,6 +509,8 @@ class IndexCache:
             while len(self._entries) > max(self.max_entries, 1) or (
                     len(self._entries) > 1 and sum(b for _, b in self._entries.values()) > self.max_bytes):
                 self._entries.popitem(last=False)
+            del self._loading[k]
+        pending.set()
         return index
 
     def clear(self) -> None:

@@ -155,3 +155,61 @@ def test_patch_pipeline_installs_everything():
     finally:
         fc.enable_index_cache(False)
         fc.IndexIVFFlat.lazy_reconstruct = False
+
+
+def test_concurrent_readers_of_one_file_load_it_once(tmp_path):
+    """Gradio worker threads share one converter (core.py:38-42): several `pipeline()` calls hitting the same cold file at
+    once must produce ONE read (a second copy of a 100 GB index would not fit), and a failed read must not wedge the
+    waiters."""
+    import threading
+    import time
+    faiss_compat = importlib.import_module("codename-rvc-fork-3_b200.faiss_compat")
+    p = str(tmp_path / "a.index")
+    open(p, "wb").write(b"x" * 10)
+    c = faiss_compat.IndexCache()
+    calls = []
+
+    def slow_opener(path, dev, shard):
+        calls.append(threading.get_ident())
+        time.sleep(0.2)
+        return FakeIndex(path, dev, shard)
+
+    got = [None] * 6
+
+    def worker(i):
+        got[i] = c.get(p, 0, None, slow_opener)
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert len(calls) == 1 and all(g is got[0] for g in got)
+    assert c.misses == 1 and c.hits == 5 and not c._loading
+
+    # the first reader fails: exactly one waiter takes over, the others get its result
+    q = str(tmp_path / "b.index")
+    open(q, "wb").write(b"y" * 10)
+    attempts = []
+    lock = threading.Lock()
+
+    def flaky_opener(path, dev, shard):
+        with lock:
+            attempts.append(1)
+            first = len(attempts) == 1
+        time.sleep(0.1)
+        if first:
+            raise RuntimeError("disk hiccup")
+        return FakeIndex(path, dev, shard)
+
+    res, errs = [], []
+
+    def worker2():
+        try:
+            res.append(c.get(q, 0, None, flaky_opener))
+        except RuntimeError as e:
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker2) for _ in range(5)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert len(errs) == 1 and len(res) == 4 and all(r is res[0] for r in res)
+    assert len(attempts) == 2 and not c._loading
