@@ -20,6 +20,7 @@ import ctypes as C
 import os
 import re
 import threading
+import weakref
 from collections import OrderedDict
 
 import numpy as np
@@ -200,7 +201,15 @@ class IndexIVFFlat:
         if n0 < 0 or ni < 0 or n0 + ni > inf.ntotal:
             raise RvcrError(-1, f"reconstruct_n: range [{n0}, {n0 + ni}) outside [0, {inf.ntotal})")
         if self.lazy_reconstruct:
-            return LazyBigNpy(self, int(n0), int(ni), int(inf.d))
+            # one placeholder per (index, range): with the index cache on, every pipeline() call asks again
+            # (pipeline.py:556) and must not trigger a second host copy if somebody does index it
+            key = (int(n0), int(ni), int(inf.ntotal))
+            memo = self.__dict__.setdefault("_lazy_memo", {})
+            lazy = memo.get(key)
+            if lazy is None:
+                memo.clear()                                   # ntotal changed (index.add) or another range: drop the old copy
+                lazy = memo.setdefault(key, LazyBigNpy(self, int(n0), int(ni), int(inf.d)))
+            return lazy
         return self._reconstruct_now(int(n0), int(ni), int(inf.d))
 
     def _reconstruct_now(self, n0: int, ni: int, d: int) -> np.ndarray:
@@ -337,8 +346,11 @@ class LazyBigNpy:
     UNPATCHED `_retrieve_speaker_embeddings` body still works; the fused path ignores it entirely."""
 
     def __init__(self, index: "IndexIVFFlat", n0: int, ni: int, d: int):
-        self._index, self._n0, self._ni, self._d = index, n0, ni, d
+        # weak: the index memoises its placeholder (reconstruct_n), and a strong back reference would be a cycle that
+        # keeps up to 100 GB of HBM alive until the cyclic GC runs instead of until the last user drops the index
+        self._index_ref, self._n0, self._ni, self._d = weakref.ref(index), n0, ni, d
         self._arr = None
+        self._lock = threading.Lock()     # one materialisation even when worker threads index it at the same time
 
     shape = property(lambda self: (self._ni, self._d))
     dtype = np.dtype(np.float32)
@@ -350,7 +362,12 @@ class LazyBigNpy:
 
     def _get(self) -> np.ndarray:
         if self._arr is None:
-            self._arr = self._index._reconstruct_now(self._n0, self._ni, self._d)
+            with self._lock:
+                if self._arr is None:
+                    index = self._index_ref()
+                    if index is None:
+                        raise RvcrError(-6, "big_npy placeholder used after its index was freed")
+                    self._arr = index._reconstruct_now(self._n0, self._ni, self._d)
         return self._arr
 
     def __array__(self, dtype=None, copy=None):

@@ -213,3 +213,59 @@ def test_concurrent_readers_of_one_file_load_it_once(tmp_path):
     [t.join() for t in ts]
     assert len(errs) == 1 and len(res) == 4 and all(r is res[0] for r in res)
     assert len(attempts) == 2 and not c._loading
+
+
+def test_lazy_big_npy_materialises_once_under_threads_and_is_shared_per_index():
+    import threading
+    import time
+
+    class SlowIdx:
+        calls = 0
+
+        def _reconstruct_now(self, n0, ni, d):
+            SlowIdx.calls += 1
+            time.sleep(0.1)
+            return np.arange(ni * d, dtype=np.float32).reshape(ni, d)
+
+    slow = SlowIdx()
+    lazy = fc.LazyBigNpy(slow, 0, 20, 8)                         # the placeholder holds its index weakly
+    outs = []
+    ts = [threading.Thread(target=lambda: outs.append(lazy[3])) for _ in range(5)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert SlowIdx.calls == 1 and all(np.array_equal(o, outs[0]) for o in outs)
+
+    # reconstruct_n on the same index and range hands back the same placeholder (pipeline() asks on every call)
+    class Inf:
+        ntotal, d = 20, 8
+
+    class Idx(fc.IndexIVFFlat):
+        lazy_reconstruct = True
+
+        def __init__(self):
+            pass
+
+        def _info(self):
+            return Inf
+
+        def __del__(self):
+            pass
+
+    idx = Idx()
+    a, b = idx.reconstruct_n(0, 20), idx.reconstruct_n(0, Inf.ntotal)
+    assert a is b and isinstance(a, fc.LazyBigNpy)
+    Inf.ntotal = 30                                             # index.add happened: a new placeholder, the old copy is dropped
+    c = idx.reconstruct_n(0, 30)
+    assert c is not a and c.shape == (30, 8) and len(idx._lazy_memo) == 1
+    # no reference cycle: dropping the index frees it at once (its HBM with it); an unmaterialised orphan says so
+    import gc
+    import weakref
+    gc.disable()
+    try:
+        w = weakref.ref(idx)
+        del idx, a, b
+        assert w() is None
+        with pytest.raises(fc.RvcrError):
+            c[0]
+    finally:
+        gc.enable()
