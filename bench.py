@@ -218,6 +218,32 @@ def run_reference_arm(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def parity_sample(gpu_rows, cpu_rows):
+    """The blended rows the GPU produced in the first timed step for the CPU-baseline sample, against the CPU restatement
+    of the reference path on the same queries (faiss-like BLAS coarse, canonical scan, numpy tail verbatim).  Rows are
+    expected to be bit-identical except where the BLAS-order and the canonical-order coarse distances pick different
+    centroids on a near-tie (the documented ties of DESIGN.md).  Never raises: the bench line must survive it."""
+    try:
+        if gpu_rows is None or cpu_rows is None:
+            return None
+        m = min(len(gpu_rows), len(cpu_rows))
+        g, c = np.asarray(gpu_rows[:m]), np.asarray(cpu_rows[:m])
+        with np.errstate(all="ignore"):
+            same = ((g == c) | (np.isnan(g) & np.isnan(c))).all(axis=1)
+            other = ~same
+            rel = 0.0
+            if other.any():
+                den = np.maximum(np.abs(c[other]), 1e-30)
+                diff = np.abs(g[other] - c[other]) / den
+                rel = float(np.nanmax(np.where(np.isfinite(diff), diff, 0.0)))
+        return {"rows": int(m), "rows_bit_identical": int(same.sum()), "rows_differing": int(other.sum()),
+                "max_rel_diff_in_differing_rows": rel,
+                "against": "CPU port of the reference path on the same queries (BLAS-order coarse like faiss >= 20 queries; "
+                           "differing rows = near-tie centroid choices between the BLAS and the canonical distance order)"}
+    except Exception as ex:                                    # pragma: no cover
+        return {"error": repr(ex)[:200]}
+
+
 def build_roofline(phase_acc, coarse_on_tensor_cores, pk, *, nst, n_home, owned_q, nlist, d, scan_impl, workload, world,
                    coarse_e4m3=False):
     """Per-phase rooflines from the library's CUDA-event phase times (ms) and the ALGORITHMIC work of SURVEY 8d.
@@ -432,6 +458,12 @@ def main():
     ms_step = ms_total / args.steps
     value = nq / (ms_step * 1e-3)
     result_check = bufs[args.warmup][:4].cpu().numpy()
+    gpu_rows = None                                           # blended rows of the first timed step, for the parity sample
+    try:
+        if world == 1 and not args.no_cpu_baseline:
+            gpu_rows = bufs[args.warmup][:min(n_home, args.cpu_sample)].cpu().numpy()
+    except Exception:
+        gpu_rows = None
     del bufs
 
     # ---- per-phase device times (separate pass, same inputs) for the roofline --------------------
@@ -480,6 +512,7 @@ def main():
 
     # ---- CPU baseline on rank 0 (N = 1 only): bounded sample of the same workload ------------------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
         sample = min(nq, args.cpu_sample)
@@ -512,6 +545,7 @@ def main():
                "sample": f"first {sample} of {nq} query frames of this workload, all {nlist} centroids, the {len(probed)} lists "
                          f"they probe staged on the host; {passes} passes, {total_s:.1f} s of CPU work; oracle port of faiss "
                          f"1.7.3 + numpy (omp_threads={oracle.num_threads()}, torch_threads={_t.get_num_threads()})"}
+        parity = parity_sample(gpu_rows, out_cpu)
         del sub_vecs
 
     if rank == 0:
@@ -533,7 +567,7 @@ def main():
                                  "exact_fallback_queries": st["coarse_fallback"]},
                 "scan_stats": {"tc_candidates_rechecked": st.get("scan_tc_candidates", 0), "exact_fallback_queries": st.get("scan_tc_fallback", 0),
                                "queries": st["queries"]},
-                "sanity": {"finite_first_rows": bool(np.isfinite(result_check).all())}}
+                "sanity": {"finite_first_rows": bool(np.isfinite(result_check).all()), "parity_sample": parity}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -102,3 +102,19 @@ def test_roofline_e4m3_coarse_uses_twice_the_bf16_figure(bench):
     assert dom == "coarse" and "e4m3" in c["kernel"] and "x 2" in c["peak_source"]
     assert c["peak"] == 2 * PK["bf16_tflops_sustained"] and abs(c["frac"] - c["achieved"] / c["peak"]) < 1e-12
     assert c["frac"] < 1.0 and abs(c["frac_vs_burst"] - c["achieved"] / (2 * PK["bf16_tflops"])) < 1e-12
+
+
+def test_parity_sample_counts_and_never_raises(bench):
+    import numpy as np
+    rng = np.random.default_rng(0)
+    c = rng.standard_normal((50, 16)).astype(np.float32)
+    g = c.copy()
+    c[3] = np.nan
+    g[3] = np.nan                                    # NaN rows (exact-match queries) count as identical
+    g[7] += np.float32(0.5)                          # a near-tie row: different centroid, different neighbours
+    out = bench.parity_sample(g, c)
+    assert out["rows"] == 50 and out["rows_bit_identical"] == 49 and out["rows_differing"] == 1
+    assert out["max_rel_diff_in_differing_rows"] > 0
+    assert bench.parity_sample(None, c) is None
+    assert "error" in bench.parity_sample("nonsense", c) or bench.parity_sample("nonsense", c) is not None
+    assert bench.parity_sample(g[:10], c)["rows"] == 10
