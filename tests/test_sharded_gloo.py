@@ -220,7 +220,7 @@ def _worker(rank, world, port, tmp):
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 8])
 def test_sharded_equals_single_on_gloo(world, tmp_path, oracle):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
