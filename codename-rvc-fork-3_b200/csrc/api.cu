@@ -918,6 +918,9 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "tc_resident")) {
         if (value != 0 && value != 6 && value != 8 && value != 9 && value != 10) return RVCR_ERR_INVALID;
         h->opt.tc_resident = value;
+    } else if (!strcmp(key, "coarse_f8_auto")) {
+        h->opt.coarse_f8_auto = value ? 1 : 0;
+        h->f8_decision = 0;
     } else if (!strcmp(key, "coarse_tc_min_flops")) {
         if (value < 0) return RVCR_ERR_INVALID;
         h->opt.coarse_tc_min_flops = value;
@@ -953,6 +956,8 @@ int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out) {
     else if (!strcmp(key, "tc_resident")) *value_out = h->opt.tc_resident;
     else if (!strcmp(key, "fused_blend")) *value_out = h->opt.fused_blend;
     else if (!strcmp(key, "kmeans_niter")) *value_out = h->opt.kmeans_niter;
+    else if (!strcmp(key, "coarse_f8_auto")) *value_out = h->opt.coarse_f8_auto;
+    else if (!strcmp(key, "coarse_f8_decision")) *value_out = h->f8_decision;   // read only: 0 not probed, 1 e4m3, -1 bf16
     else if (!strcmp(key, "coarse_tc_min_flops")) *value_out = h->opt.coarse_tc_min_flops;
     else if (!strcmp(key, "scan_tc_min_queries")) *value_out = h->opt.scan_tc_min_queries;
     else if (!strcmp(key, "coarse_tc_available")) *value_out = coarse_tc_available() ? 1 : 0;

@@ -733,6 +733,7 @@ int coarse_tc_invalidate(rvcr_index* h) {
     h->cent_norm = nullptr;
     h->cent_f8 = nullptr;
     h->cent_f8_scale = 0.f;
+    h->f8_decision = 0;
     h->cent_split = -1;
     return RVCR_OK;
 }
@@ -837,8 +838,32 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
 int coarse_exact_selected(rvcr_index* h, const float* q, int64_t n, const int32_t* qsel, const int32_t* nsel_dev,
                           int32_t* list_out, float* dist_out, cudaStream_t s);
 
+static int coarse_tc_split(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out, int split, cudaStream_t s);
+
 int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out, cudaStream_t s) {
-    const int split = h->opt.coarse_mode == 3 ? 1 : (h->opt.coarse_mode == 4 ? 2 : 0);
+    int split = h->opt.coarse_mode == 3 ? 1 : (h->opt.coarse_mode == 4 ? 2 : 0);
+    // option coarse_f8_auto (auto mode only): decide per centroid set, on the caller's own queries, whether the e4m3
+    // operands pay off -- they do when few centroids lie within the (35x wider) margin of the best one
+    if (h->opt.coarse_mode == 0 && h->opt.coarse_f8_auto && h->d % 128 == 0 && h->d <= 1024) {
+        constexpr int64_t kProbe = 8192;
+        if (h->f8_decision == 0 && n >= 8 * kProbe) {
+            int rc = coarse_tc_split(h, q, kProbe, list_out, dist_out, 2, s);   // results are overwritten by the full call below
+            if (rc == RVCR_ERR_UNSUPPORTED) {
+                h->f8_decision = -1;                                            // e.g. non-finite centroids
+            } else {
+                RVCR_TRY(rc);
+                int32_t fb = 0;
+                RVCR_CUDA(cudaMemcpyAsync(&fb, h->ws_misc.as<int32_t>() + 16, 4, cudaMemcpyDeviceToHost, s));
+                RVCR_CUDA(cudaStreamSynchronize(s));
+                h->f8_decision = fb <= kProbe / 200 ? 1 : -1;
+            }
+        }
+        if (h->f8_decision > 0) split = 2;
+    }
+    return coarse_tc_split(h, q, n, list_out, dist_out, split, s);
+}
+
+static int coarse_tc_split(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out, int split, cudaStream_t s) {
     const int cluster = h->opt.tc_cluster == 1 ? 1 : 2;
     float *topv, *qnorm;
     int* topj;

@@ -258,6 +258,9 @@ RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, i
  *                     4 = tcgen05 e4m3 operands + exact re-check (experimental, explicit only: twice the tensor rate, a
  *                         much wider margin -- pays off when few centroids lie near the best one, else queries fall
  *                         back to the exact kernel; results are identical either way)
+ *       "coarse_f8_auto" 0 (default) / 1: in auto mode, probe coarse_mode 4 on the first 8 192 queries of the first call of
+ *                     >= 65 536 queries per centroid set and keep it when <= 0.5 % of the probe fell back (experimental);
+ *                     "coarse_f8_decision" (read only) tells the outcome: 0 not probed, 1 e4m3, -1 bf16
  *       "nan_on_zero_score" 1 (default, reference behaviour: exact-match query -> NaN row)
  *       "profile" 0/1 record per-phase CUDA events (see rvcr_get_phase_ms)
  *       "tc_cluster" 1 = one CTA per SM, 2 (default) = CTA pairs issuing tcgen05.mma.cta_group::2

@@ -116,3 +116,29 @@ def test_fused_scan_equals_separate_recheck(rvcr):
         out[impl] = (D, I, f.cpu().numpy())
     assert np.array_equal(out[5][1], out[6][1]) and np.array_equal(out[5][0], out[6][0])
     assert np.array_equal(out[5][2], out[6][2], equal_nan=True)
+
+
+def test_f8_auto_probe_decides_per_centroid_set(rvcr, oracle):
+    """option coarse_f8_auto: e4m3 operands are kept where the probe shows (almost) no fallbacks -- the bench's blob
+    construction -- and dropped on centroids that crowd inside the margin; results are the exact kernel's either way."""
+    import torch
+    rng = np.random.default_rng(4)
+    d, nlist, nq = 256, 4096, 70_000
+    for crowded, want in ((False, 1), (True, -1)):
+        if crowded:      # all centroids within a few units of each other: hundreds inside the e4m3 margin
+            cent = (rng.standard_normal((1, d)) * 0.3 + rng.standard_normal((nlist, d)) * 0.02).astype(np.float32)
+            q = (cent[rng.integers(0, nlist, nq)] + rng.standard_normal((nq, d)).astype(np.float32) * 0.02).astype(np.float32)
+        else:
+            q, cent = clustered_problem(rng, nq, nlist, d)
+        index = rvcr.index_factory(d, f"IVF{nlist},Flat")
+        index.set_centroids(cent)
+        qd = torch.from_numpy(q).cuda()
+        index.set_option("coarse_mode", 0)
+        index.set_option("coarse_f8_auto", 1)
+        assert index.get_option("coarse_f8_decision") == 0
+        l_auto, d_auto = [t.cpu().numpy() for t in index.assign(qd)]
+        assert index.get_option("coarse_f8_decision") == want, crowded
+        sel = rng.choice(nq, 4000, replace=False)
+        index.set_option("coarse_mode", 1)
+        l_ex, d_ex = [t.cpu().numpy() for t in index.assign(torch.from_numpy(q[sel]).cuda())]
+        assert np.array_equal(l_auto[sel], l_ex) and np.array_equal(d_auto[sel], d_ex)
