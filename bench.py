@@ -337,6 +337,7 @@ def main():
     ap.add_argument("--workload", default="C5", choices=["C1", "C2", "C3", "C5"])
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--coarse-mode", type=int, default=0)
+    ap.add_argument("--coarse-f8-auto", type=int, default=0, help="1 = let the auto coarse mode probe e4m3 operands (experimental)")
     ap.add_argument("--scan-impl", type=int, default=0, help="0 = library default (auto by batch size), 5 = tcgen05 scan, 1-4 exact FFMA scans, 6 = experimental fused scan + re-check")
     ap.add_argument("--tc-resident", type=int, default=-1, help="coarse kernel: resident query k-blocks (0/8/9/10; -1 = library default)")
     ap.add_argument("--fused-blend", type=int, default=-1, help="1 = re-check kernel also blends (default), 0 = separate gather_blend kernel")
@@ -383,6 +384,8 @@ def main():
     synth.fill_index_by_construction(index, cent_all, sizes, N, list_range=(lo, hi))
     index.set_option("coarse_mode", args.coarse_mode)
     index.set_option("scan_impl", args.scan_impl)
+    if args.coarse_f8_auto:
+        index.set_option("coarse_f8_auto", 1)
     if args.tc_resident >= 0:
         index.set_option("tc_resident", args.tc_resident)
     if args.fused_blend >= 0:
@@ -477,9 +480,10 @@ def main():
             phase_acc[k] = phase_acc.get(k, 0.0) + v / reps
         del b
     st = index.stats()
+    coarse_e4m3 = args.coarse_mode == 4 or (args.coarse_f8_auto and index.get_option("coarse_f8_decision") == 1)
     roof, dominant = build_roofline(phase_acc, st["coarse_tc_queries"] > 0, peaks(), nst=int(sizes[lo:hi].sum()), n_home=n_home,
                                     owned_q=nq / world, nlist=nlist, d=d, scan_impl=args.scan_impl, workload=args.workload,
-                                    world=world, coarse_e4m3=args.coarse_mode == 4)
+                                    world=world, coarse_e4m3=coarse_e4m3)
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region --------------
     e2e = None
@@ -561,7 +565,7 @@ def main():
                            **({"transport": transport} if transport else {}),
                            "l2": "inputs larger than L2 (fresh 3 KB/query feature buffer per step; lists >> 126 MB)"
                            if nq * d * 4 > (126 << 20) else "inputs smaller than L2",
-                           "coarse": (("tcgen05 e4m3 (experimental coarse_mode 4)" if args.coarse_mode == 4 else "tcgen05 bf16")
+                           "coarse": (("tcgen05 e4m3 (experimental coarse_mode 4)" if coarse_e4m3 else "tcgen05 bf16")
                                       + " + exact fp32 re-check") if st["coarse_tc_queries"] else "exact FFMA",
                            "setup_s": round(setup_s, 1)},
                 "roofline": dict(roof[dominant], dominant=dominant) if dominant else None,
