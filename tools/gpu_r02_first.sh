@@ -36,6 +36,7 @@ BENCH_ARGS="--scan-impl 6" run fused RVCR_NOP=1
 BENCH_ARGS="--scan-impl 6" run fused_paired_kblocks RVCR_STC_FLAGS=8
 BENCH_ARGS="--coarse-mode 4" run coarse_e4m3 RVCR_NOP=1
 BENCH_ARGS="--coarse-mode 4 --scan-impl 6" run coarse_e4m3_fused RVCR_NOP=1
+BENCH_ARGS="--coarse-f8-auto 1" run coarse_auto_probe RVCR_NOP=1
 for ctas in 4 6 8 10; do
   for unr in 8 16; do
     run rc_${ctas}_${unr} RVCR_RC_CTAS=$ctas RVCR_RC_UNROLL=$unr
