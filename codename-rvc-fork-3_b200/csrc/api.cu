@@ -333,6 +333,8 @@ void rvcr_index_free(rvcr_index* h) {
                           &h->ws_fb, &h->ws_cstage};
         for (DevBuf* b : bufs) b->release();
         if (h->last_done) cudaEventDestroy(h->last_done);
+        if (h->f8_fb_event) cudaEventDestroy(h->f8_fb_event);
+        if (h->f8_fb_host) cudaFreeHost(h->f8_fb_host);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
         if (h->out_stream) cudaStreamDestroy(h->out_stream);
         for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);

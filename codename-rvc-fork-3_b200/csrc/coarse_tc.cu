@@ -734,6 +734,7 @@ int coarse_tc_invalidate(rvcr_index* h) {
     h->cent_f8 = nullptr;
     h->cent_f8_scale = 0.f;
     h->f8_decision = 0;
+    h->f8_last_n = 0;
     h->cent_split = -1;
     return RVCR_OK;
 }
@@ -858,9 +859,24 @@ int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float
                 h->f8_decision = fb <= kProbe / 200 ? 1 : -1;
             }
         }
+        // sticky downgrade: if the previous e4m3 call sent more than 2 % of its queries to the exact kernel (the probe's
+        // prefix was not representative), this centroid set goes back to bf16.  The count was copied asynchronously.
+        if (h->f8_decision > 0 && h->f8_last_n > 0 && h->f8_fb_event && cudaEventQuery(h->f8_fb_event) == cudaSuccess) {
+            if ((int64_t)*h->f8_fb_host * 50 > h->f8_last_n) h->f8_decision = -1;
+            h->f8_last_n = 0;
+        }
+        cudaGetLastError();   // cudaEventQuery's cudaErrorNotReady is not an error
         if (h->f8_decision > 0) split = 2;
     }
-    return coarse_tc_split(h, q, n, list_out, dist_out, split, s);
+    RVCR_TRY(coarse_tc_split(h, q, n, list_out, dist_out, split, s));
+    if (split == 2 && h->opt.coarse_mode == 0 && n >= 4096) {
+        if (!h->f8_fb_host) RVCR_CUDA(cudaMallocHost(&h->f8_fb_host, sizeof(int32_t)));
+        if (!h->f8_fb_event) RVCR_CUDA(cudaEventCreateWithFlags(&h->f8_fb_event, cudaEventDisableTiming));
+        RVCR_CUDA(cudaMemcpyAsync(h->f8_fb_host, h->ws_misc.as<int32_t>() + 16, 4, cudaMemcpyDeviceToHost, s));
+        RVCR_CUDA(cudaEventRecord(h->f8_fb_event, s));
+        h->f8_last_n = n;
+    }
+    return RVCR_OK;
 }
 
 static int coarse_tc_split(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out, int split, cudaStream_t s) {

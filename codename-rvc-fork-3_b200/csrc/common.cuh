@@ -149,6 +149,9 @@ struct rvcr_index {
     void* cent_f8 = nullptr;           // nlist_pad x d e4m3 (coarse_mode 4), scaled by cent_f8_scale (a power of two)
     float cent_f8_scale = 0.f;
     int f8_decision = 0;               // coarse_f8_auto: 0 = not probed yet, +1 = e4m3 operands, -1 = bf16 (per centroid set)
+    int32_t* f8_fb_host = nullptr;     // pinned: fallbacks of the last e4m3 call in auto mode (copied asynchronously) ...
+    cudaEvent_t f8_fb_event = nullptr; // ... valid once this event has completed; checked at the start of the next call
+    int64_t f8_last_n = 0;             // queries of that call (0 = nothing pending)
 
     // list-ordered storage
     float* vecs = nullptr;             // nstored x d fp32
