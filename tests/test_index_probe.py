@@ -8,6 +8,7 @@ files: every count is checked against the file length before it is trusted.  Cov
 ("IwFl", full / sprs list tables, direct maps, IxFl quantizer), the legacy layouts faiss 1.7.3 still reads ("IvFL",
 "IvFl") against the oracle's writer, refusals with the documented codes, truncation at every byte,
 hostile counts, random mutations, and the shard-range rule against its numpy restatement."""
+import os
 import struct
 
 import numpy as np
@@ -253,3 +254,29 @@ def test_shard_range_matches_numpy_restatement(rvcr):
         rvcr.shard_range(np.array([1, -2, 3]), 0, 2)
     with pytest.raises(rvcr.RvcrError):
         rvcr.shard_range(np.array([1, 2, 3]), 2, 2)
+
+
+def test_probe_agrees_with_oracle_writer_on_random_valid_files(rvcr, oracle, tmp_path):
+    """300 random shapes (d from 4 to 768, 1-40 lists, 0-400 vectors: empty indices, single lists, sprs and full tables)
+    in all three layouts: the library's parse and the oracle's reader agree with what was written."""
+    rng = np.random.default_rng(0)
+    p = str(tmp_path / "r.index")
+    for _ in range(300):
+        d = int(rng.choice([4, 8, 64, 128, 256, 768]))
+        nlist = int(rng.integers(1, 40))
+        n = int(rng.choice([0, 1, 5, 50, 400]))
+        sizes = np.bincount(rng.integers(0, nlist, n), minlength=nlist).astype(np.int64) if n else np.zeros(nlist, np.int64)
+        data = oracle.IVFFlatData(d=d, ntotal=n, nprobe=1, centroids=rng.standard_normal((nlist, d)).astype(np.float32),
+                                  list_sizes=sizes, vecs=rng.standard_normal((n, d)).astype(np.float32),
+                                  ids=np.arange(n, dtype=np.int64))
+        for kind in ("IwFl", "IvFL", "IvFl"):
+            if kind == "IwFl":
+                oracle.write_index(data, p)
+            else:
+                oracle.write_index_legacy(data, p, kind.encode())
+            inf = rvcr.probe_index(p, list_sizes=True)
+            assert (inf["fourcc"], inf["d"], inf["ntotal"], inf["nlist"], inf["nvectors"]) == (kind, d, n, nlist, n)
+            assert np.array_equal(inf["list_sizes"], sizes) and inf["file_bytes"] == os.path.getsize(p)
+            back = oracle.read_index(p)
+            assert np.array_equal(back.list_sizes, sizes) and np.array_equal(back.vecs, data.vecs)
+            assert np.array_equal(back.ids, data.ids) and np.array_equal(back.centroids, data.centroids)
