@@ -329,7 +329,7 @@ void rvcr_index_free(rvcr_index* h) {
         if (h->stage_assign) cudaFree(h->stage_assign);
         DevBuf* bufs[] = {&h->ws_assign, &h->ws_keys, &h->ws_vals, &h->ws_keys2, &h->ws_vals2, &h->ws_cub, &h->ws_items,
                           &h->ws_flags, &h->ws_misc, &h->ws_D, &h->ws_P, &h->ws_I, &h->ws_best, &h->ws_q, &h->ws_tc0,
-                          &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_tc4, &h->ws_stage, &h->row_norm, &h->ws_cand, &h->ws_candcnt,
+                          &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_tc4, &h->ws_tc5, &h->ws_stage, &h->row_norm, &h->ws_cand, &h->ws_candcnt,
                           &h->ws_fb, &h->ws_cstage};
         for (DevBuf* b : bufs) b->release();
         if (h->last_done) cudaEventDestroy(h->last_done);
@@ -1007,7 +1007,8 @@ int rvcr_get_stats(rvcr_index* h, rvcr_stats* out) {
 }
 
 int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t split, int32_t cluster, int32_t cap_pairs,
-                         float* v_host, int32_t* j_host, int32_t* pairs_out, float* qnorm2_host, float* cmax_out, void* stream) {
+                         float* v_host, int32_t* j_host, int32_t* pairs_out, float* qnorm2_host, float* cmax_out,
+                         float* margin_host, void* stream) {
     RVCR_ENTER(h);
     cudaStream_t s = (cudaStream_t)stream;
     if (n <= 0 || !q_dev || !v_host || !j_host || !pairs_out || (cluster != 1 && cluster != 2)) return RVCR_ERR_INVALID;
@@ -1015,10 +1016,13 @@ int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t s
         set_error("index is not trained");
         return RVCR_ERR_STATE;
     }
-    float *topv, *qnorm;
+    RVCR_TRY(stream_enter(h, s));
+    float *topv, *qnorm, *qres;
     int* topj;
     int nsplit = 0;
-    RVCR_TRY(coarse_tc_top8(h, q_dev, n, split == 2 ? 2 : (split ? 1 : 0), cluster, &topv, &topj, &nsplit, &qnorm, s));   // 2: e4m3
+    int64_t res_stride = 0;
+    const int sp = split == 2 ? 2 : (split ? 1 : 0);   // 2: e4m3
+    RVCR_TRY(coarse_tc_top8(h, q_dev, n, sp, cluster, &topv, &topj, &nsplit, &qnorm, &qres, &res_stride, s));
     const int pairs = nsplit * 8;
     *pairs_out = pairs;
     if (pairs > cap_pairs) {
@@ -1028,9 +1032,14 @@ int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t s
     RVCR_CUDA(cudaMemcpyAsync(v_host, topv, (size_t)n * pairs * 4, cudaMemcpyDeviceToHost, s));
     RVCR_CUDA(cudaMemcpyAsync(j_host, topj, (size_t)n * pairs * 4, cudaMemcpyDeviceToHost, s));
     if (qnorm2_host) RVCR_CUDA(cudaMemcpyAsync(qnorm2_host, qnorm, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (margin_host) {   // the margin the re-check kernel would use for each query
+        RVCR_TRY(h->ws_stage.reserve((size_t)n * 4 + 64));
+        RVCR_TRY(coarse_tc_margins(h, sp, qnorm, qres, res_stride, n, h->ws_stage.as<float>(), s));
+        RVCR_CUDA(cudaMemcpyAsync(margin_host, h->ws_stage.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    }
     RVCR_CUDA(cudaStreamSynchronize(s));
     if (cmax_out) *cmax_out = h->cent_norm_max;
-    return RVCR_OK;
+    return stream_leave(h, s);
 }
 
 }  // extern "C"

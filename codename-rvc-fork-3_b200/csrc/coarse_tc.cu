@@ -333,9 +333,15 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // ------------------------------------------------------------------- operand preparation ----
 
 // one warp per row: fp32 row -> bf16 operand row(s) of width kdim (= d, or 3d for the split form
-// [h | l | h] for queries / [h | h | l] for centroids) and the row's squared norm
+// [h | l | h] for queries / [h | h | l] for centroids), the row's squared norm, and the EXACT norms of what the
+// operand does not carry: res[r] = ||x - h||, and for the split form res[res_stride + r] = ||x - h - l||
+// (h = bf16(x), l = bf16(x - h); both differences are exact in fp32, so only the fp32 sum of squares rounds --
+// tc_margin() allows for it).  The re-check's margin is built from these, not from a worst-case ulp assumption:
+// bf16 round-to-nearest is off by up to 2^-8 relative per element (8 significant bits), and a row whose elements all
+// sit next to rounding midpoints reaches that.
 __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d, int split, int is_centroid,
-                                    __nv_bfloat16* __restrict__ out, float* __restrict__ norm2, float pad_norm) {
+                                    __nv_bfloat16* __restrict__ out, float* __restrict__ norm2, float pad_norm,
+                                    float* __restrict__ res, int64_t res_stride) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (r >= n_pad) return;
@@ -343,18 +349,28 @@ __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int6
     __nv_bfloat16* o = out + r * kdim;
     if (r >= n) {
         for (int c = lane; c < kdim; c += 32) o[c] = __float2bfloat16(0.f);
-        if (lane == 0 && norm2) norm2[r] = pad_norm;
+        if (lane == 0) {
+            if (norm2) norm2[r] = pad_norm;
+            if (res) {
+                res[r] = 0.f;
+                if (split) res[res_stride + r] = 0.f;
+            }
+        }
         return;
     }
     const float* xr = x + r * d;
-    float s = 0.f;
+    float s = 0.f, s1 = 0.f, s2 = 0.f;
     for (int c = lane; c < d; c += 32) {
         const float v = xr[c];
         s = fmaf(v, v, s);
         const __nv_bfloat16 h = __float2bfloat16(v);
         o[c] = h;
+        const float r1 = v - __bfloat162float(h);
+        s1 = fmaf(r1, r1, s1);
         if (split) {
-            const __nv_bfloat16 l = __float2bfloat16(v - __bfloat162float(h));
+            const __nv_bfloat16 l = __float2bfloat16(r1);
+            const float r2 = r1 - __bfloat162float(l);
+            s2 = fmaf(r2, r2, s2);
             if (is_centroid) {
                 o[d + c] = h;
                 o[2 * d + c] = l;
@@ -365,8 +381,18 @@ __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int6
         }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0 && norm2) norm2[r] = s;
+    for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    if (lane == 0) {
+        if (norm2) norm2[r] = s;
+        if (res) {
+            res[r] = sqrtf(s1);
+            if (split) res[res_stride + r] = sqrtf(s2);
+        }
+    }
 }
 
 // ---- e4m3 operands (coarse_mode 4) ----
@@ -406,7 +432,7 @@ __global__ void tc_maxabs_kernel(const float* __restrict__ x, int64_t n, unsigne
 // kept, and the re-check hands the query to the exact kernel.
 __global__ void tc_prep_rows_f8_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d, float fixed_scale,
                                        float other_scale, uint8_t* __restrict__ out, float* __restrict__ norm2,
-                                       float* __restrict__ kfac, float pad_norm) {
+                                       float* __restrict__ kfac, float pad_norm, float* __restrict__ res) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (r >= n_pad) return;
@@ -416,6 +442,7 @@ __global__ void tc_prep_rows_f8_kernel(const float* __restrict__ x, int64_t n, i
         if (lane == 0) {
             if (norm2) norm2[r] = pad_norm;
             if (kfac) kfac[r] = -2.f;
+            if (res) res[r] = 0.f;
         }
         return;
     }
@@ -440,10 +467,22 @@ __global__ void tc_prep_rows_f8_kernel(const float* __restrict__ x, int64_t n, i
         bad = true;
         scale = 1.f;
     }
-    for (int c = lane; c < d; c += 32)
-        o[c] = (uint8_t)__nv_cvt_float_to_fp8(xr[c] * scale, __NV_SATFINITE, __NV_E4M3);
+    // exact norm of what the e4m3 operand does not carry, in the row's scaled units: x * scale is exact (power of two),
+    // and the difference to its 4-significant-bit rounding is exact in fp32
+    float s1 = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        const float xs = xr[c] * scale;
+        const __nv_fp8_storage_t b = __nv_cvt_float_to_fp8(xs, __NV_SATFINITE, __NV_E4M3);
+        o[c] = (uint8_t)b;
+        const float back = __half2float(__half(__nv_cvt_fp8_to_halfraw(b, __NV_E4M3)));
+        const float r1 = xs - back;
+        s1 = fmaf(r1, r1, s1);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, off);
     if (lane == 0) {
         if (norm2) norm2[r] = s;
+        if (res) res[r] = bad ? __int_as_float(0x7fc00000) : sqrtf(s1) / scale;   // division by a power of two: exact
         if (kfac) {
             const double p = (double)scale * (double)other_scale;
             float k = (float)(-2.0 / p);
@@ -457,6 +496,7 @@ __global__ void tc_max_kernel(const float* __restrict__ v, int64_t n, unsigned i
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     float m = 0.f;
     if (i < n) m = v[i];
+    if (!(m == m)) m = INFINITY;   // a NaN row makes the maximum +inf (fmaxf would drop it): every margin becomes +inf
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order as uints
@@ -464,23 +504,53 @@ __global__ void tc_max_kernel(const float* __restrict__ v, int64_t n, unsigned i
 
 // ------------------------------------------------------------------------- exact re-check ----
 
+// The margin between two approximate values v(q, j) = ||c_j||^2 - 2 <q', c_j'> (primes: the low-precision operands):
+// with r = ||x - x'|| the EXACT residual norms written by the prep kernels (queries: per row; centroids: the maximum over
+// the set) and Cauchy-Schwarz,
+//     |<q, c> - <q', c'>|  =  |<q - q', c> + <q', c - c'>|  <=  r_q c_max + (|q| + r_q) r_c                 (bf16, e4m3)
+//     3-way bf16 split (h_q h_c + l_q h_c + h_q l_c is what the MMAs sum; rho1 = x - h, rho2 = x - h - l):
+//     |<q, c> - sum|       =  |<l_q, rho1_c> + <rho2_q, c> + <h_q, rho2_c>|  <=  (r1_q + r2_q) r1_c + r2_q c_max + (|q| + r1_q) r2_c
+// One v is off by twice that, two of them compared by four times.  On top: the accumulation of the products in the tensor
+// cores (acc_rel |q'||c'|, host-chosen per operand kind) and abs_rel (|q|^2 + c_max^2) for the fp32 roundings -- the norms
+// ||c||^2 ((d/32 + 5) ulps), the fma of the epilogue, the threshold sum, and the gap between a canonical fp32 distance and
+// the true one ((d/8 + 5) ulps of a distance <= 2 (|q|^2 + c_max^2), on both candidates).  1.002 covers the fp32 evaluation
+// of the residual norms and of this formula.  No ulp-size assumption about the rows is left: rows built to sit on bf16
+// rounding midpoints (relative error 2^-8 per element, twice the typical) just get a larger margin.
+struct TcMargin {
+    float cmax;      // max ||c||
+    float rc1, rc2;  // max ||c - c'|| (rc2: second-level residual of the 3-way split)
+    float acc_rel, abs_rel;
+    int split;       // 1 = 3-way bf16 split
+};
+__device__ __forceinline__ float tc_margin(const TcMargin& mp, float qn2, float r1, float r2) {
+    const float qn = sqrtf(qn2);
+    float e;
+    if (mp.split == 1) e = (r1 + r2) * mp.rc1 + r2 * mp.cmax + (qn + r1) * mp.rc2;
+    else e = r1 * mp.cmax + (qn + r1) * mp.rc1;
+    return 4.008f * e + mp.acc_rel * (qn + r1) * (mp.cmax + mp.rc1) + mp.abs_rel * (qn2 + mp.cmax * mp.cmax);
+}
+
+__global__ void tc_margin_kernel(const float* __restrict__ qnorm2, const float* __restrict__ qres, int64_t res_stride, int64_t n,
+                                 TcMargin mp, float* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tc_margin(mp, qnorm2[i], qres[i], mp.split == 1 ? qres[res_stride + i] : 0.f);
+}
+
 // One warp per query.  Gathers the nsplit x 8 approximate (v, j) pairs, keeps those with
 // v <= vmin + margin(q), evaluates their canonical fp32 distance (8 lanes per candidate, 4 candidates
 // per pass) and takes the argmin by (distance, id).  Flags the query for the exact kernel when a
 // split's 8th value is inside the margin (its candidate list may be truncated) or no candidate is
 // valid.
 __global__ void tc_recheck_kernel(const float* __restrict__ q, int64_t n, int d, const float* __restrict__ cent, int64_t nlist,
-                                  const float* __restrict__ qnorm2, float cmax, float rel_margin, float abs_margin,
+                                  const float* __restrict__ qnorm2, const float* __restrict__ qres, int64_t res_stride, TcMargin mp,
                                   const float* __restrict__ topv, const int* __restrict__ topj, int nsplit, int64_t list_begin,
                                   int32_t* __restrict__ list_out, float* __restrict__ dist_out, int32_t* __restrict__ fb_list,
                                   int32_t* __restrict__ counters /*[0] fallbacks of this call; [8..9], [10..11] u64 running totals*/) {
     const int lane = threadIdx.x & 31;
     const int64_t qi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (qi >= n) return;
-    const float qn2 = qnorm2[qi];
-    const float qn = sqrtf(qn2);
-    // |v_approx - v_true| <= margin/2 for every centroid  (DESIGN.md "Numerics")
-    const float margin = rel_margin * qn * cmax + abs_margin * (qn2 + cmax * cmax);
+    // |v_approx - v_true| <= margin / 2 for every centroid
+    const float margin = tc_margin(mp, qnorm2[qi], qres[qi], mp.split == 1 ? qres[res_stride + qi] : 0.f);
     const int total = nsplit * tc::TOPT;
     const float* tv = topv + qi * total;
     const int* tj = topj + qi * total;
@@ -492,7 +562,8 @@ __global__ void tc_recheck_kernel(const float* __restrict__ q, int64_t n, int d,
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, off));
     const float thr = vmin + margin;
-    bool overflow = !(vmin < __int_as_float(0x7f800000));   // no valid candidate at all (e.g. NaN query)
+    // no valid candidate at all (e.g. NaN query), or no finite margin (overflowing norms): the exact kernel decides
+    bool overflow = !(vmin < __int_as_float(0x7f800000)) || !(margin < __int_as_float(0x7f800000));
     // truncation check: the 8th (largest kept) value of any split inside the margin
     for (int s = lane; s < nsplit; s += 32) {
         const int j7 = tj[s * tc::TOPT + tc::TOPT - 1];
@@ -633,6 +704,20 @@ int make_tmap_u8(CUtensorMap* m, const void* base, int64_t rows, int kdim, int b
 
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
+// max over v[0..n) of non-negative floats (NaN counts as +inf), through slot `slot` of ws_misc; synchronises the stream
+int device_max(rvcr_index* h, const float* v, int64_t n, int slot, float* out, cudaStream_t s) {
+    unsigned int* mx = h->ws_misc.as<unsigned int>() + slot;
+    RVCR_CUDA(cudaMemsetAsync(mx, 0, 4, s));
+    tc_max_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(v, n, mx);
+    RVCR_CHECK_LAUNCH();
+    unsigned int bits = 0;
+    RVCR_CUDA(cudaMemcpyAsync(&bits, mx, 4, cudaMemcpyDeviceToHost, s));
+    RVCR_CUDA(cudaStreamSynchronize(s));
+    memcpy(out, &bits, 4);
+    count_launch(h);
+    return RVCR_OK;
+}
+
 // centroid operands are built once per (centroid set, split mode)
 int ensure_centroid_operands(rvcr_index* h, int split, cudaStream_t s) {
     if (h->cent_bf16 && h->cent_split == split) return RVCR_OK;
@@ -644,26 +729,30 @@ int ensure_centroid_operands(rvcr_index* h, int split, cudaStream_t s) {
     const int64_t npad = round_up(h->nlist, tc::BLOCK_N);
     RVCR_CUDA(cudaMalloc(&h->cent_bf16, (size_t)npad * kdim * 2));
     RVCR_CUDA(cudaMalloc(&h->cent_norm, (size_t)npad * 4));
+    float* res = nullptr;   // ||c - c'|| per centroid (two planes for the split form); only the maxima are kept
+    RVCR_CUDA(cudaMalloc(&res, (size_t)npad * 2 * 4));
     const int64_t thr = npad * 32;
     // pad centroids get ||c||^2 = +inf: v = +inf, never kept
     tc_prep_rows_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(h->cent, h->nlist, npad, h->d, split, 1,
                                                                        reinterpret_cast<__nv_bfloat16*>(h->cent_bf16),
-                                                                       h->cent_norm, INFINITY);
-    RVCR_CHECK_LAUNCH();
-    unsigned int* mx = h->ws_misc.as<unsigned int>() + 12;
-    RVCR_CUDA(cudaMemsetAsync(mx, 0, 4, s));
-    tc_max_kernel<<<(unsigned)((h->nlist + 255) / 256), 256, 0, s>>>(h->cent_norm, h->nlist, mx);
-    RVCR_CHECK_LAUNCH();
-    unsigned int bits = 0;
-    RVCR_CUDA(cudaMemcpyAsync(&bits, mx, 4, cudaMemcpyDeviceToHost, s));
-    RVCR_CUDA(cudaStreamSynchronize(s));
-    float m2;
-    memcpy(&m2, &bits, 4);
+                                                                       h->cent_norm, INFINITY, res, npad);
+    int rc = cudaGetLastError() == cudaSuccess ? RVCR_OK : RVCR_ERR_CUDA;
+    float m2 = 0.f, r1 = 0.f, r2 = 0.f;
+    if (rc == RVCR_OK) rc = device_max(h, h->cent_norm, h->nlist, 12, &m2, s);
+    if (rc == RVCR_OK) rc = device_max(h, res, h->nlist, 60, &r1, s);
+    if (rc == RVCR_OK && split) rc = device_max(h, res + npad, h->nlist, 61, &r2, s);
+    cudaFree(res);
+    if (rc != RVCR_OK) {
+        set_error("building the tensor-core centroid operands failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return rc;
+    }
     h->cent_norm_max = sqrtf(m2);
+    h->cent_res1 = r1;
+    h->cent_res2 = r2;
     h->cent_pad = npad;
     h->cent_kdim = kdim;
     h->cent_split = split;
-    count_launch(h, 2);
+    count_launch(h);
     return RVCR_OK;
 }
 
@@ -686,11 +775,21 @@ int ensure_centroid_operands_f8(rvcr_index* h, cudaStream_t s) {
         return RVCR_ERR_UNSUPPORTED;
     }
     RVCR_CUDA(cudaMalloc(&h->cent_f8, (size_t)h->cent_pad * h->d));
+    float* res = nullptr;
+    RVCR_CUDA(cudaMalloc(&res, (size_t)h->cent_pad * 4));
     const int64_t thr = h->cent_pad * 32;
     tc_prep_rows_f8_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(h->cent, h->nlist, h->cent_pad, h->d, sc, 1.f,
-                                                                          reinterpret_cast<uint8_t*>(h->cent_f8), nullptr, nullptr, 0.f);
-    RVCR_CHECK_LAUNCH();
+                                                                          reinterpret_cast<uint8_t*>(h->cent_f8), nullptr, nullptr, 0.f, res);
+    int rc = cudaGetLastError() == cudaSuccess ? RVCR_OK : RVCR_ERR_CUDA;
+    float r1 = 0.f;
+    if (rc == RVCR_OK) rc = device_max(h, res, h->nlist, 62, &r1, s);
+    cudaFree(res);
+    if (rc != RVCR_OK) {
+        set_error("building the e4m3 centroid operand failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return rc;
+    }
     h->cent_f8_scale = sc;
+    h->cent_f8_res = r1;
     count_launch(h, 2);
     return RVCR_OK;
 }
@@ -742,7 +841,7 @@ int coarse_tc_invalidate(rvcr_index* h) {
 // Approximate top-8 nearest centroids per (query, split) on the tensor cores.
 // Outputs (device, owned by the handle scratch): topv/topj [n_pad][nsplit][8]; returns nsplit.
 int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int cluster, float** topv_out, int** topj_out,
-                   int* nsplit_out, float** qnorm_out, cudaStream_t s) {
+                   int* nsplit_out, float** qnorm_out, float** qres_out, int64_t* res_stride_out, cudaStream_t s) {
     // split: 0 = bf16, 1 = bf16 3-way split along K, 2 = e4m3 operands (coarse_mode 4)
     const bool f8 = split == 2;
     const int kelems = f8 ? 2 * tc::BLOCK_K : tc::BLOCK_K;   // elements per 128-byte k-block
@@ -765,15 +864,18 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
             RVCR_TRY(h->ws_tc0.reserve((size_t)n_pad * kdim));   // e4m3 queries, each row with its own power-of-two scale
             RVCR_TRY(h->ws_tc1.reserve((size_t)n_pad * 4));      // ||q||^2
             RVCR_TRY(h->ws_tc4.reserve((size_t)n_pad * 4));      // -2 / (s_q s_c) per query
+            RVCR_TRY(h->ws_tc5.reserve((size_t)n_pad * 2 * 4));  // ||q - q'||
             tc_prep_rows_f8_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, n_pad, h->d, 0.f, h->cent_f8_scale,
                                                                                   h->ws_tc0.as<uint8_t>(), h->ws_tc1.as<float>(),
-                                                                                  h->ws_tc4.as<float>(), 0.f);
+                                                                                  h->ws_tc4.as<float>(), 0.f, h->ws_tc5.as<float>());
         } else {
         RVCR_TRY(ensure_centroid_operands(h, split, s));
         RVCR_TRY(h->ws_tc0.reserve((size_t)n_pad * kdim * 2));   // bf16 queries
         RVCR_TRY(h->ws_tc1.reserve((size_t)n_pad * 4));          // ||q||^2
+        RVCR_TRY(h->ws_tc5.reserve((size_t)n_pad * 2 * 4));      // ||q - q'|| (second plane: 3-way split)
         tc_prep_rows_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, n_pad, h->d, split, 0,
-                                                                           h->ws_tc0.as<__nv_bfloat16>(), h->ws_tc1.as<float>(), 0.f);
+                                                                           h->ws_tc0.as<__nv_bfloat16>(), h->ws_tc1.as<float>(), 0.f,
+                                                                           h->ws_tc5.as<float>(), n_pad);
         }
         RVCR_CHECK_LAUNCH();
         count_launch(h);
@@ -833,6 +935,35 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
     *topj_out = h->ws_tc3.as<int>();
     *nsplit_out = nsplit;
     *qnorm_out = h->ws_tc1.as<float>();
+    *qres_out = h->ws_tc5.as<float>();
+    *res_stride_out = n_pad;
+    return RVCR_OK;
+}
+
+// the margin parameters of the current centroid operands (split: 0 bf16, 1 3-way bf16 split, 2 e4m3)
+static TcMargin make_margin(const rvcr_index* h, int split) {
+    TcMargin mp;
+    const int d = h->d;
+    const int kdim = split == 1 ? 3 * d : d;
+    mp.cmax = h->cent_norm_max;
+    mp.rc1 = split == 2 ? h->cent_f8_res : h->cent_res1;
+    mp.rc2 = split == 1 ? h->cent_res2 : 0.f;
+    // products of bf16 / e4m3 operands are exact in fp32; their accumulation in TMEM is allowed 2 fp32 ulps of |q'||c'| per
+    // product (x 2 for v = |c|^2 - 2 <.,.>, x 2 for two values compared).  e4m3: the same, but never less than 2^-9 --
+    // kind::f8f6f4 is not documented to keep full fp32 accumulation, and against a margin of ~0.2 |q||c| the allowance is free
+    mp.acc_rel = 1.02f * (float)kdim / 2097152.f;
+    if (split == 2 && mp.acc_rel < 1.f / 512.f) mp.acc_rel = 1.f / 512.f;
+    // fp32 roundings, in ulps (2^-24) of |q|^2 + c_max^2: canonical-vs-true distance 2 x 2 x (d/8 + 5), norms 2 x (d/32 + 5),
+    // epilogue fma + threshold sum 2 x 4
+    mp.abs_rel = 1.01f * (float)(4 * (d / 8 + 5) + 2 * (d / 32 + 5) + 8) / 16777216.f;
+    mp.split = split;
+    return mp;
+}
+
+int coarse_tc_margins(rvcr_index* h, int split, const float* qnorm2, const float* qres, int64_t res_stride, int64_t n,
+                      float* out_dev, cudaStream_t s) {
+    tc_margin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(qnorm2, qres, res_stride, n, make_margin(h, split), out_dev);
+    RVCR_CHECK_LAUNCH();
     return RVCR_OK;
 }
 
@@ -881,29 +1012,21 @@ int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float
 
 static int coarse_tc_split(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out, int split, cudaStream_t s) {
     const int cluster = h->opt.tc_cluster == 1 ? 1 : 2;
-    float *topv, *qnorm;
+    float *topv, *qnorm, *qres;
     int* topj;
     int nsplit;
-    RVCR_TRY(coarse_tc_top8(h, q, n, split, cluster, &topv, &topj, &nsplit, &qnorm, s));
+    int64_t res_stride;
+    RVCR_TRY(coarse_tc_top8(h, q, n, split, cluster, &topv, &topj, &nsplit, &qnorm, &qres, &res_stride, s));
     PhaseTimer pt(h, RVCR_PHASE_COARSE_RECHECK, s);
-    // error margin between two approximate values (see DESIGN.md "Numerics"):
-    //   bf16 rounding of both operands:  2 * 2 * 2^-8 |q||c|          (1-way)   /  2 * 2 * 3 * 2^-18 |q||c| (3-way split)
-    //   fp32 accumulation over kdim products and the final fma: kdim * 2^-21 |q||c| + 2^-20 (|q|^2 + |c|^2)
-    //   e4m3 (coarse_mode 4): rounding to 4 significant bits, 2^-4 relative per element; elements below the normal range
-    //   add at most sqrt(d) 2^-10 / s <= 2.2e-4 of the row maximum (s max >= 128, d <= 1024), saturation cannot happen
-    //   (s max < 256 <= 448):  |<q,c> - <q8,c8>| <= (0.0628 + 1.0628 * 0.0628) |q| c_max = 0.1296 |q| c_max,
-    //   times 2 (v = |c|^2 - 2 <q,c>) times 2 (two approximate values compared) = 0.5184 -> 0.53
-    const int kdim = split == 1 ? 3 * h->d : h->d;
-    const float rel = (split == 2 ? 0.53f : split == 1 ? 12.f * 1.01f / 262144.f : 1.01f / 64.f) + (float)kdim / 2097152.f;
-    const float absm = 1.f / 1048576.f;
+    // error margin between two approximate values: tc_margin(), from the exact residual norms of both operands
     RVCR_TRY(h->ws_stage.reserve((size_t)n * 4 + 64));
     int32_t* fb_list = h->ws_stage.as<int32_t>();
     int32_t* counters = h->ws_misc.as<int32_t>() + 16;   // [16] fallbacks of this call; [24..27] running totals
     RVCR_CUDA(cudaMemsetAsync(counters, 0, 4, s));
     const int64_t thr = n * 32;
-    tc_recheck_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, h->d, h->cent, h->nlist, qnorm, h->cent_norm_max, rel,
-                                                                     absm, topv, topj, nsplit, 0, list_out, dist_out,
-                                                                     fb_list, counters);
+    tc_recheck_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, h->d, h->cent, h->nlist, qnorm, qres, res_stride,
+                                                                     make_margin(h, split), topv, topj, nsplit, 0, list_out,
+                                                                     dist_out, fb_list, counters);
     RVCR_CHECK_LAUNCH();
     count_launch(h);
     RVCR_TRY(coarse_exact_selected(h, q, n, fb_list, counters, list_out, dist_out, s));

@@ -143,6 +143,9 @@ struct rvcr_index {
     void* cent_bf16 = nullptr;         // nlist_pad x kdim bf16, K-major
     float* cent_norm = nullptr;        // nlist_pad fp32 ||c||^2 (pad rows = +inf)
     float cent_norm_max = 0.f;         // max ||c||
+    float cent_res1 = 0.f;             // max ||c - bf16(c)||                     (exact residual norms: the re-check's
+    float cent_res2 = 0.f;             // max ||c - bf16(c) - bf16(c - bf16(c))||  margin is built from these)
+    float cent_f8_res = 0.f;           // max ||c - e4m3(c s_c) / s_c||
     int64_t cent_pad = 0;
     int cent_kdim = 0;                 // d (mode 2) or 3d (mode 3)
     int cent_split = 0;
@@ -179,7 +182,7 @@ struct rvcr_index {
     bool scan_fb_dirty = false;
 
     rvcr::DevBuf ws_assign, ws_keys, ws_vals, ws_keys2, ws_vals2, ws_cub, ws_items, ws_flags, ws_misc,
-        ws_D, ws_P, ws_I, ws_best, ws_q, ws_tc0, ws_tc1, ws_tc2, ws_tc3, ws_tc4, ws_stage;
+        ws_D, ws_P, ws_I, ws_best, ws_q, ws_tc0, ws_tc1, ws_tc2, ws_tc3, ws_tc4, ws_tc5, ws_stage;
     cudaStream_t copy_stream = nullptr;          // host-buffer entry points: H2D chunks overlap the coarse step
     cudaStream_t out_stream = nullptr;           // ... and blended rows stream out while later lists are scanned
     std::vector<cudaEvent_t> copy_events;
@@ -220,7 +223,9 @@ int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float
               cudaStream_t s);
 bool coarse_tc_available();
 int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int cluster, float** topv_out, int** topj_out,
-                   int* nsplit_out, float** qnorm_out, cudaStream_t s);
+                   int* nsplit_out, float** qnorm_out, float** qres_out, int64_t* res_stride_out, cudaStream_t s);
+int coarse_tc_margins(rvcr_index* h, int split, const float* qnorm2, const float* qres, int64_t res_stride, int64_t n,
+                      float* out_dev, cudaStream_t s);
 int coarse_tc_invalidate(rvcr_index* h);
 // scan_topk.cu
 int group_queries(rvcr_index* h, const int32_t* assign, int64_t n, bool only_local, cudaStream_t s);

@@ -281,10 +281,13 @@ RVCR_API int rvcr_get_phase_ms(rvcr_index* h, float* ms_out);
 /* Diagnostics for tests: run only the tensor-core stage of the coarse quantizer (coarse_tc.cu) and
  * return its raw output -- per query, `*pairs_out` = 8 * (number of centroid splits) approximate
  * (v = ||c||^2 - 2<q,c>, centroid id) pairs -- to host buffers of capacity cap_pairs per query,
- * plus ||q||^2 per query and max ||c||.  split: 0 = bf16, 1 = 3-way split bf16, 2 = e4m3; cluster: 1 | 2. */
+ * plus ||q||^2 per query, max ||c||, and (margin_host, n floats, nullable) the margin the exact re-check uses for each
+ * query: two approximate values further apart than that are ordered like the true distances (built from the exact
+ * norms of what the low-precision operands drop, coarse_tc.cu tc_margin).  split: 0 = bf16, 1 = 3-way split bf16,
+ * 2 = e4m3; cluster: 1 | 2. */
 RVCR_API int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t split, int32_t cluster,
                                   int32_t cap_pairs, float* v_host, int32_t* j_host, int32_t* pairs_out,
-                                  float* qnorm2_host, float* cmax_out, void* stream);
+                                  float* qnorm2_host, float* cmax_out, float* margin_host, void* stream);
 
 /* Host-only pieces of rvcr_index_train, exposed so that they can be checked without a GPU: faiss rand_perm
  * (identity, then swap(perm[i], perm[i + mt() % (n - i)]) with std::mt19937(seed)) and faiss split_clusters
