@@ -189,6 +189,7 @@ def run_reference_arm(args, cfg):
         return
     import oracle
     import torch
+    threads, blas = use_all_host_threads()
     N, d, nq, nlist = cfg
     sample = min(nq, args.cpu_sample)
     t0 = time.time()
@@ -203,7 +204,7 @@ def run_reference_arm(args, cfg):
             times.append(dt)
     sec = float(np.mean(times))
     val = sample / sec
-    cores = len(os.sched_getaffinity(0))
+    cores = threads
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -213,7 +214,7 @@ def run_reference_arm(args, cfg):
                              "sample": f"{sample} of {nq} query frames per step against all {nlist} centroids and the "
                                        f"{int((np.diff(list_off) > 0).sum())} lists they probe (avg {N / nlist:.0f} rows); "
                                        f"oracle port of faiss 1.7.3 + numpy (faiss itself is not installable here); "
-                                       f"omp_threads={oracle.num_threads()} torch_threads={torch.get_num_threads()} setup {setup_s:.0f}s"},
+                                       f"omp_threads={oracle.num_threads()} torch_threads={torch.get_num_threads()} blas={blas} setup {setup_s:.0f}s"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -328,28 +329,132 @@ def build_roofline(phase_acc, coarse_on_tensor_cores, pk, *, nst, n_home, owned_
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 
+def use_all_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would time the CPU legs on one core (round 1:
+    the per-N reference arm ran 3.5 x slower under the launcher than alone).  Set every pool explicitly to the cores this
+    process may use: OpenMP of the C restatement, the BLAS behind numpy (sgemm coarse step) and torch."""
+    n = len(os.sched_getaffinity(0))
+    import oracle
+    import torch
+    oracle.set_num_threads(n)
+    torch.set_num_threads(n)
+    blas = None
+    try:
+        import threadpoolctl
+        global _BLAS_LIMIT                                     # keep the limiter object alive
+        _BLAS_LIMIT = threadpoolctl.threadpool_limits(limits=n)
+        blas = [(i.get("internal_api"), i.get("num_threads")) for i in threadpoolctl.threadpool_info()]
+    except Exception:
+        pass
+    return n, blas
+
+
+def make_row_fetcher(vecs, row_bounds, rank, world, dist):
+    """Sharded setup helper: fetch(gpos) -> the stored rows at global list-ordered positions gpos (int64 device tensor),
+    wherever they live: positions are routed to the owning rank with all_to_all, gathered there, routed back.  Collective
+    (every rank calls it once per use)."""
+    import torch
+
+    def fetch(gpos):
+        dev = gpos.device
+        bounds = torch.as_tensor(row_bounds[1:-1], dtype=torch.int64, device=dev)
+        owner = torch.bucketize(gpos, bounds, right=True)
+        order = torch.argsort(owner, stable=True)
+        send_counts = torch.bincount(owner, minlength=world)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts)
+        both = torch.stack([send_counts, recv_counts]).cpu()
+        ss, rs = [int(x) for x in both[0]], [int(x) for x in both[1]]
+        want = torch.empty(sum(rs), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(want, gpos[order].contiguous(), rs, ss)
+        rows = vecs[want - int(row_bounds[rank])]
+        back = torch.empty((gpos.numel(), vecs.shape[1]), dtype=vecs.dtype, device=dev)
+        dist.all_to_all_single(back, rows, ss, rs)
+        out = torch.empty_like(back)
+        out[order] = back
+        return out
+    return fetch
+
+
+def stage_probed_lists(index, probed, ranges, rank, world, nlist, d, dev, dist):
+    """CPU legs: the rows of the lists in `probed` (sorted global list ids, known to every rank), from whichever shard
+    stores them, assembled on rank 0's host as (sub_off (nlist + 1,), sub_vecs).  Other ranks return (None, None)."""
+    import torch
+    vecs_d, _, offs_d, _ = index.device_views()
+    offs_h = offs_d.cpu().numpy()
+    lo, hi = ranges[rank]
+    mine = probed[(probed >= lo) & (probed < hi)]
+    sz_mine = offs_h[mine + 1] - offs_h[mine]
+    if len(mine):
+        idx = torch.cat([torch.arange(int(offs_h[l]), int(offs_h[l + 1]), device=dev) for l in mine]) if sz_mine.sum() else \
+            torch.empty(0, dtype=torch.int64, device=dev)
+        rows = vecs_d[idx]
+    else:
+        rows = torch.empty((0, d), dtype=torch.float32, device=dev)
+    if world == 1:
+        sz = np.zeros(nlist, np.int64)
+        sz[mine] = sz_mine
+        sub_off = np.zeros(nlist + 1, np.int64)
+        np.cumsum(sz, out=sub_off[1:])
+        return sub_off, rows.cpu().numpy()
+    # sizes of every probed list, in list order (lists are contiguous per rank, so rank order == list order)
+    cnt = torch.tensor([len(mine), int(sz_mine.sum())], dtype=torch.int64, device=dev)
+    cnts = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    cnts = [(int(c[0]), int(c[1])) for c in cnts]
+    szt = torch.as_tensor(sz_mine, dtype=torch.int64, device=dev)
+    if rank == 0:
+        parts_sz, parts_rows = [sz_mine], [rows.cpu().numpy()]
+        for r in range(1, world):
+            t = torch.empty(cnts[r][0], dtype=torch.int64, device=dev)
+            if cnts[r][0]:
+                dist.recv(t, src=r)
+            parts_sz.append(t.cpu().numpy())
+            got = torch.empty((cnts[r][1], d), dtype=torch.float32, device=dev)
+            if cnts[r][1]:
+                dist.recv(got, src=r)
+            parts_rows.append(got.cpu().numpy())
+            del got
+        sz = np.zeros(nlist, np.int64)
+        sz[probed] = np.concatenate(parts_sz)
+        sub_off = np.zeros(nlist + 1, np.int64)
+        np.cumsum(sz, out=sub_off[1:])
+        return sub_off, np.concatenate(parts_rows)
+    if cnts[rank][0]:
+        dist.send(szt, dst=0)
+    if cnts[rank][1]:
+        dist.send(rows, dst=0)
+    return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C5", choices=["C1", "C2", "C3", "C5"])
+    ap.add_argument("--workload", default="C5", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--coarse-mode", type=int, default=0)
-    ap.add_argument("--coarse-f8-auto", type=int, default=0, help="1 = let the auto coarse mode probe e4m3 operands (experimental)")
-    ap.add_argument("--scan-impl", type=int, default=0, help="0 = library default (auto by batch size), 5 = tcgen05 scan, 1-4 exact FFMA scans, 6 = experimental fused scan + re-check")
+    ap.add_argument("--coarse-f8-auto", type=int, default=-1, help="1 / 0 = let / do not let the auto coarse mode probe e4m3 operands (-1 = library default)")
+    ap.add_argument("--scan-impl", type=int, default=0, help="0 = library default (auto by batch size), 5 = tcgen05 scan, 1-4 exact FFMA scans")
     ap.add_argument("--tc-resident", type=int, default=-1, help="coarse kernel: resident query k-blocks (0/8/9/10; -1 = library default)")
     ap.add_argument("--fused-blend", type=int, default=-1, help="1 = re-check kernel also blends (default), 0 = separate gather_blend kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: use the NCCL all-to-all transport instead of peer memory")
+    ap.add_argument("--near-frac", type=float, default=0.8, help="fraction of queries that are a stored row + N(0, 0.05^2) (SURVEY 8d)")
+    ap.add_argument("--query-skew", type=float, default=0.75, help="Zipf exponent of the extra skewed-query measurement (0 = skip it)")
+    ap.add_argument("--ring", type=int, default=4, help="input buffers kept on the device (refilled between steps, outside the events)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
 
     synth = importlib.import_module(PKG + ".synth")
     cfg = synth.CONFIGS[args.workload]
+    if args.workload == "C4":
+        import bench_build
+        return bench_build.main(args, cfg)
     if args.impl == "reference":
         run_reference_arm(args, cfg)
         return
@@ -370,7 +475,7 @@ def main():
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # the launcher's own setting (e.g. INFO for the rank check) wins
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- build this rank's shard (by construction, on the device) --------------------------------
@@ -378,23 +483,35 @@ def main():
     sizes = synth.list_sizes(N, nlist)
     ranges = synth.shard_ranges(sizes, world)
     lo, hi = ranges[rank]
+    offs_all = np.concatenate([[0], np.cumsum(sizes)])
+    row_bounds = [int(offs_all[r[0]]) for r in ranges] + [int(offs_all[-1])]
     cent_all = synth.all_centroids(nlist, d, dev)
     index = rvcr.index_factory(d, f"IVF{nlist},Flat", device=local_rank)
     index.nprobe = 1
     synth.fill_index_by_construction(index, cent_all, sizes, N, list_range=(lo, hi))
     index.set_option("coarse_mode", args.coarse_mode)
     index.set_option("scan_impl", args.scan_impl)
-    if args.coarse_f8_auto:
-        index.set_option("coarse_f8_auto", 1)
+    if args.coarse_f8_auto >= 0:
+        index.set_option("coarse_f8_auto", args.coarse_f8_auto)
     if args.tc_resident >= 0:
         index.set_option("tc_resident", args.tc_resident)
     if args.fused_blend >= 0:
         index.set_option("fused_blend", args.fused_blend)
     index.set_option("profile", 1)
     nq_lo, nq_hi = nq * rank // world, nq * (rank + 1) // world
-    q_home = synth.device_queries(cent_all, nq, q_range=(nq_lo, nq_hi))
     n_home = nq_hi - nq_lo
-    del cent_all
+    vecs_view = index.device_views()[0]
+    fetch = make_row_fetcher(vecs_view, row_bounds, rank, world, dist) if world > 1 else None
+
+    def make_queries(zipf):
+        """this rank's home queries: 80 % stored row + N(0, 0.05^2), 20 % fresh mixture samples"""
+        if args.near_frac > 0:
+            q, near = synth.device_queries(cent_all, nq, q_range=(nq_lo, nq_hi), zipf=zipf, near_frac=args.near_frac, sizes=sizes)
+            synth.apply_near_rows(q, near, vecs_view, row_base=row_bounds[rank], fetch=fetch)
+            return q
+        return synth.device_queries(cent_all, nq, q_range=(nq_lo, nq_hi), zipf=zipf)
+
+    q_home = make_queries(0.0)
     torch.cuda.synchronize()
     setup_s = time.time() - t_setup
 
@@ -402,21 +519,23 @@ def main():
     peer = None
     transport = None
     total_steps = args.warmup + args.steps
+    R = max(1, min(args.ring, total_steps))
+    SLOT_SCRATCH, SLOT_E2E = R, R + 1
     if world > 1:
         sh = sharded.ShardedIndex(sharded.CudaShardBackend(index))
         transport = "nccl all-to-all (dispatch + combine)"
         if not args.no_peer:
             try:                                                   # collective: raises on every rank or on none
-                peer = sh.enable_peer((total_steps + 2) * n_home + 16, d)
-                transport = "peer memory over NVLink (cudaIpc): owner pulls rows, blend epilogue pushes them home"
+                peer = sh.enable_peer((R + 2) * n_home + 16, d)
+                transport = sh.transport_name()
             except Exception as ex:
                 transport += f"; peer memory unavailable: {str(ex)[:160]}"
 
-    def fresh(slot):
-        """a fresh (un-blended) copy of this rank's queries; inside the peer buffer when that transport is on"""
+    def slot(i):
+        """(n_home, d) device buffer number i; inside the peer buffer when that transport is on"""
         if peer is None:
-            return q_home.clone()
-        return peer.rows(n_home, slot * n_home).copy_(q_home)
+            return torch.empty((n_home, d), dtype=torch.float32, device=dev)
+        return peer.rows(n_home, i * n_home)
 
     def step(buf):
         if sh is None:
@@ -429,61 +548,95 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    bufs = [fresh(i) for i in range(total_steps)]             # every step gets a fresh (un-blended) input
+    def timed_steps(src, nsteps, warm, keep_first=0):
+        """`warm` untimed + `nsteps` timed steps over the ring, every step on a fresh (un-blended) copy of `src`.  The
+        steps are enqueued back to back; each is bracketed by its own CUDA events and the ring slot it used is refilled
+        right after its closing event, so the refill copies are outside every timed interval.  Returns (sum of the step
+        times in ms, max over ranks; the first `keep_first` blended rows of the first timed step)."""
+        for b in ring:
+            b.copy_(src)
+        barrier()
+        for i in range(warm):
+            step(ring[i % R])
+            ring[i % R].copy_(src)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        kept = None
+        l0 = index.stats()["kernels_launched"]
+        barrier()
+        sampler.mark_begin()
+        for i in range(nsteps):
+            b = ring[(warm + i) % R]
+            ev[i][0].record()
+            step(b)
+            ev[i][1].record()
+            if i == 0 and keep_first:
+                kept = b[:keep_first].clone()
+            b.copy_(src)
+        barrier()
+        sampler.mark_end()
+        ms = float(sum(a.elapsed_time(b) for a, b in ev))
+        nl = index.stats()["kernels_launched"] - l0            # librvcr kernels launched inside the timed steps (this rank)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            lt = torch.tensor([nl], device=dev, dtype=torch.int64)
+            dist.all_reduce(lt)
+            nl = int(lt.item())
+        return ms, kept, nl
+
+    ring = [slot(i) for i in range(R)]
+    scratch = slot(SLOT_SCRATCH)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    step(bufs[0])                                             # first call: lazy setup (row norms, tensor maps, scratch)
+    scratch.copy_(q_home)
+    step(scratch)                                             # first call: lazy setup (row norms, tensor maps, scratch)
     barrier()
     time.sleep(0.25)                                          # let nvidia-smi deliver its first samples
-    for i in range(1, args.warmup):
-        step(bufs[i])
-    barrier()
-    launches0 = index.stats()["kernels_launched"]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    sampler.mark_begin()
-    e0.record()
-    for i in range(args.steps):
-        step(bufs[args.warmup + i])
-    e1.record()
-    barrier()
-    sampler.mark_end()
+    keep = min(n_home, args.cpu_sample) if rank == 0 else 0
+    ms_total, gpu_rows_dev, launches = timed_steps(q_home, args.steps, args.warmup - 1, keep_first=keep)
     clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    launches = index.stats()["kernels_launched"] - launches0
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
-        dist.all_reduce(lt)
-        launches = int(lt.item())
     ms_step = ms_total / args.steps
     value = nq / (ms_step * 1e-3)
-    result_check = bufs[args.warmup][:4].cpu().numpy()
-    gpu_rows = None                                           # blended rows of the first timed step, for the parity sample
-    try:
-        if world == 1 and not args.no_cpu_baseline:
-            gpu_rows = bufs[args.warmup][:min(n_home, args.cpu_sample)].cpu().numpy()
-    except Exception:
-        gpu_rows = None
-    del bufs
+    gpu_rows = gpu_rows_dev.cpu().numpy() if gpu_rows_dev is not None else None
+    result_check = gpu_rows[:4] if gpu_rows is not None else None
 
     # ---- per-phase device times (separate pass, same inputs) for the roofline --------------------
     phase_acc = {}
     reps = max(1, min(args.steps, 3))
     for _ in range(reps):
-        b = fresh(total_steps)
-        step(b)
+        scratch.copy_(q_home)
+        step(scratch)
         torch.cuda.synchronize()
         for k, v in index.phase_ms().items():
             phase_acc[k] = phase_acc.get(k, 0.0) + v / reps
-        del b
     st = index.stats()
-    coarse_e4m3 = args.coarse_mode == 4 or (args.coarse_f8_auto and index.get_option("coarse_f8_decision") == 1)
+    coarse_e4m3 = args.coarse_mode == 4 or index.get_option("coarse_f8_decision") == 1
     roof, dominant = build_roofline(phase_acc, st["coarse_tc_queries"] > 0, peaks(), nst=int(sizes[lo:hi].sum()), n_home=n_home,
                                     owned_q=nq / world, nlist=nlist, d=d, scan_impl=args.scan_impl, workload=args.workload,
                                     world=world, coarse_e4m3=coarse_e4m3)
+
+    # ---- the same steps under a skewed query mass (Zipf over lists): what real clips do to the shard balance ----
+    skewed = None
+    if args.query_skew > 0:
+        try:
+            q_skew = make_queries(args.query_skew)
+            sk_steps = max(1, min(args.steps, 3))
+            sampler = ClockSampler(local_rank)                     # not started: mark_begin / mark_end are no-ops on the record
+            ms_sk, _, _ = timed_steps(q_skew, sk_steps, 1)
+            a_sk = index.assign(q_skew[:min(n_home, 65536)])[0]
+            own = torch.bucketize(a_sk, torch.as_tensor([r[0] for r in ranges[1:]], dtype=torch.int32, device=dev), right=True)
+            cnt = torch.bincount(own.clamp_(min=0), minlength=world).to(torch.float64)
+            if world > 1:
+                dist.all_reduce(cnt)
+            skewed = {"zipf_exponent": args.query_skew, "value": nq / (ms_sk / sk_steps * 1e-3), "unit": UNIT,
+                      "ms_per_step": ms_sk / sk_steps, "steps": sk_steps,
+                      "owner_load_max_over_mean": float(cnt.max() / cnt.mean()) if world > 1 else 1.0,
+                      "note": "same index, query lists drawn with mass ~ (rank + 1)^-s over a fixed random ranking of the lists"}
+            del q_skew
+        except Exception as ex:                                    # pragma: no cover
+            skewed = {"error": repr(ex)[:200]}
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region --------------
     e2e = None
@@ -500,7 +653,7 @@ def main():
                 index.retrieve_blend_host_(host.numpy(), INDEX_RATE)     # H2D, search+blend, D2H, sync
             else:
                 sh.retrieve_blend_host_(host, INDEX_RATE,                 # chunked H2D under the coarse step, D2H, sync
-                                        device_rows=peer.rows(n_home, (total_steps + 1) * n_home) if peer is not None else None)
+                                        device_rows=slot(SLOT_E2E) if peer is not None else None)
             barrier()
             if it > 0:
                 times.append(time.perf_counter() - t0)
@@ -514,47 +667,57 @@ def main():
                if sh is None else "ShardedIndex.retrieve_blend_host_, pinned host buffers per rank"}
         del host, src
 
-    # ---- CPU baseline on rank 0 (N = 1 only): bounded sample of the same workload ------------------
+    # ---- CPU legs on rank 0: the parity sample at every N, the timed CPU baseline at N = 1 only ----------
     cpu = None
     parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    parity_str = None
+    if not args.no_cpu_baseline:
         try:                                                   # the bench line must survive a failing baseline leg
             import oracle
-            sample = min(nq, args.cpu_sample)
-            qs = q_home[:sample].cpu().numpy()
-            vecs_d, ids_d, offs_d, cent_d = index.device_views()
-            cent_h = cent_d.cpu().numpy()
-            a, _ = oracle.coarse_assign_blas(qs, cent_h)                 # untimed: which lists to stage on the host
-            probed = np.unique(a[a >= 0])
-            offs_h = offs_d.cpu().numpy()
-            sz = np.zeros(nlist, np.int64)
-            sz[probed] = offs_h[probed + 1] - offs_h[probed]
-            sub_off = np.zeros(nlist + 1, np.int64)
-            np.cumsum(sz, out=sub_off[1:])
-            sub_vecs = np.empty((int(sub_off[-1]), d), np.float32)
-            for l in probed:
-                sub_vecs[sub_off[l]:sub_off[l + 1]] = vecs_d[offs_h[l]:offs_h[l + 1]].cpu().numpy()
-            sub_ids = np.arange(len(sub_vecs), dtype=np.int64)
-            cpu_path(oracle, qs[:256], cent_h, sub_off, sub_vecs, sub_ids)      # warm-up (thread pools, page faults)
-            t0 = time.perf_counter()
-            passes = 0
-            while True:                                                         # about 10 s of CPU work, at most 8 passes
-                out_cpu, _ = cpu_path(oracle, qs, cent_h, sub_off, sub_vecs, sub_ids)
-                passes += 1
-                if time.perf_counter() - t0 >= 10.0 or passes >= 8:
-                    break
-            total_s = time.perf_counter() - t0
-            sec = total_s / passes
-            import torch as _t
-            cpu = {"value": sample / sec, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
-                   "sample": f"first {sample} of {nq} query frames of this workload, all {nlist} centroids, the {len(probed)} lists "
-                             f"they probe staged on the host; {passes} passes, {total_s:.1f} s of CPU work; oracle port of faiss "
-                             f"1.7.3 + numpy (omp_threads={oracle.num_threads()}, torch_threads={_t.get_num_threads()})"}
-            parity = parity_sample(gpu_rows, out_cpu)
-            del sub_vecs
+            sample = min(n_home if world > 1 else nq, args.cpu_sample)
+            cent_h = index.device_views()[3].cpu().numpy()
+            probed_t = torch.zeros(sample + 1, dtype=torch.int64, device=dev)
+            if rank == 0:
+                threads, blas = use_all_host_threads()
+                qs = q_home[:sample].cpu().numpy()
+                a, _ = oracle.coarse_assign_blas(qs, cent_h)                 # untimed: which lists to stage on the host
+                probed = np.unique(a[a >= 0])
+                probed_t[0] = len(probed)
+                probed_t[1:1 + len(probed)] = torch.as_tensor(probed, device=dev)
+            if world > 1:
+                dist.broadcast(probed_t, src=0)
+            probed = probed_t[1:1 + int(probed_t[0])].cpu().numpy()
+            sub_off, sub_vecs = stage_probed_lists(index, probed, ranges, rank, world, nlist, d, dev, dist)
+            if rank == 0:
+                sub_ids = np.arange(len(sub_vecs), dtype=np.int64)
+                cpu_path(oracle, qs[:256], cent_h, sub_off, sub_vecs, sub_ids)      # warm-up (thread pools, page faults)
+                t0 = time.perf_counter()
+                passes = 0
+                while True:                                                         # N = 1: about 10 s of CPU work, at most 8 passes
+                    out_cpu, _ = cpu_path(oracle, qs, cent_h, sub_off, sub_vecs, sub_ids)
+                    passes += 1
+                    if world > 1 or time.perf_counter() - t0 >= 10.0 or passes >= 8:
+                        break
+                total_s = time.perf_counter() - t0
+                sec = total_s / passes
+                if world == 1:
+                    cpu = {"value": sample / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                           "sample": f"first {sample} of {nq} query frames of this workload, all {nlist} centroids, the {len(probed)} lists "
+                                     f"they probe staged on the host; {passes} passes, {total_s:.1f} s of CPU work; oracle port of faiss "
+                                     f"1.7.3 + numpy (omp_threads={oracle.num_threads()}, torch_threads={torch.get_num_threads()}, blas={blas})"}
+                parity = parity_sample(gpu_rows, out_cpu)
+                if parity and "rows" in parity:
+                    parity_str = (f"{parity['rows_bit_identical']}/{parity['rows']} blended rows of the first timed step bit-identical to the "
+                                  f"CPU port of the reference path, {parity['rows_differing']} differing"
+                                  + (f" (max rel diff {parity['max_rel_diff_in_differing_rows']:.2e}; near-tie centroid choices of the "
+                                     f"BLAS-order coarse distances)" if parity["rows_differing"] else "")
+                                  + (f"; lists gathered from their owner ranks ({world} GPUs)" if world > 1 else ""))
+                del sub_vecs
         except Exception as ex:
-            cpu = {"value": None, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
-                   "sample": "CPU baseline leg failed: " + repr(ex)[:200]}
+            if rank == 0:
+                cpu = {"value": None, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                       "sample": "CPU leg failed: " + repr(ex)[:200]}
+                parity_str = "parity sample failed: " + repr(ex)[:160]
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -565,17 +728,23 @@ def main():
                            **({"transport": transport} if transport else {}),
                            "l2": "inputs larger than L2 (fresh 3 KB/query feature buffer per step; lists >> 126 MB)"
                            if nq * d * 4 > (126 << 20) else "inputs smaller than L2",
-                           "coarse": (("tcgen05 e4m3 (experimental coarse_mode 4)" if coarse_e4m3 else "tcgen05 bf16")
+                           "coarse": (("tcgen05 e4m3" if coarse_e4m3 else "tcgen05 bf16")
                                       + " + exact fp32 re-check") if st["coarse_tc_queries"] else "exact FFMA",
+                           "queries": f"{args.near_frac:.0%} stored row + N(0, 0.05^2), rest fresh mixture samples; index has 0.1 % exact "
+                                      f"duplicate rows (SURVEY 8d)",
+                           "timing": f"per-step CUDA events summed over {args.steps} back-to-back steps (max over ranks); ring of {R} "
+                                     f"input buffers refilled between steps outside the events",
+                           "parity_sample": parity_str,
                            "setup_s": round(setup_s, 1)},
                 "roofline": dict(roof[dominant], dominant=dominant) if dominant else None,
                 "roofline_all": roof, "phase_ms": phase_acc, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-                "clocks": clocks, "host_affinity": numa,
+                "clocks": clocks, "host_affinity": numa, "skewed_queries": skewed,
                 "coarse_stats": {"tc_queries": st["coarse_tc_queries"], "rechecked_candidates": st["coarse_candidates"],
                                  "exact_fallback_queries": st["coarse_fallback"]},
                 "scan_stats": {"tc_candidates_rechecked": st.get("scan_tc_candidates", 0), "exact_fallback_queries": st.get("scan_tc_fallback", 0),
                                "queries": st["queries"]},
-                "sanity": {"finite_first_rows": bool(np.isfinite(result_check).all()), "parity_sample": parity}}
+                "sanity": {"finite_first_rows": bool(np.isfinite(result_check).all()) if result_check is not None else None,
+                           "parity_sample": parity}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -43,22 +43,41 @@ constexpr int BLOCK_M = 128;   // queries per CTA
 constexpr int BLOCK_N = 256;   // centroids per accumulator tile
 constexpr int BLOCK_K = 64;    // bf16 elements per stage row = 128 B = one swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int TOPT = 8;        // approximate nearest centroids kept per (query, split)
-constexpr int THREADS = 256;
+constexpr int TOPT = 8;        // approximate nearest centroids kept per (query, split, column group)
 constexpr int EPI_WARP0 = 4;
+constexpr int NCG = 4;         // column groups of the epilogue: 4 lane quarters x NCG warps drain one accumulator tile
+constexpr int THREADS = (EPI_WARP0 + 4 * NCG) * 32;   // 640
 
-// sorted (ascending) top-T insertion, fully unrolled, registers only
-__device__ __forceinline__ void top_insert(float (&tv)[TOPT], int (&tj)[TOPT], float x, int j) {
-    if (!(x < tv[TOPT - 1])) return;
-    tv[TOPT - 1] = x;
+// sorted (DESCENDING key = ascending v) top-T insertion, fully unrolled, registers only
+__device__ __forceinline__ void top_insert(float (&tk)[TOPT], int (&tj)[TOPT], float x, int j) {
+    if (!(x > tk[TOPT - 1])) return;
+    tk[TOPT - 1] = x;
     tj[TOPT - 1] = j;
 #pragma unroll
     for (int i = TOPT - 1; i > 0; --i) {
-        if (tv[i] < tv[i - 1]) {
-            float fv = tv[i]; tv[i] = tv[i - 1]; tv[i - 1] = fv;
+        if (tk[i] > tk[i - 1]) {
+            float fv = tk[i]; tk[i] = tk[i - 1]; tk[i - 1] = fv;
             int fj = tj[i]; tj[i] = tj[i - 1]; tj[i - 1] = fj;
         }
     }
+}
+
+// tcgen05.wait::ld with the loaded registers as in/out operands: nothing that reads them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// 1-D bulk copy global -> this CTA's shared memory, completing (bytes) on a local mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_addr, const void* src, uint32_t bytes, uint32_t bar_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_addr),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar_addr)
+                 : "memory");
 }
 
 // NRES = k-blocks of the query operand (A) kept resident in shared memory for a whole work item (one m-block
@@ -78,19 +97,34 @@ struct Cfg {
     static constexpr int B_BYTES = LOAD_N * BLOCK_K * 2;                  // 32 KB / 16 KB
     static constexpr int RES_BYTES = NRES * A_BYTES;
     static constexpr int RING_BYTES = SB * B_BYTES + SA * A_BYTES;
-    static constexpr int SMEM_BYTES = RES_BYTES + RING_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
+    static constexpr int NORM_BYTES = 2 * BLOCK_N * 4;                    // ||c||^2 of the tile in each accumulator stage
+    static constexpr int BAR_BYTES = 512;
+    // the dynamic shared memory of a kernel without static shared memory starts 1024-byte aligned (the kernel traps if not)
+    static constexpr int SMEM_BYTES = RES_BYTES + RING_BYTES + NORM_BYTES + BAR_BYTES;
     static constexpr int UMMA_M = BLOCK_M * CLUSTER;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(NRES > 0 || SA == SB, "fully streamed: one A slot per B stage");
+    static_assert((2 * SB + SA + 11) * 8 + 8 <= BAR_BYTES, "barrier block");
 };
 
 // grid = persistent CTAs (multiple of CLUSTER); work item = (m-block of 128*CLUSTER queries, split
 // of the centroid tiles); item i is taken by cluster (i mod nclusters).
 //
-// F8 = 1 (coarse_mode 4, experimental): e4m3 operands (kind::f8f6f4).  A 128-byte k-block then holds 128 elements
+// Epilogue (round 2): the r01 kernel drained an accumulator tile with 4 warps, one 32-column tcgen05.ld at a time, the
+// ||c||^2 of the columns fetched with 8 LDG.128 per load and 8 data-dependent branches per 32 columns; ncu (profiles/
+// r01_ncu_summary.md) showed the tensor pipe idle 35 % of the time behind it (a third of the epilogue warps' samples on
+// the first FFMA after the loads, a quarter on branch resolution) -- and e4m3 operands, which halve the MMA time, gained
+// only 10 %.  Now 4 x NCG warps drain a tile (warp w: TMEM lane quarter w % 4, columns [cg 256/NCG, (cg + 1) 256/NCG) with
+// cg = (w - 4) / 4), the next 32-column load is in flight while the current one is processed, the tile's ||c||^2 arrive
+// in shared memory by one 1 KB bulk copy per tile (producer warp, double-buffered with the accumulator stages) and are
+// read as broadcast LDS.128, and a chunk is searched for insertions only if its maximum beats the row's current 8th
+// key (one branch per 32 columns).  Keys are -v = 2 <q', c'> - ||c||^2 (larger = nearer).  Each (query, split, column
+// group) writes its own top-8; the re-check merges them.
+//
+// F8 = 1 (coarse_mode 4): e4m3 operands (kind::f8f6f4).  A 128-byte k-block then holds 128 elements
 // instead of 64, every tile / descriptor / byte count stays as it is, the instruction descriptor and the MMA kind
-// change, and the epilogue multiplies the accumulator by the per-query factor qk[row] = -2 / (s_q(row) s_c) that undoes
-// the power-of-two operand scales (bf16: the constant -2).
+// change, and the epilogue multiplies the accumulator by the per-query factor -qk[row] = 2 / (s_q(row) s_c) that undoes
+// the power-of-two operand scales (bf16: the constant 2).
 template <int CLUSTER, int NRES, int SB, int SA, int P, int F8 = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -98,12 +132,12 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  int num_kblocks, float* __restrict__ topv, int* __restrict__ topj, const float* __restrict__ qk) {
     using C = Cfg<CLUSTER, NRES, SB, SA, P>;
     constexpr int KE = F8 ? 2 * BLOCK_K : BLOCK_K;   // elements per 128-byte k-block (TMA coordinates are in elements)
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sAres = smem;                               // NRES resident A k-blocks
     uint8_t* sB = smem + C::RES_BYTES;                   // SB stages
     uint8_t* sA = sB + SB * C::B_BYTES;                  // SA slots (streamed A k-blocks)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RES_BYTES + C::RING_BYTES);
+    float* sNorm = reinterpret_cast<float*>(smem + C::RES_BYTES + C::RING_BYTES);   // [2][BLOCK_N]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RES_BYTES + C::RING_BYTES + C::NORM_BYTES);
     uint64_t* full_bar = bars;                      // [SB]  TMA -> MMA       (leader CTA's are used)
     uint64_t* empty_bar = full_bar + SB;            // [SB]  MMA -> TMA       (each CTA its own)
     uint64_t* aempty_bar = empty_bar + SB;          // [SA]  MMA -> TMA: streamed A slot free (each CTA its own)
@@ -111,7 +145,9 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* ares_empty_bar = ares_full_bar + 1;   // [1]   MMA -> TMA: the item's MMAs are complete (each CTA its own)
     uint64_t* tmem_full_bar = ares_empty_bar + 1;   // [2]   MMA -> epilogue  (each CTA its own)
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]   epilogue -> MMA  (leader CTA's are used)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* norm_full_bar = tmem_empty_bar + 2;   // [2]   bulk copy -> epilogue (each CTA its own)
+    uint64_t* norm_empty_bar = norm_full_bar + 2;   // [2]   epilogue -> producer (each CTA its own)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(norm_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -123,6 +159,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // k-block kb is streamed when it is every P-th one or the resident slots are used up; else it lives in slot kb - kb / P
     auto is_streamed = [](int kb) { return NRES == 0 || kb % P == P - 1 || kb - kb / P >= NRES; };
 
+    if ((smem_u32(smem) & 1023u) != 0) __trap();   // the swizzled tiles need 1024-byte alignment (see Cfg)
     if constexpr (CLUSTER > 1) cluster_sync_all();
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -137,8 +174,10 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_init(ares_full_bar, CLUSTER);
         mbar_init(ares_empty_bar, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&tmem_full_bar[i], 1);                // one tcgen05.commit
-            mbar_init(&tmem_empty_bar[i], CLUSTER * 128);   // every epilogue thread of the pair
+            mbar_init(&tmem_full_bar[i], 1);                  // one tcgen05.commit
+            mbar_init(&tmem_empty_bar[i], CLUSTER * 4 * NCG); // every epilogue warp of the pair
+            mbar_init(&norm_full_bar[i], 1);                  // the producer's arrive (+ tx bytes)
+            mbar_init(&norm_empty_bar[i], 4 * NCG);           // every epilogue warp of this CTA
         }
         fence_mbar_init();
     } else if (warp == 2) {
@@ -159,7 +198,8 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t sA_addr = tc::warp_uniform(smem_u32(sA)), sB_addr = tc::warp_uniform(smem_u32(sB));
         const uint32_t full_addr = tc::warp_uniform(smem_u32(full_bar));
         const uint32_t ares_full_addr = tc::warp_uniform(smem_u32(ares_full_bar));
-        uint32_t stage = 0, phase = 0, astage = 0, aphase = 0, item_cnt = 0;
+        const uint32_t norm_addr = tc::warp_uniform(smem_u32(sNorm)), nfull_addr = tc::warp_uniform(smem_u32(norm_full_bar));
+        uint32_t stage = 0, phase = 0, astage = 0, aphase = 0, item_cnt = 0, tile_cnt = 0;
         for (int item = cluster_id; item < nitems; item += nclusters, ++item_cnt) {
             const int mb = item / nsplit, sp = item - mb * nsplit;
             const int m0 = mb * (BLOCK_M * CLUSTER) + (int)cta_rank * BLOCK_M;
@@ -180,8 +220,18 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 __syncwarp();
             }
-            for (int t = t0; t < t1; ++t) {
+            for (int t = t0; t < t1; ++t, ++tile_cnt) {
                 const int n0 = t * BLOCK_N + (int)cta_rank * C::LOAD_N;
+                {
+                    // this tile's ||c||^2 (all BLOCK_N columns: the epilogue of either CTA of a pair sees the whole tile)
+                    const uint32_t ns = tile_cnt & 1, nphase = (tile_cnt >> 1) & 1;
+                    mbar_wait_warp(&norm_empty_bar[ns], nphase ^ 1, lane);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx_addr(nfull_addr + ns * 8, BLOCK_N * 4);
+                        bulk_load_1d(norm_addr + ns * (BLOCK_N * 4), cn + (int64_t)t * BLOCK_N, BLOCK_N * 4, nfull_addr + ns * 8);
+                    }
+                    __syncwarp();
+                }
                 for (int kb = 0; kb < num_kblocks; ++kb) {
                     const bool streamed = is_streamed(kb);     // uniform
                     mbar_wait_warp(&empty_bar[stage], phase ^ 1, lane);
@@ -263,61 +313,85 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp >= EPI_WARP0) {
         // ================================ epilogue =====================================
-        const int ew = warp - EPI_WARP0;               // == warp % 4: TMEM lane quarter of this warp
+        constexpr int CGW = BLOCK_N / NCG;             // columns per column group
+        constexpr int NCH = CGW / 32;                  // 32-column chunks per warp and tile
+        const int ew = (warp - EPI_WARP0) & 3;         // == warp % 4: TMEM lane quarter of this warp
+        const int cg = (warp - EPI_WARP0) >> 2;        // column group
         const int row = ew * 32 + lane;                // accumulator row == TMEM lane
         uint32_t tile_cnt = 0;
         for (int item = cluster_id; item < nitems; item += nclusters) {
             const int mb = item / nsplit, sp = item - mb * nsplit;
             const int t0 = sp * tiles_per_split;
             const int t1 = min(t0 + tiles_per_split, num_ntiles);
-            float tv[TOPT];
+            float tk[TOPT];
             int tj[TOPT];
 #pragma unroll
-            for (int i = 0; i < TOPT; ++i) { tv[i] = __int_as_float(0x7f800000); tj[i] = -1; }
-            float kr = -2.f;   // v = ||c||^2 + kr * acc
-            if constexpr (F8) kr = __ldg(qk + (int64_t)mb * (BLOCK_M * CLUSTER) + (int64_t)cta_rank * BLOCK_M + row);
+            for (int i = 0; i < TOPT; ++i) { tk[i] = __int_as_float(0xff800000); tj[i] = -1; }
+            float nkr = 2.f;   // key = -v = nkr * acc - ||c||^2
+            if constexpr (F8) nkr = -__ldg(qk + (int64_t)mb * (BLOCK_M * CLUSTER) + (int64_t)cta_rank * BLOCK_M + row);
             for (int t = t0; t < t1; ++t, ++tile_cnt) {
                 const uint32_t as = tile_cnt & 1, aphase = (tile_cnt >> 1) & 1;
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + cg * CGW;
+                const float4* sn4 = reinterpret_cast<const float4*>(sNorm + as * BLOCK_N + cg * CGW);
+                const int j0 = t * BLOCK_N + cg * CGW;
+                uint32_t ra[32], rb[32];
                 mbar_wait_warp(&tmem_full_bar[as], aphase, lane);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N;
-                const int n0 = t * BLOCK_N;
-                const float4* cn4 = reinterpret_cast<const float4*>(cn + n0);
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c * 32, r);
-                    float4 nn[8];
+                tmem_ld32(taddr, ra);
+                mbar_wait_warp(&norm_full_bar[as], aphase, lane);
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) nn[g] = __ldg(cn4 + c * 8 + g);
-                    tmem_ld_wait();
+                for (int c = 0; c < NCH; ++c) {
+                    uint32_t (&r)[32] = (c & 1) ? rb : ra;
+                    tmem_ld_wait_regs(r);
+                    if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, (c & 1) ? ra : rb);   // in flight while chunk c is processed
+                    float key[32];
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
-                        const float x0 = fmaf(F8 ? kr : -2.f, __uint_as_float(r[4 * g + 0]), nn[g].x);
-                        const float x1 = fmaf(F8 ? kr : -2.f, __uint_as_float(r[4 * g + 1]), nn[g].y);
-                        const float x2 = fmaf(F8 ? kr : -2.f, __uint_as_float(r[4 * g + 2]), nn[g].z);
-                        const float x3 = fmaf(F8 ? kr : -2.f, __uint_as_float(r[4 * g + 3]), nn[g].w);
-                        const float m = fminf(fminf(x0, x1), fminf(x2, x3));
-                        if (m < tv[TOPT - 1]) {
-                            const int jb = n0 + c * 32 + 4 * g;
-                            top_insert(tv, tj, x0, jb + 0);
-                            top_insert(tv, tj, x1, jb + 1);
-                            top_insert(tv, tj, x2, jb + 2);
-                            top_insert(tv, tj, x3, jb + 3);
+                        const float4 nn = sn4[c * 8 + g];   // same address in every lane: one broadcast LDS.128
+                        key[4 * g + 0] = fmaf(nkr, __uint_as_float(r[4 * g + 0]), -nn.x);
+                        key[4 * g + 1] = fmaf(nkr, __uint_as_float(r[4 * g + 1]), -nn.y);
+                        key[4 * g + 2] = fmaf(nkr, __uint_as_float(r[4 * g + 2]), -nn.z);
+                        key[4 * g + 3] = fmaf(nkr, __uint_as_float(r[4 * g + 3]), -nn.w);
+                    }
+                    // chunk maximum over (i, i + 16, ...) strides: a different association than the per-group maxima of the slow
+                    // path, so the compiler does not keep eight of those alive (and spilled) across the branch
+                    float mx;
+                    {
+                        float a8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a8[i] = fmaxf(fmaxf(key[i], key[i + 8]), fmaxf(key[i + 16], key[i + 24]));
+                        mx = fmaxf(fmaxf(fmaxf(a8[0], a8[1]), fmaxf(a8[2], a8[3])), fmaxf(fmaxf(a8[4], a8[5]), fmaxf(a8[6], a8[7])));
+                    }
+                    if (mx > tk[TOPT - 1]) {       // rare after the first tiles: one branch per 32 columns
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const float m4 = fmaxf(fmaxf(key[4 * g], key[4 * g + 1]), fmaxf(key[4 * g + 2], key[4 * g + 3]));
+                            if (m4 > tk[TOPT - 1]) {
+                                const int jb = j0 + c * 32 + 4 * g;
+                                top_insert(tk, tj, key[4 * g + 0], jb + 0);
+                                top_insert(tk, tj, key[4 * g + 1], jb + 1);
+                                top_insert(tk, tj, key[4 * g + 2], jb + 2);
+                                top_insert(tk, tj, key[4 * g + 3], jb + 3);
+                            }
                         }
                     }
                 }
-                // accumulator fully read: hand it back to the MMA issuer (leader CTA's barrier)
+                // accumulator columns and norms of this warp fully read: hand the stage back (leader CTA's barrier / own barrier)
                 tc_fence_before();
-                if (CLUSTER == 1 || leader) mbar_arrive_local(&tmem_empty_bar[as]);
-                else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                __syncwarp();
+                if (lane == 0) {
+                    if (CLUSTER == 1 || leader) mbar_arrive_local(&tmem_empty_bar[as]);
+                    else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                    mbar_arrive_local(&norm_empty_bar[as]);
+                }
             }
-            // write this (query, split)'s approximate top-8
+            // write this (query, split, column group)'s approximate top-8 as v = -key, ascending
             const int64_t q = (int64_t)mb * (BLOCK_M * CLUSTER) + (int64_t)cta_rank * BLOCK_M + row;
-            float4* ov = reinterpret_cast<float4*>(topv + (q * nsplit + sp) * TOPT);
-            int4* oj = reinterpret_cast<int4*>(topj + (q * nsplit + sp) * TOPT);
-            ov[0] = make_float4(tv[0], tv[1], tv[2], tv[3]);
-            ov[1] = make_float4(tv[4], tv[5], tv[6], tv[7]);
+            const int64_t o = ((q * nsplit + sp) * NCG + cg) * TOPT;
+            float4* ov = reinterpret_cast<float4*>(topv + o);
+            int4* oj = reinterpret_cast<int4*>(topj + o);
+            ov[0] = make_float4(-tk[0], -tk[1], -tk[2], -tk[3]);
+            ov[1] = make_float4(-tk[4], -tk[5], -tk[6], -tk[7]);
             oj[0] = make_int4(tj[0], tj[1], tj[2], tj[3]);
             oj[1] = make_int4(tj[4], tj[5], tj[6], tj[7]);
         }
@@ -898,8 +972,8 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
     }
     int tps = (num_ntiles + nsplit - 1) / nsplit;
     nsplit = (num_ntiles + tps - 1) / tps;
-    RVCR_TRY(h->ws_tc2.reserve((size_t)n_pad * nsplit * tc::TOPT * 4));
-    RVCR_TRY(h->ws_tc3.reserve((size_t)n_pad * nsplit * tc::TOPT * 4));
+    RVCR_TRY(h->ws_tc2.reserve((size_t)n_pad * nsplit * tc::NCG * tc::TOPT * 4));   // one top-8 per (query, split, column group)
+    RVCR_TRY(h->ws_tc3.reserve((size_t)n_pad * nsplit * tc::NCG * tc::TOPT * 4));
     CUtensorMap ta, tb;
     if (f8) {
         RVCR_TRY(make_tmap_u8(&ta, h->ws_tc0.p, n_pad, kdim, tc::BLOCK_M));
@@ -915,9 +989,10 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
         const int nkb = kdim / kelems;
         // option "tc_resident": A k-blocks pinned in shared memory (0 = stream both operands, the r01 v1 kernel)
         const int64_t res = h->opt.tc_resident;
-        if (f8) {   // d / 128 k-blocks (6 at d = 768): the 9-resident configuration keeps all but every 4th in shared memory
+        if (f8) {   // d / 128 k-blocks (6 at d = 768)
             const float* qk = h->ws_tc4.as<float>();
-            if (cluster == 2) RVCR_TRY((launch_tc<2, 9, 4, 1, 4, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
+            // cluster 2: every k-block of the query operand resident (d <= 1024: at most 8), 5 centroid stages
+            if (cluster == 2) RVCR_TRY((launch_tc<2, 8, 5, 1, 64, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
             else RVCR_TRY((launch_tc<1, 8, 2, 2, 3, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
         } else if (cluster == 2) {
             if (res == 0) RVCR_TRY((launch_tc<2, 0, 6, 6, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
@@ -933,7 +1008,7 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
     }
     *topv_out = h->ws_tc2.as<float>();
     *topj_out = h->ws_tc3.as<int>();
-    *nsplit_out = nsplit;
+    *nsplit_out = nsplit * tc::NCG;   // top-8 lists per query
     *qnorm_out = h->ws_tc1.as<float>();
     *qres_out = h->ws_tc5.as<float>();
     *res_stride_out = n_pad;

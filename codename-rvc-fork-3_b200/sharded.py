@@ -263,6 +263,11 @@ class ShardedIndex:
         self.peer = transport if transport is not None else CudaPeer(capacity_rows, d or self.be.d, self.be.device, self.group)
         return self.peer
 
+    def transport_name(self) -> str:
+        if self.peer is None:
+            return "nccl all-to-all (dispatch + combine)"
+        return "peer memory over NVLink (cudaIpc): owner pulls rows, blend epilogue pushes them home"
+
     def _peer_scan_push(self, feats, assign, row0, index_rate, want_neighbours=False):
         """Steps 2-4 over peer memory.  feats = rows [row0, row0 + n) of this rank's peer buffer, blended in place by
         whichever ranks own the lists.  row0 = -1 (tensor outside the peer buffer, or neighbours wanted) on ANY rank

@@ -131,11 +131,12 @@ def all_centroids(nlist: int, d: int, device, seed: int = 1234, sigma_c: float =
 
 
 def fill_index_by_construction(index, cent_all, sizes: np.ndarray, n_total: int, list_range=None, seed: int = 1234,
-                               sigma_p: float = 0.14):
+                               sigma_p: float = 0.14, dup_every: int = 1000):
     """`index` = index_factory(d, f"IVF{nlist},Flat") on its GPU.  List l holds sizes[l] points
     = centroid_l + N(0, sigma_p^2); ids = global row position (ascending inside a list, the only order
-    property faiss guarantees).  With list_range=(lo, hi) only those lists are stored (a shard); the
-    quantizer is always complete."""
+    property faiss guarantees).  One row in every `dup_every` (0.1 %) is an exact copy of another row of
+    the same list -- true distance ties inside a list, which the top-8 must break by list position.  With
+    list_range=(lo, hi) only those lists are stored (a shard); the quantizer is always complete."""
     import torch
     dev = cent_all.device
     nlist, d = cent_all.shape
@@ -158,6 +159,17 @@ def fill_index_by_construction(index, cent_all, sizes: np.ndarray, n_total: int,
             continue
         g.manual_seed(seed * 1000003 + 9_000_011 + b0 // LIST_BLOCK)
         noise = torch.randn((rows, d), generator=g, device=dev, dtype=torch.float32) * sigma_p
+        if dup_every and rows >= dup_every:
+            # exact duplicates: destination row k * dup_every + jitter (distinct by construction), source = a random row of
+            # the same list; drawn from the block's own stream over the WHOLE block, so a shard reproduces them
+            nd = rows // dup_every
+            dst = torch.arange(nd, device=dev) * dup_every + torch.randint(0, dup_every, (nd,), generator=g, device=dev)
+            boff = torch.as_tensor(offs_all[b0:b1 + 1] - offs_all[b0], device=dev)
+            lst = torch.searchsorted(boff, dst, right=True) - 1
+            u = torch.rand((nd,), generator=g, device=dev, dtype=torch.float64)
+            src = boff[lst] + (u * (boff[lst + 1] - boff[lst]).to(torch.float64)).to(torch.int64)
+            noise[dst] = noise[src]                    # the right-hand side is gathered before the scatter
+            del dst, lst, u, src, boff
         l0, l1 = max(b0, lo), min(b1, hi)
         r0, r1 = int(offs_all[l0] - offs_all[b0]), int(offs_all[l1] - offs_all[b0])
         if r1 > r0:
@@ -170,19 +182,72 @@ def fill_index_by_construction(index, cent_all, sizes: np.ndarray, n_total: int,
     index.commit()
 
 
-def device_queries(cent_all, nq: int, q_range=None, seed: int = 4321, sigma_p: float = 0.14):
-    """Fresh mixture samples: query i = centroid[list_i] + N(0, sigma_p^2), list_i uniform; generated
-    per block of QUERY_BLOCK queries so any contiguous range reproduces the same rows."""
+def zipf_list_cdf(nlist: int, s: float, device, seed: int = 4321):
+    """Cumulative distribution over list ids with mass proportional to (rank + 1)^-s under a fixed random ranking of
+    the lists (heavy lists land anywhere in the id range, hence on any shard).  s = 0: uniform."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed * 1000003 + 555)
+    rank_of = torch.randperm(nlist, generator=g, device=device)
+    w = (rank_of.to(torch.float64) + 1.0) ** (-float(s))
+    cdf = torch.cumsum(w / w.sum(), 0)
+    cdf[-1] = 1.0
+    return cdf
+
+
+def device_queries(cent_all, nq: int, q_range=None, seed: int = 4321, sigma_p: float = 0.14, zipf: float = 0.0,
+                   near_frac: float = 0.0, sizes=None, sigma_near: float = 0.05):
+    """Queries of the bench, generated per block of QUERY_BLOCK so any contiguous range reproduces the same rows
+    whatever the number of GPUs.  Query i draws a list (uniform, or Zipf with exponent `zipf` over a fixed random ranking
+    of the lists: the skewed variant).  A fresh query is centroid[list] + N(0, sigma_p^2).  With near_frac > 0 (and
+    `sizes` = the list sizes of the index) that fraction of the queries is marked "near": the caller replaces them by a
+    stored row of that list + N(0, sigma_near^2) (`apply_near_rows`); returned as (q, near) with near = dict(mask, gpos,
+    noise) or None."""
     import torch
     dev = cent_all.device
     nlist, d = cent_all.shape
     q0, q1 = (0, nq) if q_range is None else q_range
     out = torch.empty((q1 - q0, d), dtype=torch.float32, device=dev)
     g = torch.Generator(device=dev)
+    cdf = zipf_list_cdf(nlist, zipf, dev, seed) if zipf > 0 else None
+    want_near = near_frac > 0 and sizes is not None
+    if want_near:
+        offs = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]), device=dev)
+        mask = torch.zeros(q1 - q0, dtype=torch.bool, device=dev)
+        gpos = torch.zeros(q1 - q0, dtype=torch.int64, device=dev)
     for b0 in range((q0 // QUERY_BLOCK) * QUERY_BLOCK, q1, QUERY_BLOCK):
         g.manual_seed(seed * 1000003 + b0 // QUERY_BLOCK)
-        lists = torch.randint(0, nlist, (QUERY_BLOCK,), generator=g, device=dev)
+        if cdf is None:
+            lists = torch.randint(0, nlist, (QUERY_BLOCK,), generator=g, device=dev)
+        else:
+            u = torch.rand((QUERY_BLOCK,), generator=g, device=dev, dtype=torch.float64)
+            lists = torch.searchsorted(cdf, u).clamp_(max=nlist - 1)
         qb = cent_all[lists] + torch.randn((QUERY_BLOCK, d), generator=g, device=dev, dtype=torch.float32) * sigma_p
         a, b = max(b0, q0), min(b0 + QUERY_BLOCK, q1)
+        if want_near:
+            u = torch.rand((2, QUERY_BLOCK), generator=g, device=dev, dtype=torch.float64)
+            ln = (offs[lists + 1] - offs[lists])
+            nb = (u[0] < near_frac) & (ln > 0)
+            pos = offs[lists] + torch.minimum((u[1] * ln.to(torch.float64)).to(torch.int64), (ln - 1).clamp_(min=0))
+            # near queries: keep only the sigma_near noise here (rescaled from the fresh noise), the row is added later
+            qb = torch.where(nb[:, None], (qb - cent_all[lists]) * (sigma_near / sigma_p), qb)
+            mask[a - q0:b - q0] = nb[a - b0:b - b0]
+            gpos[a - q0:b - q0] = pos[a - b0:b - b0]
         out[a - q0:b - q0] = qb[a - b0:b - b0]
+    if want_near:
+        return out, {"mask": mask, "gpos": gpos}
     return out
+
+
+def apply_near_rows(q, near, vecs, row_base: int = 0, fetch=None):
+    """q[i] += stored row at global list-ordered position near['gpos'][i] for the marked queries.  Single GPU: the rows
+    are read from `vecs` (position - row_base).  Sharded: `fetch(gpos) -> rows` gets them from their owners."""
+    idx = near["mask"].nonzero().squeeze(1)
+    if idx.numel() == 0:
+        return q
+    gp = near["gpos"][idx]
+    step = 1 << 18
+    for s in range(0, idx.numel(), step):
+        sl = slice(s, s + step)
+        rows = fetch(gp[sl]) if fetch is not None else vecs[gp[sl] - row_base]
+        q[idx[sl]] += rows
+    return q

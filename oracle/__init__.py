@@ -49,6 +49,8 @@ def lib():
         L.rvco_l2sqr_f64.restype = C.c_double
         L.rvco_l2sqr_f64.argtypes = [fp, fp, C.c_int]
         L.rvco_num_threads.restype = C.c_int
+        L.rvco_set_num_threads.restype = None
+        L.rvco_set_num_threads.argtypes = [C.c_int]
         L.rvco_coarse_assign.restype = None
         L.rvco_coarse_assign.argtypes = [fp, C.c_int64, fp, C.c_int64, C.c_int, C.c_int, ip, fp, dp]
         L.rvco_scan_topk.restype = None
@@ -71,6 +73,12 @@ def _p(a, ty):
 
 def num_threads() -> int:
     return int(lib().rvco_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the C restatement (scan, canonical coarse, tail); returns the count now in force."""
+    lib().rvco_set_num_threads(int(n))
+    return num_threads()
 
 
 def l2sqr(x, y, fma: bool = True) -> np.float32:

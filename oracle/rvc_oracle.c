@@ -85,6 +85,16 @@ RVCO_API int rvco_num_threads(void) {
 #endif
 }
 
+/* torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the timed CPU legs of bench.py set the count
+ * explicitly (faiss itself would use every core: omp_get_max_threads() under the launcher's default environment) */
+RVCO_API void rvco_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* coarse quantizer, k = 1 (IndexFlatL2::search -> knn_L2sqr).                       */
 /* Strict "best > dis" replacement scanning j ascending  =>  ties go to the lowest centroid id. */

@@ -45,7 +45,7 @@ def test_f8_raw_values_match_float64(rvcr, cluster, shape):
     sq = f8_scale(np.abs(q64).max(axis=1))
     q8 = e4m3_round(q64 * sq[:, None])
     c8 = e4m3_round(c64 * sc)
-    assert np.abs(q8).max() < 256 and np.abs(c8).max() < 256
+    assert np.abs(q8).max() <= 256 and np.abs(c8).max() <= 256      # scaled maxima are < 256 and may round up to 256 (<= 448)
     vref = cn[None, :] - 2.0 * (q8 @ c8.T) / (sq[:, None] * sc)
     vtrue = cn[None, :] - 2.0 * (q64 @ c64.T)
     for i in range(nq):
