@@ -286,8 +286,7 @@ def build_roofline(phase_acc, coarse_on_tensor_cores, pk, *, nst, n_home, owned_
         roof["scan"] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / pk["hbm_gbs"],
                         "traffic": None, "kernel": ("scan_tc_kernel (tcgen05 tf32 + TMA) + scan_recheck_kernel (exact fp32"
                                                     + (" + gather/weights/blend)" if fused else ")")) if "scan_recheck" in phase_acc
-                        else ("scan_tc_fused_kernel (tcgen05 tf32 + TMA; exact re-check + tail as a warp role)" if scan_impl == 6
-                              else f"scan_topk_kernel_v{scan_impl or 4}"), "ms": phase_acc["scan"], "bytes_per_launch": sb,
+                        else f"scan_topk_kernel_v{scan_impl or 4}", "ms": phase_acc["scan"], "bytes_per_launch": sb,
                         "bytes_note": "B_s + B_g (SURVEY 8d): scan and fused tail" if fused else "B_s (SURVEY 8d)",
                         "peak_source": pk["source"]}
     if "blend" in phase_acc:
@@ -439,6 +438,7 @@ def main():
     ap.add_argument("--coarse-f8-auto", type=int, default=-1, help="1 / 0 = let / do not let the auto coarse mode probe e4m3 operands (-1 = library default)")
     ap.add_argument("--scan-impl", type=int, default=0, help="0 = library default (auto by batch size), 5 = tcgen05 scan, 1-4 exact FFMA scans")
     ap.add_argument("--tc-resident", type=int, default=-1, help="coarse kernel: resident query k-blocks (0/8/9/10; -1 = library default)")
+    ap.add_argument("--tc-cluster", type=int, default=-1, help="coarse kernel: 2 = CTA pairs (default), 1 = one CTA per SM")
     ap.add_argument("--fused-blend", type=int, default=-1, help="1 = re-check kernel also blends (default), 0 = separate gather_blend kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -497,6 +497,8 @@ def main():
         index.set_option("tc_resident", args.tc_resident)
     if args.fused_blend >= 0:
         index.set_option("fused_blend", args.fused_blend)
+    if args.tc_cluster > 0:
+        index.set_option("tc_cluster", args.tc_cluster)
     index.set_option("profile", 1)
     nq_lo, nq_hi = nq * rank // world, nq * (rank + 1) // world
     n_home = nq_hi - nq_lo

@@ -99,7 +99,7 @@ SIGNATURES = {
     "rvcr_debug_rand_perm": (C.c_int, [_I64, _I64, _P]),
     "rvcr_debug_split_clusters": (C.c_int, [_I32, _I64, _I64, _P, _P, C.POINTER(_I32)]),
     "rvcr_debug_coarse_tc": (C.c_int, [_H, _P, _I64, _I32, _I32, _I32, _P, _P, C.POINTER(_I32), _P,
-                                       C.POINTER(C.c_float), _P, _P]),
+                                       C.POINTER(C.c_float), _P, _P, _P]),
 }
 
 _lib = None

@@ -83,12 +83,11 @@ int check_searchable(rvcr_index* h, int32_t k) {
         set_error("k=%d unsupported: the RVC pipeline always searches k=8 (pipeline.py:499)", k);
         return RVCR_ERR_UNSUPPORTED;
     }
-    if (h->nprobe != 1) {
-        set_error("nprobe=%lld unsupported: RVC indices are built with nprobe=1 (extract_index.py:64)",
-                  (long long)h->nprobe);
-        return RVCR_ERR_UNSUPPORTED;
+    if (h->nprobe < 1) {
+        set_error("nprobe=%lld is not a valid probe count", (long long)h->nprobe);
+        return RVCR_ERR_STATE;
     }
-    return RVCR_OK;
+    return RVCR_OK;   // nprobe > 1 (a file made elsewhere; this fork writes 1, extract_index.py:64): multiprobe.cu
 }
 
 // nearest centroid for n device queries; dispatch FFMA-exact vs tcgen05 + exact re-check
@@ -124,6 +123,14 @@ int search_device(rvcr_index* h, float* feats_or_q, int64_t n, const int32_t* as
     RVCR_TRY(stream_enter(h, s));
     // a caller-supplied assignment came from an earlier rvcr_assign call: keep its coarse phase timings
     for (int i = assign_in ? RVCR_PHASE_GROUP : 0; i < RVCR_NUM_PHASES; ++i) h->pev_used[i] = false;
+    if (h->nprobe > 1 && h->nlist > 1) {
+        if (assign_in) {
+            set_error("a caller-supplied list assignment carries one list per query; this index has nprobe=%lld", (long long)h->nprobe);
+            return RVCR_ERR_UNSUPPORTED;
+        }
+        RVCR_TRY(search_multiprobe(h, feats_or_q, n, blend, index_rate, D_dev, I_dev, s));
+        return stream_leave(h, s);
+    }
     const int32_t* assign = assign_in;
     if (!assign) {
         RVCR_TRY(h->ws_assign.reserve((size_t)n * 4));
@@ -329,9 +336,10 @@ void rvcr_index_free(rvcr_index* h) {
         if (h->stage_assign) cudaFree(h->stage_assign);
         DevBuf* bufs[] = {&h->ws_assign, &h->ws_keys, &h->ws_vals, &h->ws_keys2, &h->ws_vals2, &h->ws_cub, &h->ws_items,
                           &h->ws_flags, &h->ws_misc, &h->ws_D, &h->ws_P, &h->ws_I, &h->ws_best, &h->ws_q, &h->ws_tc0,
-                          &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_tc4, &h->ws_tc5, &h->ws_stage, &h->row_norm, &h->ws_cand, &h->ws_candcnt,
+                          &h->ws_tc1, &h->ws_tc2, &h->ws_tc3, &h->ws_tc4, &h->ws_tc5, &h->ws_tc6, &h->ws_tc7, &h->ws_stage, &h->row_norm, &h->ws_cand, &h->ws_candcnt,
                           &h->ws_fb, &h->ws_cstage};
         for (DevBuf* b : bufs) b->release();
+        for (DevBuf& b : h->ws_mp) b.release();
         if (h->last_done) cudaEventDestroy(h->last_done);
         if (h->f8_fb_event) cudaEventDestroy(h->f8_fb_event);
         if (h->f8_fb_host) cudaFreeHost(h->f8_fb_host);
@@ -624,6 +632,14 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     RVCR_TRY(h->ws_q.reserve((size_t)n * rowb));
     RVCR_TRY(h->ws_assign.reserve((size_t)n * 4));
     RVCR_TRY(finalize_pending(h, s));
+    if (h->nprobe > 1 && h->nlist > 1) {   // interop path (multiprobe.cu): plain copy in, search + blend, copy out
+        RVCR_TRY(stream_enter(h, s));
+        RVCR_CUDA(cudaMemcpyAsync(h->ws_q.p, feats_host, (size_t)n * rowb, cudaMemcpyHostToDevice, s));
+        RVCR_TRY(search_device(h, h->ws_q.as<float>(), n, nullptr, true, index_rate, nullptr, nullptr, s));
+        RVCR_CUDA(cudaMemcpyAsync(feats_host, h->ws_q.p, (size_t)n * rowb, cudaMemcpyDeviceToHost, s));
+        RVCR_CUDA(cudaStreamSynchronize(s));
+        return RVCR_OK;
+    }
     if (!h->copy_stream) RVCR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     // chunk sizes ramp up (32 Ki, 64 Ki, then 128 Ki rows) so that only a small first copy is exposed
     std::vector<int64_t> coff;
@@ -912,7 +928,7 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "profile")) {
         h->opt.profile = value ? 1 : 0;
     } else if (!strcmp(key, "scan_impl")) {
-        if (value < 0 || value > 6) return RVCR_ERR_INVALID;   // 6: experimental fused re-check (scan_tc_fused.cu), never auto
+        if (value < 0 || value > 5) return RVCR_ERR_INVALID;
         h->opt.scan_impl = value;
     } else if (!strcmp(key, "tc_cluster")) {
         if (value != 1 && value != 2) return RVCR_ERR_INVALID;
@@ -1008,7 +1024,7 @@ int rvcr_get_stats(rvcr_index* h, rvcr_stats* out) {
 
 int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t split, int32_t cluster, int32_t cap_pairs,
                          float* v_host, int32_t* j_host, int32_t* pairs_out, float* qnorm2_host, float* cmax_out,
-                         float* margin_host, void* stream) {
+                         float* margin_host, float* dropped_host, void* stream) {
     RVCR_ENTER(h);
     cudaStream_t s = (cudaStream_t)stream;
     if (n <= 0 || !q_dev || !v_host || !j_host || !pairs_out || (cluster != 1 && cluster != 2)) return RVCR_ERR_INVALID;
@@ -1017,12 +1033,11 @@ int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t s
         return RVCR_ERR_STATE;
     }
     RVCR_TRY(stream_enter(h, s));
-    float *topv, *qnorm, *qres;
+    float *topv, *topd, *qnorm, *qmargin;
     int* topj;
     int nsplit = 0;
-    int64_t res_stride = 0;
     const int sp = split == 2 ? 2 : (split ? 1 : 0);   // 2: e4m3
-    RVCR_TRY(coarse_tc_top8(h, q_dev, n, sp, cluster, &topv, &topj, &nsplit, &qnorm, &qres, &res_stride, s));
+    RVCR_TRY(coarse_tc_top8(h, q_dev, n, sp, cluster, &topv, &topj, &topd, &nsplit, &qnorm, &qmargin, s));
     const int pairs = nsplit * 8;
     *pairs_out = pairs;
     if (pairs > cap_pairs) {
@@ -1032,11 +1047,9 @@ int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t s
     RVCR_CUDA(cudaMemcpyAsync(v_host, topv, (size_t)n * pairs * 4, cudaMemcpyDeviceToHost, s));
     RVCR_CUDA(cudaMemcpyAsync(j_host, topj, (size_t)n * pairs * 4, cudaMemcpyDeviceToHost, s));
     if (qnorm2_host) RVCR_CUDA(cudaMemcpyAsync(qnorm2_host, qnorm, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    if (margin_host) {   // the margin the re-check kernel would use for each query
-        RVCR_TRY(h->ws_stage.reserve((size_t)n * 4 + 64));
-        RVCR_TRY(coarse_tc_margins(h, sp, qnorm, qres, res_stride, n, h->ws_stage.as<float>(), s));
-        RVCR_CUDA(cudaMemcpyAsync(margin_host, h->ws_stage.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    }
+    if (margin_host)   // the margin the epilogue collected with and the re-check kernel selects with
+        RVCR_CUDA(cudaMemcpyAsync(margin_host, qmargin, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (dropped_host) RVCR_CUDA(cudaMemcpyAsync(dropped_host, topd, (size_t)n * (pairs / 8) * 4, cudaMemcpyDeviceToHost, s));
     RVCR_CUDA(cudaStreamSynchronize(s));
     if (cmax_out) *cmax_out = h->cent_norm_max;
     return stream_leave(h, s);

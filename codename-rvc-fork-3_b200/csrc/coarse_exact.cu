@@ -32,7 +32,7 @@ __global__ void init_best_kernel(unsigned long long* best, int64_t n) {
 __global__ void __launch_bounds__(PD_THREADS, 1)
 coarse_exact_kernel(const float* __restrict__ q, const int32_t* __restrict__ qsel, int64_t nq,
                     const int32_t* __restrict__ nsel_ptr, const float* __restrict__ cent, int64_t nlist, int d,
-                    int blocks_per_split, unsigned long long* __restrict__ best) {
+                    int blocks_per_split, unsigned long long* __restrict__ best, float* __restrict__ dmat) {
     extern __shared__ __align__(16) float smem[];
     const int QS = d + 8;
     float* sQ = smem;             // CE_QT x QS
@@ -103,6 +103,11 @@ coarse_exact_kernel(const float* __restrict__ q, const int32_t* __restrict__ qse
                 for (int b = 0; b < 4; ++b) {
                     const int64_t j = rb * PD_RB + 4 * w + b;  // ascending within a thread
                     if (j < nlist) {
+                        if (dmat && l == 0) {   // nprobe > 1 (multiprobe.cu): the whole (query, centroid) distance matrix
+#pragma unroll
+                            for (int a = 0; a < CE_TQ; ++a)
+                                if (qg + 4 * a < cnt) dmat[(q0 + qg + 4 * a) * nlist + j] = tile.acc[a][b];
+                        }
 #pragma unroll
                         for (int a = 0; a < CE_TQ; ++a) {
                             // faiss: if (best > dis) replace  -- strict, first (lowest id) wins; a NaN
@@ -198,12 +203,38 @@ int coarse_exact(rvcr_index* h, const float* q, int64_t n, const int32_t* qsel, 
     const int bps = (int)((nblk + nsplit - 1) / nsplit);
     nsplit = (nblk + bps - 1) / bps;
     dim3 grid((unsigned)qtiles, (unsigned)nsplit);
-    coarse_exact_kernel<<<grid, PD_THREADS, smem, s>>>(q, qsel, nwork, nullptr, h->cent, h->nlist, h->d, bps, best);
+    coarse_exact_kernel<<<grid, PD_THREADS, smem, s>>>(q, qsel, nwork, nullptr, h->cent, h->nlist, h->d, bps, best, nullptr);
     RVCR_CHECK_LAUNCH();
     unpack_best_kernel<<<(unsigned)((nwork + 255) / 256), 256, 0, s>>>(best, qsel, nwork, nullptr, 0, list_out,
                                                                          dist_out);
     RVCR_CHECK_LAUNCH();
     count_launch(h, 3);
+    return RVCR_OK;
+}
+
+// Canonical distances of queries q[0 .. n) to every centroid, written to dmat (n x nlist, row-major) -- the coarse step of
+// an index whose file says nprobe > 1 (multiprobe.cu selects the nprobe smallest per row).
+int coarse_exact_matrix(rvcr_index* h, const float* q, int64_t n, float* dmat, cudaStream_t s) {
+    if (n <= 0) return RVCR_OK;
+    size_t smem = 0;
+    RVCR_TRY(ce_prepare(h, &smem));
+    RVCR_TRY(h->ws_best.reserve((size_t)n * 8));
+    const int64_t qtiles = (n + CE_QT - 1) / CE_QT;
+    const int64_t nblk = (h->nlist + PD_RB - 1) / PD_RB;
+    int64_t nsplit = (2 * h->num_sms + qtiles - 1) / qtiles;
+    const int64_t max_split = (nblk + 3) / 4;
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > 65535) nsplit = 65535;
+    const int bps = (int)((nblk + nsplit - 1) / nsplit);
+    nsplit = (nblk + bps - 1) / bps;
+    dim3 grid((unsigned)qtiles, (unsigned)nsplit);
+    init_best_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->ws_best.as<unsigned long long>(), n);
+    RVCR_CHECK_LAUNCH();
+    coarse_exact_kernel<<<grid, PD_THREADS, smem, s>>>(q, nullptr, n, nullptr, h->cent, h->nlist, h->d, bps,
+                                                        h->ws_best.as<unsigned long long>(), dmat);
+    RVCR_CHECK_LAUNCH();
+    count_launch(h, 2);
     return RVCR_OK;
 }
 
@@ -229,7 +260,7 @@ int coarse_exact_selected(rvcr_index* h, const float* q, int64_t n, const int32_
     const int64_t gx_max = std::max<int64_t>(1, (int64_t)(8 * h->num_sms) / nsplit);
     if (gx > gx_max) gx = gx_max;
     dim3 grid((unsigned)gx, (unsigned)nsplit);
-    coarse_exact_kernel<<<grid, PD_THREADS, smem, s>>>(q, qsel, n, nsel_dev, h->cent, h->nlist, h->d, bps, best);
+    coarse_exact_kernel<<<grid, PD_THREADS, smem, s>>>(q, qsel, n, nsel_dev, h->cent, h->nlist, h->d, bps, best, nullptr);
     RVCR_CHECK_LAUNCH();
     unpack_best_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(best, qsel, n, nsel_dev, 0, list_out, dist_out);
     RVCR_CHECK_LAUNCH();

@@ -24,8 +24,8 @@
 //   warp 1   MMA issuer (one elected thread; leader CTA only): 4 x tcgen05.mma (K = 16) per stage
 //            into a 128 x 256 fp32 accumulator, double-buffered in TMEM (2 x 256 columns)
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld 32 columns at a time, v = fma(-2, acc, ||c||^2), running top-8
-//            per row in registers; overlaps the next tile's MMAs
+//   warps 4-19 epilogue (4 lane quarters x 4 column groups): tcgen05.ld 32 columns at a time, key = 2 acc - ||c||^2,
+//            per row the candidates within margin(q) of the running best; overlaps the next tile's MMAs
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
@@ -48,17 +48,34 @@ constexpr int EPI_WARP0 = 4;
 constexpr int NCG = 4;         // column groups of the epilogue: 4 lane quarters x NCG warps drain one accumulator tile
 constexpr int THREADS = (EPI_WARP0 + 4 * NCG) * 32;   // 640
 
-// sorted (DESCENDING key = ascending v) top-T insertion, fully unrolled, registers only
-__device__ __forceinline__ void top_insert(float (&tk)[TOPT], int (&tj)[TOPT], float x, int j) {
-    if (!(x > tk[TOPT - 1])) return;
-    tk[TOPT - 1] = x;
-    tj[TOPT - 1] = j;
+// Candidate list of one (query, split, column group): up to TOPT (key, centroid) pairs with key >= best - margin, unsorted.
+// A passing element takes a free slot (key -inf) or evicts the smallest key kept if it beats it; whatever passed the test
+// but is not kept (evicted or turned away) is remembered by its largest key in `dropped`, so the re-check can tell whether
+// the list may be missing a candidate (dropped >= final best - margin -> the exact kernel answers the query).
+__device__ __forceinline__ void cand_insert(float (&ck)[TOPT], int (&cj)[TOPT], float& best, float& thr, float& dropped,
+                                            float margin, float x, int j) {
+    float vk = ck[0];
+    int vs = 0;
 #pragma unroll
-    for (int i = TOPT - 1; i > 0; --i) {
-        if (tk[i] > tk[i - 1]) {
-            float fv = tk[i]; tk[i] = tk[i - 1]; tk[i - 1] = fv;
-            int fj = tj[i]; tj[i] = tj[i - 1]; tj[i - 1] = fj;
+    for (int i = 1; i < TOPT; ++i)
+        if (ck[i] < vk) {
+            vk = ck[i];
+            vs = i;
         }
+    if (x > vk) {
+        dropped = fmaxf(dropped, vk);
+#pragma unroll
+        for (int i = 0; i < TOPT; ++i)
+            if (i == vs) {
+                ck[i] = x;
+                cj[i] = j;
+            }
+    } else {
+        dropped = fmaxf(dropped, x);
+    }
+    if (x > best) {
+        best = x;
+        thr = best - margin;
     }
 }
 
@@ -129,7 +146,8 @@ template <int CLUSTER, int NRES, int SB, int SA, int P, int F8 = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const float* __restrict__ cn, int num_mblocks, int num_ntiles, int nsplit, int tiles_per_split,
-                 int num_kblocks, float* __restrict__ topv, int* __restrict__ topj, const float* __restrict__ qk) {
+                 int num_kblocks, float* __restrict__ topv, int* __restrict__ topj, float* __restrict__ topd,
+                 const float* __restrict__ qk, const float* __restrict__ qmargin) {
     using C = Cfg<CLUSTER, NRES, SB, SA, P>;
     constexpr int KE = F8 ? 2 * BLOCK_K : BLOCK_K;   // elements per 128-byte k-block (TMA coordinates are in elements)
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -323,27 +341,32 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int mb = item / nsplit, sp = item - mb * nsplit;
             const int t0 = sp * tiles_per_split;
             const int t1 = min(t0 + tiles_per_split, num_ntiles);
-            float tk[TOPT];
-            int tj[TOPT];
+            const int64_t q = (int64_t)mb * (BLOCK_M * CLUSTER) + (int64_t)cta_rank * BLOCK_M + row;
+            float ck[TOPT];
+            int cj[TOPT];
 #pragma unroll
-            for (int i = 0; i < TOPT; ++i) { tk[i] = __int_as_float(0xff800000); tj[i] = -1; }
+            for (int i = 0; i < TOPT; ++i) { ck[i] = __int_as_float(0xff800000); cj[i] = -1; }
+            // margin(q) of the re-check (tc_margin, written by the prep kernel): only keys within it of the row's running best
+            // can still be the nearest centroid.  A margin that is NaN or absurd collects nothing -> exact kernel.
+            float margin = __ldg(qmargin + q);
+            if (!(margin < 1e30f)) margin = __int_as_float(0x7fc00000);
+            float best = __int_as_float(0xff800000), dropped = __int_as_float(0xff800000);
+            float thr = margin == margin ? __int_as_float(0xff800000) : margin;   // -inf: the first columns all pass
             float nkr = 2.f;   // key = -v = nkr * acc - ||c||^2
-            if constexpr (F8) nkr = -__ldg(qk + (int64_t)mb * (BLOCK_M * CLUSTER) + (int64_t)cta_rank * BLOCK_M + row);
+            if constexpr (F8) nkr = -__ldg(qk + q);
             for (int t = t0; t < t1; ++t, ++tile_cnt) {
                 const uint32_t as = tile_cnt & 1, aphase = (tile_cnt >> 1) & 1;
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + cg * CGW;
                 const float4* sn4 = reinterpret_cast<const float4*>(sNorm + as * BLOCK_N + cg * CGW);
                 const int j0 = t * BLOCK_N + cg * CGW;
-                uint32_t ra[32], rb[32];
                 mbar_wait_warp(&tmem_full_bar[as], aphase, lane);
                 tc_fence_after();
-                tmem_ld32(taddr, ra);
                 mbar_wait_warp(&norm_full_bar[as], aphase, lane);
-#pragma unroll
+#pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
-                    uint32_t (&r)[32] = (c & 1) ? rb : ra;
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
                     tmem_ld_wait_regs(r);
-                    if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, (c & 1) ? ra : rb);   // in flight while chunk c is processed
                     float key[32];
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
@@ -353,8 +376,6 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         key[4 * g + 2] = fmaf(nkr, __uint_as_float(r[4 * g + 2]), -nn.z);
                         key[4 * g + 3] = fmaf(nkr, __uint_as_float(r[4 * g + 3]), -nn.w);
                     }
-                    // chunk maximum over (i, i + 16, ...) strides: a different association than the per-group maxima of the slow
-                    // path, so the compiler does not keep eight of those alive (and spilled) across the branch
                     float mx;
                     {
                         float a8[8];
@@ -362,17 +383,23 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int i = 0; i < 8; ++i) a8[i] = fmaxf(fmaxf(key[i], key[i + 8]), fmaxf(key[i + 16], key[i + 24]));
                         mx = fmaxf(fmaxf(fmaxf(a8[0], a8[1]), fmaxf(a8[2], a8[3])), fmaxf(fmaxf(a8[4], a8[5]), fmaxf(a8[6], a8[7])));
                     }
-                    if (mx > tk[TOPT - 1]) {       // rare after the first tiles: one branch per 32 columns
+                    if (mx >= thr) {               // one branch per 32 columns; a few dozen times per row and item
+                        const int jb = j0 + c * 32;
+#pragma unroll 1
+                        for (;;) {                 // largest first: the threshold rises before the rest is looked at
+                            float m = key[0];
+                            int mi = 0;
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            const float m4 = fmaxf(fmaxf(key[4 * g], key[4 * g + 1]), fmaxf(key[4 * g + 2], key[4 * g + 3]));
-                            if (m4 > tk[TOPT - 1]) {
-                                const int jb = j0 + c * 32 + 4 * g;
-                                top_insert(tk, tj, key[4 * g + 0], jb + 0);
-                                top_insert(tk, tj, key[4 * g + 1], jb + 1);
-                                top_insert(tk, tj, key[4 * g + 2], jb + 2);
-                                top_insert(tk, tj, key[4 * g + 3], jb + 3);
-                            }
+                            for (int i = 1; i < 32; ++i)
+                                if (key[i] > m) {
+                                    m = key[i];
+                                    mi = i;
+                                }
+                            if (!(m >= thr)) break;
+                            cand_insert(ck, cj, best, thr, dropped, margin, m, jb + mi);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i == mi) key[i] = __int_as_float(0xff800000);
                         }
                     }
                 }
@@ -385,15 +412,16 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_arrive_local(&norm_empty_bar[as]);
                 }
             }
-            // write this (query, split, column group)'s approximate top-8 as v = -key, ascending
-            const int64_t q = (int64_t)mb * (BLOCK_M * CLUSTER) + (int64_t)cta_rank * BLOCK_M + row;
-            const int64_t o = ((q * nsplit + sp) * NCG + cg) * TOPT;
-            float4* ov = reinterpret_cast<float4*>(topv + o);
-            int4* oj = reinterpret_cast<int4*>(topj + o);
-            ov[0] = make_float4(-tk[0], -tk[1], -tk[2], -tk[3]);
-            ov[1] = make_float4(-tk[4], -tk[5], -tk[6], -tk[7]);
-            oj[0] = make_int4(tj[0], tj[1], tj[2], tj[3]);
-            oj[1] = make_int4(tj[4], tj[5], tj[6], tj[7]);
+            // write this (query, split, column group)'s candidates as v = -key (free slots: +inf, -1) and the largest v-wise
+            // nearest thing it had to let go
+            const int64_t ol = (q * nsplit + sp) * NCG + cg;
+            float4* ov = reinterpret_cast<float4*>(topv + ol * TOPT);
+            int4* oj = reinterpret_cast<int4*>(topj + ol * TOPT);
+            ov[0] = make_float4(-ck[0], -ck[1], -ck[2], -ck[3]);
+            ov[1] = make_float4(-ck[4], -ck[5], -ck[6], -ck[7]);
+            oj[0] = make_int4(cj[0], cj[1], cj[2], cj[3]);
+            oj[1] = make_int4(cj[4], cj[5], cj[6], cj[7]);
+            topd[ol] = -dropped;
         }
     }
 
@@ -406,6 +434,33 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 // ------------------------------------------------------------------- operand preparation ----
 
+// The margin between two approximate values v(q, j) = ||c_j||^2 - 2 <q', c_j'> (primes: the low-precision operands):
+// with r = ||x - x'|| the EXACT residual norms written by the prep kernels (queries: per row; centroids: the maximum over
+// the set) and Cauchy-Schwarz,
+//     |<q, c> - <q', c'>|  =  |<q - q', c> + <q', c - c'>|  <=  r_q c_max + (|q| + r_q) r_c                 (bf16, e4m3)
+//     3-way bf16 split (h_q h_c + l_q h_c + h_q l_c is what the MMAs sum; rho1 = x - h, rho2 = x - h - l):
+//     |<q, c> - sum|       =  |<l_q, rho1_c> + <rho2_q, c> + <h_q, rho2_c>|  <=  (r1_q + r2_q) r1_c + r2_q c_max + (|q| + r1_q) r2_c
+// One v is off by twice that, two of them compared by four times.  On top: the accumulation of the products in the tensor
+// cores (acc_rel |q'||c'|, host-chosen per operand kind) and abs_rel (|q|^2 + c_max^2) for the fp32 roundings -- the norms
+// ||c||^2 ((d/32 + 5) ulps), the fma of the epilogue, the threshold sum, and the gap between a canonical fp32 distance and
+// the true one ((d/8 + 5) ulps of a distance <= 2 (|q|^2 + c_max^2), on both candidates).  1.002 covers the fp32 evaluation
+// of the residual norms and of this formula.  No ulp-size assumption about the rows is left: rows built to sit on bf16
+// rounding midpoints (relative error 2^-8 per element, twice the typical) just get a larger margin.
+struct TcMargin {
+    float cmax;      // max ||c||
+    float rc1, rc2;  // max ||c - c'|| (rc2: second-level residual of the 3-way split)
+    float acc_rel, abs_rel;
+    int split;       // 1 = 3-way bf16 split
+};
+__device__ __forceinline__ float tc_margin(const TcMargin& mp, float qn2, float r1, float r2) {
+    const float qn = sqrtf(qn2);
+    float e;
+    if (mp.split == 1) e = (r1 + r2) * mp.rc1 + r2 * mp.cmax + (qn + r1) * mp.rc2;
+    else e = r1 * mp.cmax + (qn + r1) * mp.rc1;
+    return 4.008f * e + mp.acc_rel * (qn + r1) * (mp.cmax + mp.rc1) + mp.abs_rel * (qn2 + mp.cmax * mp.cmax);
+}
+
+
 // one warp per row: fp32 row -> bf16 operand row(s) of width kdim (= d, or 3d for the split form
 // [h | l | h] for queries / [h | h | l] for centroids), the row's squared norm, and the EXACT norms of what the
 // operand does not carry: res[r] = ||x - h||, and for the split form res[res_stride + r] = ||x - h - l||
@@ -415,7 +470,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // sit next to rounding midpoints reaches that.
 __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d, int split, int is_centroid,
                                     __nv_bfloat16* __restrict__ out, float* __restrict__ norm2, float pad_norm,
-                                    float* __restrict__ res, int64_t res_stride) {
+                                    float* __restrict__ res, int64_t res_stride, TcMargin mp, float* __restrict__ margin_out) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (r >= n_pad) return;
@@ -429,6 +484,7 @@ __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int6
                 res[r] = 0.f;
                 if (split) res[res_stride + r] = 0.f;
             }
+            if (margin_out) margin_out[r] = 0.f;
         }
         return;
     }
@@ -466,6 +522,7 @@ __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int6
             res[r] = sqrtf(s1);
             if (split) res[res_stride + r] = sqrtf(s2);
         }
+        if (margin_out) margin_out[r] = tc_margin(mp, s, sqrtf(s1), sqrtf(s2));   // queries: the re-check's margin
     }
 }
 
@@ -506,7 +563,8 @@ __global__ void tc_maxabs_kernel(const float* __restrict__ x, int64_t n, unsigne
 // kept, and the re-check hands the query to the exact kernel.
 __global__ void tc_prep_rows_f8_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d, float fixed_scale,
                                        float other_scale, uint8_t* __restrict__ out, float* __restrict__ norm2,
-                                       float* __restrict__ kfac, float pad_norm, float* __restrict__ res) {
+                                       float* __restrict__ kfac, float pad_norm, float* __restrict__ res, TcMargin mp,
+                                       float* __restrict__ margin_out) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (r >= n_pad) return;
@@ -517,6 +575,7 @@ __global__ void tc_prep_rows_f8_kernel(const float* __restrict__ x, int64_t n, i
             if (norm2) norm2[r] = pad_norm;
             if (kfac) kfac[r] = -2.f;
             if (res) res[r] = 0.f;
+            if (margin_out) margin_out[r] = 0.f;
         }
         return;
     }
@@ -556,7 +615,9 @@ __global__ void tc_prep_rows_f8_kernel(const float* __restrict__ x, int64_t n, i
     for (int off = 16; off > 0; off >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, off);
     if (lane == 0) {
         if (norm2) norm2[r] = s;
-        if (res) res[r] = bad ? __int_as_float(0x7fc00000) : sqrtf(s1) / scale;   // division by a power of two: exact
+        const float rq = bad ? __int_as_float(0x7fc00000) : sqrtf(s1) / scale;   // division by a power of two: exact
+        if (res) res[r] = rq;
+        if (margin_out) margin_out[r] = tc_margin(mp, s, rq, 0.f);
         if (kfac) {
             const double p = (double)scale * (double)other_scale;
             float k = (float)(-2.0 / p);
@@ -578,53 +639,20 @@ __global__ void tc_max_kernel(const float* __restrict__ v, int64_t n, unsigned i
 
 // ------------------------------------------------------------------------- exact re-check ----
 
-// The margin between two approximate values v(q, j) = ||c_j||^2 - 2 <q', c_j'> (primes: the low-precision operands):
-// with r = ||x - x'|| the EXACT residual norms written by the prep kernels (queries: per row; centroids: the maximum over
-// the set) and Cauchy-Schwarz,
-//     |<q, c> - <q', c'>|  =  |<q - q', c> + <q', c - c'>|  <=  r_q c_max + (|q| + r_q) r_c                 (bf16, e4m3)
-//     3-way bf16 split (h_q h_c + l_q h_c + h_q l_c is what the MMAs sum; rho1 = x - h, rho2 = x - h - l):
-//     |<q, c> - sum|       =  |<l_q, rho1_c> + <rho2_q, c> + <h_q, rho2_c>|  <=  (r1_q + r2_q) r1_c + r2_q c_max + (|q| + r1_q) r2_c
-// One v is off by twice that, two of them compared by four times.  On top: the accumulation of the products in the tensor
-// cores (acc_rel |q'||c'|, host-chosen per operand kind) and abs_rel (|q|^2 + c_max^2) for the fp32 roundings -- the norms
-// ||c||^2 ((d/32 + 5) ulps), the fma of the epilogue, the threshold sum, and the gap between a canonical fp32 distance and
-// the true one ((d/8 + 5) ulps of a distance <= 2 (|q|^2 + c_max^2), on both candidates).  1.002 covers the fp32 evaluation
-// of the residual norms and of this formula.  No ulp-size assumption about the rows is left: rows built to sit on bf16
-// rounding midpoints (relative error 2^-8 per element, twice the typical) just get a larger margin.
-struct TcMargin {
-    float cmax;      // max ||c||
-    float rc1, rc2;  // max ||c - c'|| (rc2: second-level residual of the 3-way split)
-    float acc_rel, abs_rel;
-    int split;       // 1 = 3-way bf16 split
-};
-__device__ __forceinline__ float tc_margin(const TcMargin& mp, float qn2, float r1, float r2) {
-    const float qn = sqrtf(qn2);
-    float e;
-    if (mp.split == 1) e = (r1 + r2) * mp.rc1 + r2 * mp.cmax + (qn + r1) * mp.rc2;
-    else e = r1 * mp.cmax + (qn + r1) * mp.rc1;
-    return 4.008f * e + mp.acc_rel * (qn + r1) * (mp.cmax + mp.rc1) + mp.abs_rel * (qn2 + mp.cmax * mp.cmax);
-}
-
-__global__ void tc_margin_kernel(const float* __restrict__ qnorm2, const float* __restrict__ qres, int64_t res_stride, int64_t n,
-                                 TcMargin mp, float* __restrict__ out) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = tc_margin(mp, qnorm2[i], qres[i], mp.split == 1 ? qres[res_stride + i] : 0.f);
-}
-
-// One warp per query.  Gathers the nsplit x 8 approximate (v, j) pairs, keeps those with
-// v <= vmin + margin(q), evaluates their canonical fp32 distance (8 lanes per candidate, 4 candidates
-// per pass) and takes the argmin by (distance, id).  Flags the query for the exact kernel when a
-// split's 8th value is inside the margin (its candidate list may be truncated) or no candidate is
-// valid.
+// One warp per query.  Gathers the nsplit x 8 approximate (v, j) pairs (nsplit = centroid splits x column groups; unsorted,
+// free slots hold j = -1), keeps those with v <= vmin + margin(q), evaluates their canonical fp32 distance (8 lanes per
+// candidate, 4 candidates per pass) and takes the argmin by (distance, id).  Flags the query for the exact kernel when a
+// list dropped something inside the margin (it may be incomplete) or no candidate is valid.
 __global__ void tc_recheck_kernel(const float* __restrict__ q, int64_t n, int d, const float* __restrict__ cent, int64_t nlist,
-                                  const float* __restrict__ qnorm2, const float* __restrict__ qres, int64_t res_stride, TcMargin mp,
-                                  const float* __restrict__ topv, const int* __restrict__ topj, int nsplit, int64_t list_begin,
+                                  const float* __restrict__ qmargin, const float* __restrict__ topv,
+                                  const int* __restrict__ topj, const float* __restrict__ topd, int nsplit, int64_t list_begin,
                                   int32_t* __restrict__ list_out, float* __restrict__ dist_out, int32_t* __restrict__ fb_list,
                                   int32_t* __restrict__ counters /*[0] fallbacks of this call; [8..9], [10..11] u64 running totals*/) {
     const int lane = threadIdx.x & 31;
     const int64_t qi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (qi >= n) return;
-    // |v_approx - v_true| <= margin / 2 for every centroid
-    const float margin = tc_margin(mp, qnorm2[qi], qres[qi], mp.split == 1 ? qres[res_stride + qi] : 0.f);
+    // |v_approx - v_true| <= margin / 2 for every centroid; the same number the tensor-core epilogue collected with
+    const float margin = qmargin[qi];
     const int total = nsplit * tc::TOPT;
     const float* tv = topv + qi * total;
     const int* tj = topj + qi * total;
@@ -638,11 +666,9 @@ __global__ void tc_recheck_kernel(const float* __restrict__ q, int64_t n, int d,
     const float thr = vmin + margin;
     // no valid candidate at all (e.g. NaN query), or no finite margin (overflowing norms): the exact kernel decides
     bool overflow = !(vmin < __int_as_float(0x7f800000)) || !(margin < __int_as_float(0x7f800000));
-    // truncation check: the 8th (largest kept) value of any split inside the margin
-    for (int s = lane; s < nsplit; s += 32) {
-        const int j7 = tj[s * tc::TOPT + tc::TOPT - 1];
-        if (j7 >= 0 && tv[s * tc::TOPT + tc::TOPT - 1] <= thr) overflow = true;
-    }
+    // truncation check: a list (one per split and column group) had to let go of something inside the margin
+    for (int s = lane; s < nsplit; s += 32)
+        if (topd[qi * nsplit + s] <= thr) overflow = true;
     overflow = __any_sync(0xffffffffu, overflow);
     if (overflow) {
         if (lane == 0) {
@@ -778,6 +804,26 @@ int make_tmap_u8(CUtensorMap* m, const void* base, int64_t rows, int kdim, int b
 
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
+// the margin parameters of the current centroid operands (split: 0 bf16, 1 3-way bf16 split, 2 e4m3)
+TcMargin make_margin(const rvcr_index* h, int split) {
+    TcMargin mp;
+    const int d = h->d;
+    const int kdim = split == 1 ? 3 * d : d;
+    mp.cmax = h->cent_norm_max;
+    mp.rc1 = split == 2 ? h->cent_f8_res : h->cent_res1;
+    mp.rc2 = split == 1 ? h->cent_res2 : 0.f;
+    // products of bf16 / e4m3 operands are exact in fp32; their accumulation in TMEM is allowed 2 fp32 ulps of |q'||c'| per
+    // product (x 2 for v = |c|^2 - 2 <.,.>, x 2 for two values compared).  e4m3: the same, but never less than 2^-9 --
+    // kind::f8f6f4 is not documented to keep full fp32 accumulation, and against a margin of ~0.2 |q||c| the allowance is free
+    mp.acc_rel = 1.02f * (float)kdim / 2097152.f;
+    if (split == 2 && mp.acc_rel < 1.f / 512.f) mp.acc_rel = 1.f / 512.f;
+    // fp32 roundings, in ulps (2^-24) of |q|^2 + c_max^2: canonical-vs-true distance 2 x 2 x (d/8 + 5), norms 2 x (d/32 + 5),
+    // epilogue fma + threshold sum 2 x 4
+    mp.abs_rel = 1.01f * (float)(4 * (d / 8 + 5) + 2 * (d / 32 + 5) + 8) / 16777216.f;
+    mp.split = split;
+    return mp;
+}
+
 // max over v[0..n) of non-negative floats (NaN counts as +inf), through slot `slot` of ws_misc; synchronises the stream
 int device_max(rvcr_index* h, const float* v, int64_t n, int slot, float* out, cudaStream_t s) {
     unsigned int* mx = h->ws_misc.as<unsigned int>() + slot;
@@ -809,7 +855,7 @@ int ensure_centroid_operands(rvcr_index* h, int split, cudaStream_t s) {
     // pad centroids get ||c||^2 = +inf: v = +inf, never kept
     tc_prep_rows_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(h->cent, h->nlist, npad, h->d, split, 1,
                                                                        reinterpret_cast<__nv_bfloat16*>(h->cent_bf16),
-                                                                       h->cent_norm, INFINITY, res, npad);
+                                                                       h->cent_norm, INFINITY, res, npad, TcMargin{}, nullptr);
     int rc = cudaGetLastError() == cudaSuccess ? RVCR_OK : RVCR_ERR_CUDA;
     float m2 = 0.f, r1 = 0.f, r2 = 0.f;
     if (rc == RVCR_OK) rc = device_max(h, h->cent_norm, h->nlist, 12, &m2, s);
@@ -853,7 +899,8 @@ int ensure_centroid_operands_f8(rvcr_index* h, cudaStream_t s) {
     RVCR_CUDA(cudaMalloc(&res, (size_t)h->cent_pad * 4));
     const int64_t thr = h->cent_pad * 32;
     tc_prep_rows_f8_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(h->cent, h->nlist, h->cent_pad, h->d, sc, 1.f,
-                                                                          reinterpret_cast<uint8_t*>(h->cent_f8), nullptr, nullptr, 0.f, res);
+                                                                          reinterpret_cast<uint8_t*>(h->cent_f8), nullptr, nullptr, 0.f, res,
+                                                                          TcMargin{}, nullptr);
     int rc = cudaGetLastError() == cudaSuccess ? RVCR_OK : RVCR_ERR_CUDA;
     float r1 = 0.f;
     if (rc == RVCR_OK) rc = device_max(h, res, h->nlist, 62, &r1, s);
@@ -871,6 +918,8 @@ int ensure_centroid_operands_f8(rvcr_index* h, cudaStream_t s) {
 template <int CLUSTER, int NRES, int SB, int SA, int P, int F8 = 0>
 int launch_tc(rvcr_index* h, const CUtensorMap& ta, const CUtensorMap& tb, int num_mblocks, int num_ntiles, int nsplit,
               int tps, int nkb, float* topv, int* topj, cudaStream_t s, const float* qk = nullptr) {
+    float* topd = h->ws_tc7.as<float>();
+    const float* qmargin = h->ws_tc6.as<float>();
     using C = tc::Cfg<CLUSTER, NRES, SB, SA, P>;
     static SmemOptIn opt_in;   // one per template instantiation
     RVCR_TRY(opt_in.ensure(tc::coarse_tc_kernel<CLUSTER, NRES, SB, SA, P, F8>, (size_t)C::SMEM_BYTES, h->device));
@@ -890,7 +939,7 @@ int launch_tc(rvcr_index* h, const CUtensorMap& ta, const CUtensorMap& tb, int n
     cfg.attrs = at;
     cfg.numAttrs = 1;
     RVCR_CUDA(cudaLaunchKernelEx(&cfg, tc::coarse_tc_kernel<CLUSTER, NRES, SB, SA, P, F8>, ta, tb, (const float*)h->cent_norm,
-                                 num_mblocks, num_ntiles, nsplit, tps, nkb, topv, topj, qk));
+                                 num_mblocks, num_ntiles, nsplit, tps, nkb, topv, topj, topd, qk, qmargin));
     return RVCR_OK;
 }
 
@@ -915,7 +964,7 @@ int coarse_tc_invalidate(rvcr_index* h) {
 // Approximate top-8 nearest centroids per (query, split) on the tensor cores.
 // Outputs (device, owned by the handle scratch): topv/topj [n_pad][nsplit][8]; returns nsplit.
 int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int cluster, float** topv_out, int** topj_out,
-                   int* nsplit_out, float** qnorm_out, float** qres_out, int64_t* res_stride_out, cudaStream_t s) {
+                   float** topd_out, int* nsplit_out, float** qnorm_out, float** qmargin_out, cudaStream_t s) {
     // split: 0 = bf16, 1 = bf16 3-way split along K, 2 = e4m3 operands (coarse_mode 4)
     const bool f8 = split == 2;
     const int kelems = f8 ? 2 * tc::BLOCK_K : tc::BLOCK_K;   // elements per 128-byte k-block
@@ -939,17 +988,21 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
             RVCR_TRY(h->ws_tc1.reserve((size_t)n_pad * 4));      // ||q||^2
             RVCR_TRY(h->ws_tc4.reserve((size_t)n_pad * 4));      // -2 / (s_q s_c) per query
             RVCR_TRY(h->ws_tc5.reserve((size_t)n_pad * 2 * 4));  // ||q - q'||
+            RVCR_TRY(h->ws_tc6.reserve((size_t)n_pad * 4));      // margin(q)
             tc_prep_rows_f8_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, n_pad, h->d, 0.f, h->cent_f8_scale,
                                                                                   h->ws_tc0.as<uint8_t>(), h->ws_tc1.as<float>(),
-                                                                                  h->ws_tc4.as<float>(), 0.f, h->ws_tc5.as<float>());
+                                                                                  h->ws_tc4.as<float>(), 0.f, h->ws_tc5.as<float>(),
+                                                                                  make_margin(h, 2), h->ws_tc6.as<float>());
         } else {
         RVCR_TRY(ensure_centroid_operands(h, split, s));
         RVCR_TRY(h->ws_tc0.reserve((size_t)n_pad * kdim * 2));   // bf16 queries
         RVCR_TRY(h->ws_tc1.reserve((size_t)n_pad * 4));          // ||q||^2
         RVCR_TRY(h->ws_tc5.reserve((size_t)n_pad * 2 * 4));      // ||q - q'|| (second plane: 3-way split)
+        RVCR_TRY(h->ws_tc6.reserve((size_t)n_pad * 4));          // margin(q)
         tc_prep_rows_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, n_pad, h->d, split, 0,
                                                                            h->ws_tc0.as<__nv_bfloat16>(), h->ws_tc1.as<float>(), 0.f,
-                                                                           h->ws_tc5.as<float>(), n_pad);
+                                                                           h->ws_tc5.as<float>(), n_pad, make_margin(h, split),
+                                                                           h->ws_tc6.as<float>());
         }
         RVCR_CHECK_LAUNCH();
         count_launch(h);
@@ -974,6 +1027,7 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
     nsplit = (num_ntiles + tps - 1) / tps;
     RVCR_TRY(h->ws_tc2.reserve((size_t)n_pad * nsplit * tc::NCG * tc::TOPT * 4));   // one top-8 per (query, split, column group)
     RVCR_TRY(h->ws_tc3.reserve((size_t)n_pad * nsplit * tc::NCG * tc::TOPT * 4));
+    RVCR_TRY(h->ws_tc7.reserve((size_t)n_pad * nsplit * tc::NCG * 4));               // nearest value each list let go of
     CUtensorMap ta, tb;
     if (f8) {
         RVCR_TRY(make_tmap_u8(&ta, h->ws_tc0.p, n_pad, kdim, tc::BLOCK_M));
@@ -1010,35 +1064,8 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
     *topj_out = h->ws_tc3.as<int>();
     *nsplit_out = nsplit * tc::NCG;   // top-8 lists per query
     *qnorm_out = h->ws_tc1.as<float>();
-    *qres_out = h->ws_tc5.as<float>();
-    *res_stride_out = n_pad;
-    return RVCR_OK;
-}
-
-// the margin parameters of the current centroid operands (split: 0 bf16, 1 3-way bf16 split, 2 e4m3)
-static TcMargin make_margin(const rvcr_index* h, int split) {
-    TcMargin mp;
-    const int d = h->d;
-    const int kdim = split == 1 ? 3 * d : d;
-    mp.cmax = h->cent_norm_max;
-    mp.rc1 = split == 2 ? h->cent_f8_res : h->cent_res1;
-    mp.rc2 = split == 1 ? h->cent_res2 : 0.f;
-    // products of bf16 / e4m3 operands are exact in fp32; their accumulation in TMEM is allowed 2 fp32 ulps of |q'||c'| per
-    // product (x 2 for v = |c|^2 - 2 <.,.>, x 2 for two values compared).  e4m3: the same, but never less than 2^-9 --
-    // kind::f8f6f4 is not documented to keep full fp32 accumulation, and against a margin of ~0.2 |q||c| the allowance is free
-    mp.acc_rel = 1.02f * (float)kdim / 2097152.f;
-    if (split == 2 && mp.acc_rel < 1.f / 512.f) mp.acc_rel = 1.f / 512.f;
-    // fp32 roundings, in ulps (2^-24) of |q|^2 + c_max^2: canonical-vs-true distance 2 x 2 x (d/8 + 5), norms 2 x (d/32 + 5),
-    // epilogue fma + threshold sum 2 x 4
-    mp.abs_rel = 1.01f * (float)(4 * (d / 8 + 5) + 2 * (d / 32 + 5) + 8) / 16777216.f;
-    mp.split = split;
-    return mp;
-}
-
-int coarse_tc_margins(rvcr_index* h, int split, const float* qnorm2, const float* qres, int64_t res_stride, int64_t n,
-                      float* out_dev, cudaStream_t s) {
-    tc_margin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(qnorm2, qres, res_stride, n, make_margin(h, split), out_dev);
-    RVCR_CHECK_LAUNCH();
+    *qmargin_out = h->ws_tc6.as<float>();
+    *topd_out = h->ws_tc7.as<float>();
     return RVCR_OK;
 }
 
@@ -1087,21 +1114,20 @@ int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float
 
 static int coarse_tc_split(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out, int split, cudaStream_t s) {
     const int cluster = h->opt.tc_cluster == 1 ? 1 : 2;
-    float *topv, *qnorm, *qres;
+    float *topv, *topd, *qnorm, *qmargin;
     int* topj;
     int nsplit;
-    int64_t res_stride;
-    RVCR_TRY(coarse_tc_top8(h, q, n, split, cluster, &topv, &topj, &nsplit, &qnorm, &qres, &res_stride, s));
+    RVCR_TRY(coarse_tc_top8(h, q, n, split, cluster, &topv, &topj, &topd, &nsplit, &qnorm, &qmargin, s));
     PhaseTimer pt(h, RVCR_PHASE_COARSE_RECHECK, s);
-    // error margin between two approximate values: tc_margin(), from the exact residual norms of both operands
+    // error margin between two approximate values: tc_margin(), from the exact residual norms of both operands (written per
+    // query by the prep kernel, used by the tensor-core epilogue to collect and here to select)
     RVCR_TRY(h->ws_stage.reserve((size_t)n * 4 + 64));
     int32_t* fb_list = h->ws_stage.as<int32_t>();
     int32_t* counters = h->ws_misc.as<int32_t>() + 16;   // [16] fallbacks of this call; [24..27] running totals
     RVCR_CUDA(cudaMemsetAsync(counters, 0, 4, s));
     const int64_t thr = n * 32;
-    tc_recheck_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, h->d, h->cent, h->nlist, qnorm, qres, res_stride,
-                                                                     make_margin(h, split), topv, topj, nsplit, 0, list_out,
-                                                                     dist_out, fb_list, counters);
+    tc_recheck_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, s>>>(q, n, h->d, h->cent, h->nlist, qmargin, topv, topj, topd,
+                                                                     nsplit, 0, list_out, dist_out, fb_list, counters);
     RVCR_CHECK_LAUNCH();
     count_launch(h);
     RVCR_TRY(coarse_exact_selected(h, q, n, fb_list, counters, list_out, dist_out, s));

@@ -85,8 +85,7 @@ struct Options {
     int64_t profile = 0;      // record CUDA events around each phase's kernels
     int64_t scan_impl = 0;    // 0 auto (default): 5 for batches of >= scan_tc_min_queries, else 4; 5 tcgen05 tf32 + exact
                               // re-check; exact FFMA scans: 1 scalar 8-lane, 2 packed f32x2
-                              // TQx4, 3 same with 16 warps, 4 packed TQx8 tile; 6 = 5 with the re-check folded into the
-                              // scan kernel (scan_tc_fused.cu; experimental, explicit only)
+                              // TQx4, 3 same with 16 warps, 4 packed TQx8 tile
     int64_t tc_cluster = 2;   // tcgen05 path: 1 = one CTA per SM, 2 = CTA pairs (cta_group::2)
     int64_t fused_blend = 1;  // scan_impl 5: re-check kernel also does the gather + weights + blend
     // Size rules of the auto modes, set from measurements (profiles/r01_small_dispatch.json, B200).  The tensor-core scan has
@@ -182,7 +181,8 @@ struct rvcr_index {
     bool scan_fb_dirty = false;
 
     rvcr::DevBuf ws_assign, ws_keys, ws_vals, ws_keys2, ws_vals2, ws_cub, ws_items, ws_flags, ws_misc,
-        ws_D, ws_P, ws_I, ws_best, ws_q, ws_tc0, ws_tc1, ws_tc2, ws_tc3, ws_tc4, ws_tc5, ws_stage;
+        ws_D, ws_P, ws_I, ws_best, ws_q, ws_tc0, ws_tc1, ws_tc2, ws_tc3, ws_tc4, ws_tc5, ws_tc6, ws_tc7, ws_stage;
+    rvcr::DevBuf ws_mp[6];             // nprobe > 1 (multiprobe.cu): probe lists, one column, per-probe D / P / I, distance matrix
     cudaStream_t copy_stream = nullptr;          // host-buffer entry points: H2D chunks overlap the coarse step
     cudaStream_t out_stream = nullptr;           // ... and blended rows stream out while later lists are scanned
     std::vector<cudaEvent_t> copy_events;
@@ -223,9 +223,7 @@ int coarse_tc(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float
               cudaStream_t s);
 bool coarse_tc_available();
 int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int cluster, float** topv_out, int** topj_out,
-                   int* nsplit_out, float** qnorm_out, float** qres_out, int64_t* res_stride_out, cudaStream_t s);
-int coarse_tc_margins(rvcr_index* h, int split, const float* qnorm2, const float* qres, int64_t res_stride, int64_t n,
-                      float* out_dev, cudaStream_t s);
+                   float** topd_out, int* nsplit_out, float** qnorm_out, float** qmargin_out, cudaStream_t s);
 int coarse_tc_invalidate(rvcr_index* h);
 // scan_topk.cu
 int group_queries(rvcr_index* h, const int32_t* assign, int64_t n, bool only_local, cudaStream_t s);
@@ -241,6 +239,9 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
                   int ticket_slot, bool fill, cudaStream_t s);
 int gather_blend_range(rvcr_index* h, const float* feats, int64_t n, const float* D, const int32_t* P, double index_rate,
                        int item_begin, int item_end, float* out, int max_ctas, cudaStream_t s);
+// multiprobe.cu : index.search / retrieve + blend when the index says nprobe > 1
+int search_multiprobe(rvcr_index* h, float* feats_or_q, int64_t n, bool blend, double index_rate, float* D_dev, int64_t* I_dev,
+                      cudaStream_t s);
 // blend.cu
 int gather_blend(rvcr_index* h, float* feats, int64_t n, const float* D, const int32_t* P,
                  const int32_t* assign /*nullable: restrict to owned*/, double index_rate,

@@ -319,8 +319,9 @@ int probe_index_file(const char* path, rvcr_file_info* out, int64_t* sizes_out, 
         out->nonempty_lists = non0;
         out->file_bytes = p.file_bytes;
         out->payload_offset = p.layout == 0 ? p.payload_off : -1;
-        // what rvcr_index_read + rvcr_search accept: the kernels tile the dimension by 128 and implement nprobe = 1
-        out->searchable = (p.ih.d % 128 == 0 && p.ih.trained && p.nprobe == 1) ? 1 : 0;
+        // what rvcr_index_read + rvcr_search accept: the kernels tile the dimension by 128; nprobe 1 (the tuned path) up
+        // to 128 probes (multiprobe.cu)
+        out->searchable = (p.ih.d % 128 == 0 && p.ih.trained && p.nprobe >= 1 && p.nprobe <= 128) ? 1 : 0;
         memcpy(out->fourcc, p.fourcc, 4);
         memcpy(out->quantizer_fourcc, p.qfourcc, 4);
     }

@@ -731,13 +731,6 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     const float absm = 1.f / 524288.f;
     int grid = h->num_sms;
     const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(h->scan_tmaps);
-    const bool fused_recheck = h->opt.scan_impl == 6;   // experimental: re-check + tail as a warp role of the scan kernel
-    if (fused_recheck) {
-        const bool blend_f = h->fuse.active;
-        BlendArgs baf{h->fuse.out, h->last_row_pos, h->fuse.r32, h->fuse.omr32, h->fuse.post, h->fuse.push};
-        const int bmode_f = !blend_f ? 0 : (baf.post.out2 ? 2 : (baf.push.bases ? 3 : 1));
-        RVCR_TRY(launch_scan_tc_fused(h, tm, q, n, rel, absm, item_begin, item_end, ticket_slot, fb_count, D, P, I, baf, bmode_f, s));
-    } else
     stc::scan_tc_kernel<<<grid, stc::THREADS, smem, s>>>(
         tm[0], tm[1], tm[2], tm[3], q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), h->ws_items.as<int32_t>(),
         h->ws_misc.as<int32_t>(), h->ws_misc.as<int32_t>() + ticket_slot, h->offsets, h->row_norm.as<float>(), (uint32_t)h->nlist, n, d,
@@ -749,9 +742,11 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     const bool blend = h->fuse.active;
     BlendArgs ba{h->fuse.out, h->last_row_pos, h->fuse.r32, h->fuse.omr32, h->fuse.post, h->fuse.push};
     const int bmode = !blend ? 0 : (ba.post.out2 ? 2 : (ba.push.bases ? 3 : 1));
-    if (!fused_recheck) {
+    {
         PhaseTimer pt(h, RVCR_PHASE_SCAN_RECHECK, s);
-        // One warp per query, 32 warps per SM.  A variant that staged the candidate rows in shared memory with
+        // One warp per query, 32 warps per SM.  A variant that folded the re-check into the persistent scan kernel as extra
+        // warp roles (round 2, "scan_impl 6": 615 lines, bit-identical results) measured 47.7 ms for the phase against
+        // 32.6 ms for the two kernels and was deleted (profiles/r02_summary.md).  A variant that staged the candidate rows in shared memory with
         // cp.async.bulk (so the fused gather never left the SM) was measured slower (r01: 14.2 vs 8.1 ms at C5 -- with
         // 52 KB per query only 4 warps fit per SM, and the per-query chain header -> copies -> distances -> top-8 ->
         // blend is serial inside a warp) and was removed.
@@ -783,7 +778,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     if (blend) h->fuse.done = true;
     // running total of fallback queries (read back lazily by rvcr_get_stats)
     h->scan_fb_dirty = true;
-    count_launch(h, (fill ? 4 : 3) - (fused_recheck ? 1 : 0));
+    count_launch(h, fill ? 4 : 3);
     return RVCR_OK;
 }
 

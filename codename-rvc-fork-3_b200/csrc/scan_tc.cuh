@@ -1,6 +1,5 @@
-// scan_tc.cuh -- pieces shared by the tensor-core list-scan kernels (scan_tc.cu: streaming scan + separate exact re-check;
-// scan_tc_fused.cu: the same scan with the re-check folded in as a warp role): tile constants, the shared-memory control
-// block, work-item fetch, query staging, and the pipeline.py:500-506 tail arithmetic.
+// scan_tc.cuh -- pieces of the tensor-core list scan (scan_tc.cu: streaming scan + exact re-check): tile constants, the
+// shared-memory control block, work-item fetch, query staging, and the pipeline.py:500-506 tail arithmetic.
 #pragma once
 
 #include <stddef.h>
@@ -171,10 +170,5 @@ __device__ __forceinline__ float4 blend_vec(const float4 (&v)[RVCR_K], const flo
     o.w = __fadd_rn(__fmul_rn(acc.w, r32), __fmul_rn(omr32, f.w));
     return o;
 }
-
-// scan_tc_fused.cu (scan_impl 6, experimental)
-int launch_scan_tc_fused(rvcr_index* h, const CUtensorMap* tm, const float* q, int64_t n, float rel, float absm, int item_begin,
-                         int item_end, int ticket_slot, int32_t* fb_count, float* D, int32_t* P, int64_t* I,
-                         const BlendArgs& ba, int bmode, cudaStream_t s);
 
 }  // namespace rvcr

@@ -917,7 +917,7 @@ int scan_topk(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, in
 int scan_topk_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P, int64_t* I, int item_begin, int item_end,
                     int ticket_slot, bool fill, cudaStream_t s) {
     // scan_impl 0 (auto): the tensor-core scan pays off once a call carries enough queries per list (Options)
-    const bool want_tc = h->opt.scan_impl == 5 || h->opt.scan_impl == 6 || (h->opt.scan_impl == 0 && n >= h->opt.scan_tc_min_queries);
+    const bool want_tc = h->opt.scan_impl == 5 || (h->opt.scan_impl == 0 && n >= h->opt.scan_tc_min_queries);
     if (want_tc && scan_tc_supported(h))
         return scan_tc_range(h, q, n, D, P, I, item_begin, item_end, ticket_slot, fill, s);
     if (h->d % PD_KC != 0) {

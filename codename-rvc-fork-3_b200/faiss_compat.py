@@ -291,7 +291,9 @@ class IndexIVFFlat:
         return {k: int(getattr(s, k)) for k, _ in Stats._fields_ if k != "reserved"}
 
     def debug_coarse_tc(self, q, split: int = 0, cluster: int = 2, cap_pairs: int = 4096):
-        """Raw output of the tcgen05 stage: (v (n, P) f32, j (n, P) i32, ||q||^2 (n,), max||c||, re-check margin (n,))."""
+        """Raw output of the tcgen05 stage: (v (n, P) f32, j (n, P) i32, ||q||^2 (n,), max||c||, re-check margin (n,),
+        dropped (n, P / 8) f32): P / 8 candidate lists per query, each with up to 8 centroids within the margin of the best it
+        saw (free slots +inf / -1) and the smallest v it let go of."""
         import torch
         inf = self._info()
         t = _check_cuda_tensor(q, inf, "debug_coarse_tc")
@@ -300,15 +302,16 @@ class IndexIVFFlat:
         j = np.empty((n, cap_pairs), np.int32)
         qn = np.empty(n, np.float32)
         margin = np.empty(n, np.float32)
+        dropped = np.empty((n, cap_pairs // 8), np.float32)
         pairs = C.c_int32(0)
         cmax = C.c_float(0)
         check(lib().rvcr_debug_coarse_tc(self.handle, C.c_void_p(t.data_ptr()), n, int(split), int(cluster), cap_pairs,
                                          v.ctypes.data_as(C.c_void_p), j.ctypes.data_as(C.c_void_p), C.byref(pairs),
                                          qn.ctypes.data_as(C.c_void_p), C.byref(cmax), margin.ctypes.data_as(C.c_void_p),
-                                         _stream_of(t)))
+                                         dropped.ctypes.data_as(C.c_void_p), _stream_of(t)))
         P = pairs.value
         return (v.reshape(-1)[: n * P].reshape(n, P).copy(), j.reshape(-1)[: n * P].reshape(n, P).copy(), qn,
-                float(cmax.value), margin)
+                float(cmax.value), margin, dropped.reshape(-1)[: n * (P // 8)].reshape(n, P // 8).copy())
 
     PHASES = ("coarse_prep", "coarse_main", "coarse_recheck", "group", "scan", "blend", "scan_recheck", "scan_fallback")
 

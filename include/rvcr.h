@@ -87,7 +87,7 @@ typedef struct rvcr_file_info {
     int64_t nonempty_lists;
     int64_t file_bytes;
     int64_t payload_offset;   /* layout 0: offset of the first list's vectors; -1 for the legacy layouts         */
-    int32_t searchable;       /* 1 if rvcr_index_read + rvcr_search accept it as is (L2, d % 128 == 0, nprobe 1) */
+    int32_t searchable;       /* 1 if rvcr_index_read + rvcr_search accept it as is (L2, d % 128 == 0, nprobe 1..128) */
     char fourcc[8];           /* NUL-terminated                                                                */
     char quantizer_fourcc[8];
     int32_t reserved32;
@@ -141,7 +141,9 @@ RVCR_API int rvcr_index_write(rvcr_index* h, const char* path);
 RVCR_API void rvcr_index_free(rvcr_index* h);
 RVCR_API int rvcr_index_info(rvcr_index* h, rvcr_info* out);
 /* faiss.extract_index_ivf(index).nprobe = v             rvc/train/process/extract_index.py:63-64
- * The value is persisted; search itself supports nprobe == 1 only (RVCR_ERR_UNSUPPORTED). */
+ * The value is persisted and honoured by search: 1 takes the tuned single-list path, 2..128 (a file made by another
+ * fork) the multi-probe path -- nprobe nearest centroids by canonical distance, lists scanned in coarse-rank
+ * order into one top-8 with faiss's strict replacement rule (csrc/multiprobe.cu).  More than 128: RVCR_ERR_UNSUPPORTED. */
 RVCR_API int rvcr_index_set_nprobe(rvcr_index* h, int64_t nprobe);
 /* Quantizer centroids (nlist x d, row-major fp32, host memory). `set` marks the index trained;
  * it is what index.train() produces (extract_index.py:65). */
@@ -278,16 +280,18 @@ RVCR_API int rvcr_get_stats(rvcr_index* h, rvcr_stats* out);
  * around each phase; this synchronises on them and returns the last call's per-phase device time
  * in milliseconds (RVCR_NUM_PHASES floats, -1 for phases that did not run). */
 RVCR_API int rvcr_get_phase_ms(rvcr_index* h, float* ms_out);
-/* Diagnostics for tests: run only the tensor-core stage of the coarse quantizer (coarse_tc.cu) and
- * return its raw output -- per query, `*pairs_out` = 8 * (number of centroid splits) approximate
- * (v = ||c||^2 - 2<q,c>, centroid id) pairs -- to host buffers of capacity cap_pairs per query,
- * plus ||q||^2 per query, max ||c||, and (margin_host, n floats, nullable) the margin the exact re-check uses for each
- * query: two approximate values further apart than that are ordered like the true distances (built from the exact
- * norms of what the low-precision operands drop, coarse_tc.cu tc_margin).  split: 0 = bf16, 1 = 3-way split bf16,
+/* Diagnostics for tests: run only the tensor-core stage of the coarse quantizer (coarse_tc.cu) and return its raw
+ * output to host buffers: per query `*pairs_out` = 8 * L approximate (v = ||c||^2 - 2<q,c>, centroid id) pairs (L lists:
+ * centroid splits x the epilogue's column groups; each list holds up to 8 centroids whose v is within the query's
+ * margin of the smallest v the list saw, unsorted, free slots v = +inf / id = -1), capacity cap_pairs per query; plus
+ * ||q||^2 per query, max ||c||, (margin_host, n floats, nullable) the margin the epilogue collects with and the exact
+ * re-check selects with -- two approximate values further apart than that are ordered like the true distances (built
+ * from the exact norms of what the low-precision operands drop, coarse_tc.cu tc_margin) -- and (dropped_host, n x L floats,
+ * nullable) per list the smallest v it had to let go of (+inf: nothing).  split: 0 = bf16, 1 = 3-way split bf16,
  * 2 = e4m3; cluster: 1 | 2. */
 RVCR_API int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t split, int32_t cluster,
                                   int32_t cap_pairs, float* v_host, int32_t* j_host, int32_t* pairs_out,
-                                  float* qnorm2_host, float* cmax_out, float* margin_host, void* stream);
+                                  float* qnorm2_host, float* cmax_out, float* margin_host, float* dropped_host, void* stream);
 
 /* Host-only pieces of rvcr_index_train, exposed so that they can be checked without a GPU: faiss rand_perm
  * (identity, then swap(perm[i], perm[i + mt() % (n - i)]) with std::mt19937(seed)) and faiss split_clusters

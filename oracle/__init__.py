@@ -53,6 +53,8 @@ def lib():
         L.rvco_set_num_threads.argtypes = [C.c_int]
         L.rvco_coarse_assign.restype = None
         L.rvco_coarse_assign.argtypes = [fp, C.c_int64, fp, C.c_int64, C.c_int, C.c_int, ip, fp, dp]
+        L.rvco_coarse_topn.restype = None
+        L.rvco_coarse_topn.argtypes = [fp, C.c_int64, fp, C.c_int64, C.c_int, C.c_int, ip, fp]
         L.rvco_scan_topk.restype = None
         L.rvco_scan_topk.argtypes = [fp, C.c_int64, ip, lp, fp, lp, C.c_int, C.c_int, C.c_int, fp, lp, lp]
         L.rvco_tail.restype = None
@@ -104,6 +106,39 @@ def coarse_assign(q, centroids, fma: bool = True, want_gap: bool = False):
                              _p(out, C.c_int32), _p(dist, C.c_float),
                              _p(gap, C.c_double) if want_gap else None)
     return (out, dist, gap) if want_gap else (out, dist)
+
+
+def coarse_topn(q, centroids, nprobe: int):
+    """The nprobe nearest centroids per query (canonical distance, ascending; lower id first among equal distances):
+    quantizer->search(n, x, nprobe) of IndexIVF::search (SURVEY A3).  Returns (lists int32[nq, nprobe], dist f32[nq, nprobe]);
+    missing entries (NaN queries, nprobe > nlist) are -1 / FLT_MAX."""
+    q, cent = _f32(q), _f32(centroids)
+    nq, d = q.shape
+    nprobe = int(nprobe)
+    assert nprobe >= 1 and cent.shape[1] == d and d % 8 == 0
+    out = np.empty((nq, nprobe), np.int32)
+    dist = np.empty((nq, nprobe), np.float32)
+    lib().rvco_coarse_topn(_p(q, C.c_float), nq, _p(cent, C.c_float), cent.shape[0], d, nprobe, _p(out, C.c_int32),
+                           _p(dist, C.c_float))
+    return out, dist
+
+
+def scan_topk_multi(q, lists, list_off, vecs, ids, k: int = 8, want_pos: bool = False):
+    """IndexIVF::search_preassigned with nprobe > 1 (SURVEY A3/A6): the probed lists are scanned in coarse-rank order
+    into ONE k-heap with the strict replacement rule, so among equal distances the entry scanned first (lower probe
+    rank, then lower list position) is the one kept / listed first.  Restated as: top-k of each list (same scan as
+    nprobe = 1), concatenated in probe order, stable sort by distance."""
+    lists = np.ascontiguousarray(lists, np.int32)
+    nq, nprobe = lists.shape
+    Ds, Is, Ps = [], [], []
+    for p in range(nprobe):
+        D, I, P = scan_topk(q, lists[:, p], list_off, vecs, ids, k=k, want_pos=True)
+        Ds.append(D), Is.append(I), Ps.append(P)
+    D, I, P = np.concatenate(Ds, 1), np.concatenate(Is, 1), np.concatenate(Ps, 1)
+    order = np.argsort(D, axis=1, kind="stable")[:, :k]
+    rows = np.arange(nq)[:, None]
+    D, I, P = D[rows, order], I[rows, order], P[rows, order]
+    return (D, I, P) if want_pos else (D, I)
 
 
 def coarse_assign_blas(q, centroids, block: int = 4096):
@@ -309,7 +344,11 @@ class OracleIndex:
         out[self.ids[sel] - i0] = self.vecs[sel]
         return out
 
-    def search(self, q, k: int = 8, fma: bool = True):
+    def search(self, q, k: int = 8, fma: bool = True, nprobe: int | None = None):
+        nprobe = min(self.nlist, self.nprobe if nprobe is None else int(nprobe))     # IndexIVF::search clamps to nlist
+        if nprobe > 1:
+            lists, _ = coarse_topn(q, self.centroids, nprobe)
+            return scan_topk_multi(q, lists, self.list_off, self.vecs, self.ids, k=k)
         a, _ = coarse_assign(q, self.centroids, fma=fma)
         return scan_topk(q, a, self.list_off, self.vecs, self.ids, k=k, fma=fma)
 

@@ -134,6 +134,41 @@ RVCO_API void rvco_coarse_assign(const float* q, int64_t nq, const float* cent, 
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* coarse quantizer, k = nprobe > 1 (IndexIVF::search -> quantizer->search(n, x, nprobe); a file written  */
+/* by another fork may carry any nprobe, Appendix B offset 45).  The nprobe nearest centroids by canonical distance,     */
+/* ascending; among equal distances the lower centroid id first (faiss's k > 1 heap leaves that order                    */
+/* implementation-defined: documented tie).  Queries with a NaN distance everywhere get -1 ids and FLT_MAX distances.    */
+RVCO_API void rvco_coarse_topn(const float* q, int64_t nq, const float* cent, int64_t nlist, int d, int nprobe,
+                               int32_t* list_out /* nq x nprobe */, float* dist_out /* nq x nprobe, optional */) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < nq; ++i) {
+        const float* x = q + i * d;
+        int32_t* lo = list_out + i * nprobe;
+        float bd[nprobe];
+        int cnt = 0;
+        for (int64_t j = 0; j < nlist; ++j) {
+            float dis = l2sqr_fma(x, cent + j * d, d);
+            if (!(dis == dis)) continue;
+            if (cnt == nprobe && !(dis < bd[cnt - 1])) continue;   /* strict: an equal distance with a higher id stays out */
+            int p = cnt < nprobe ? cnt++ : nprobe - 1;
+            while (p > 0 && dis < bd[p - 1]) {
+                bd[p] = bd[p - 1];
+                lo[p] = lo[p - 1];
+                --p;
+            }
+            bd[p] = dis;
+            lo[p] = (int32_t)j;
+        }
+        for (int p = cnt; p < nprobe; ++p) {
+            bd[p] = FLT_MAX;
+            lo[p] = -1;
+        }
+        if (dist_out)
+            for (int p = 0; p < nprobe; ++p) dist_out[i * nprobe + p] = bd[p];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* inverted-list scan, nprobe = 1 (IVFFlatScanner<L2,CMax>::scan_codes + heap).      */
 /* The faiss max-heap keeps, among equal distances at the k-th boundary, the entry scanned      */
 /* first (strict "top > dis").  The order faiss gives to EQUAL distances inside the top-k is    */

@@ -63,15 +63,16 @@ def test_files_from_other_writers(rvcr, oracle, tmp_path):
     f3 = bytearray(raw[:dm]) + bytes([2]) + struct.pack("<Q", 0) + struct.pack("<Q", n) + pairs + raw[dm + 9:]
     (tmp_path / "dm_hash.index").write_bytes(f3)
     check_same_answers(rvcr, str(tmp_path / "dm_hash.index"), b)
-    # nprobe taken from the header; the search path only implements the reference's nprobe = 1 (extract_index.py:64)
+    # nprobe taken from the header and honoured (faiss does: IndexIVF::search reads the stored field)
     f4 = bytearray(raw)
     struct.pack_into("<Q", f4, b["off_nprobe"], 4)
     (tmp_path / "np4.index").write_bytes(f4)
     idx = rvcr.read_index(str(tmp_path / "np4.index"))
     assert idx.nprobe == 4
-    with pytest.raises(rvcr.RvcrError) as e:
-        idx.search(b["q"], k=8)
-    assert e.value.code == -5
+    D, I = idx.search(b["q"], k=8)
+    Do, Io = b["oidx"].search(b["q"], k=8, nprobe=4)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+    assert not np.array_equal(I, b["oidx"].search(b["q"], k=8)[1])       # and it matters on this data
     idx.nprobe = 1
     D, I = idx.search(b["q"], k=8)
     assert np.array_equal(I, b["oidx"].search(b["q"], k=8)[1])

@@ -244,9 +244,11 @@ def test_api_errors_and_empty(rvcr, oracle, tmp_path):
     with pytest.raises(rvcr.RvcrError) as e:
         index.search(x[:2], k=4)
     assert e.value.code == -5
-    index.nprobe = 4
+    index.nprobe = 1000                                     # clamped to nlist like IndexIVF::search: every list is scanned
+    D, I = index.search(x[:2], k=8)
+    assert I[0, 0] == 0 and D[0, 0] == 0 and I[1, 0] == 1
     with pytest.raises(rvcr.RvcrError):
-        index.search(x[:2], k=8)
+        index.set_option("nosuchoption", 1)
     index.nprobe = 1
     with pytest.raises(AssertionError):
         index.search(x[:2, :64], k=8)

@@ -2,7 +2,6 @@
 scan (scan_impl = 4).  The tensor-core pass only nominates candidates; the re-check evaluates the canonical
 fp32 distance, so ids AND distances must be bit-identical -- including ties, duplicates, short lists and
 the overflow path that falls back to the brute-force exact kernel."""
-import os
 from importlib import import_module
 
 import numpy as np
@@ -10,9 +9,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-# RVCR_TEST_SCAN_IMPL=6 runs this whole file against the experimental fused scan + re-check kernel (csrc/scan_tc_fused.cu),
-# which must give the same bits; the default suite tests the shipped tensor-core scan (5).
-TC_IMPL = int(os.environ.get("RVCR_TEST_SCAN_IMPL", "5"))
+TC_IMPL = 5
 
 
 def _build(rvcr, x, cent):

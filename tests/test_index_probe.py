@@ -111,7 +111,7 @@ def test_probe_other_writers_and_refusals(rvcr, oracle, tmp_path):
     f4 = bytearray(raw)
     struct.pack_into("<Q", f4, o["nprobe"], 4)
     i4 = rvcr.probe_index(write(tmp_path, "np4.index", f4))
-    assert i4["nprobe"] == 4 and i4["searchable"] == 0             # read_index loads it, search needs nprobe = 1
+    assert i4["nprobe"] == 4 and i4["searchable"] == 1             # honoured by the multi-probe search path
     # trailing bytes after the payload are ignored, like faiss
     assert rvcr.probe_index(write(tmp_path, "trail.index", raw + b"xyz" * 11))["nvectors"] == n
     # an empty-lists object ("il00")

@@ -194,3 +194,33 @@ def test_documented_tie_zone_is_small_and_classified(oracle, golden):
         cols = np.nonzero(I1[r] != I2[r])[0]
         assert np.allclose(D1[r, cols], D2[r, cols], rtol=2e-6, atol=0)
     assert differ.mean() <= 0.05
+
+
+def test_nprobe_restatement_against_brute_force(oracle):
+    """nprobe > 1: the probe lists are the nprobe nearest centroids in (distance, id) order, probing every
+    list equals a brute-force search over all stored rows, and probe rank breaks distance ties across lists."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((3000, 64)).astype(np.float32)
+    cent = x[rng.choice(3000, 40, replace=False)].copy()
+    q = (x[:200] + 0.3 * rng.standard_normal((200, 64))).astype(np.float32)
+    idx = oracle.OracleIndex.from_vectors(x, cent)
+    lists, dist = oracle.coarse_topn(q, cent, 5)
+    d64 = ((q[:, None, :].astype(np.float64) - cent[None].astype(np.float64)) ** 2).sum(-1)
+    assert np.array_equal(lists, np.argsort(d64, 1, kind="stable")[:, :5])
+    assert np.array_equal(lists[:, 0], oracle.coarse_assign(q, cent)[0]) and (np.diff(dist, axis=1) >= 0).all()
+    Dm, Im = idx.search(q, nprobe=40)
+    dall = ((q[:, None, :].astype(np.float64) - x[None].astype(np.float64)) ** 2).sum(-1)
+    assert np.array_equal(Im, np.argsort(dall, 1, kind="stable")[:, :8])
+    assert np.array_equal(idx.search(q, nprobe=1000)[1], Im)                     # clamped to nlist
+    # the same row stored in two lists: the copy in the list probed first is reported first, the other right after it
+    x2 = np.concatenate([x, x[:1]])
+    a = oracle.coarse_assign(x2, cent)[0]
+    l2 = oracle.coarse_topn(x2[:1], cent, 2)[0][0]
+    a[-1] = l2[1]                                                               # force the duplicate into the 2nd-nearest list
+    off, vecs, ids = oracle.build_lists(x2, a, 40)
+    idx2 = oracle.OracleIndex(64, cent, off, vecs, ids, len(x2), nprobe=2)
+    D, I = idx2.search(x2[:1])
+    assert D[0, 0] == 0 and D[0, 1] == 0 and I[0, 0] == 0 and I[0, 1] == len(x2) - 1
+    qn = q[:2].copy()
+    qn[0, 3] = np.nan
+    assert (oracle.coarse_topn(qn, cent, 3)[0][0] == -1).all() and (idx.search(qn, nprobe=3)[1][0] == -1).all()
