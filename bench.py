@@ -528,7 +528,7 @@ def main():
         transport = "nccl all-to-all (dispatch + combine)"
         if not args.no_peer:
             try:                                                   # collective: raises on every rank or on none
-                peer = sh.enable_peer((R + 2) * n_home + 16, d)
+                peer = sh.enable_peer((R + 2) * n_home + 16, d, max_batch_rows=-(-nq // world))
                 transport = sh.transport_name()
             except Exception as ex:
                 transport += f"; peer memory unavailable: {str(ex)[:160]}"

@@ -8,12 +8,12 @@ or through the `rvcr` alias module at the repo root.
 Host side only: every number is computed by librvcr.so (hand-written sm_100a CUDA, include/rvcr.h).
 """
 from ._ffi import RvcrError, device_count, lib  # noqa: F401
-from .faiss_compat import (METRIC_L2, IndexCache, IndexIVFFlat, LazyBigNpy, enable_index_cache,  # noqa: F401
-                           extract_index_ivf, index_cache, index_factory, probe_index, read_index, shard_range,
-                           upsample_protect, write_index)
+from .faiss_compat import (METRIC_L2, IndexCache, IndexIVFFlat, LazyBigNpy, MiniBatchKMeans, enable_index_cache,  # noqa: F401
+                           extract_index_ivf, final_proj, index_cache, index_factory, probe_index, read_index,
+                           shard_range, upsample_protect, write_index)
 from . import sharded, synth  # noqa: F401
 from .retrieve import convert_features, patch_pipeline, retrieve_speaker_embeddings  # noqa: F401
 
 __all__ = ["IndexIVFFlat", "read_index", "write_index", "index_factory", "extract_index_ivf", "METRIC_L2",
            "retrieve_speaker_embeddings", "patch_pipeline", "enable_index_cache", "index_cache", "IndexCache",
-           "LazyBigNpy", "upsample_protect", "probe_index", "shard_range", "convert_features", "RvcrError", "device_count", "lib"]
+           "LazyBigNpy", "upsample_protect", "final_proj", "MiniBatchKMeans", "probe_index", "shard_range", "convert_features", "RvcrError", "device_count", "lib"]

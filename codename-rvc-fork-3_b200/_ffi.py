@@ -38,6 +38,12 @@ class FileInfo(C.Structure):
                 ("reserved32", C.c_int32), ("reserved", C.c_int64 * 4)]
 
 
+class MbkStats(C.Structure):
+    _fields_ = [("n_steps", C.c_int64), ("max_steps", C.c_int64), ("batch_size", C.c_int64), ("init_size", C.c_int64),
+                ("n_reassigned", C.c_int64), ("kernels_launched", C.c_int64), ("converged", C.c_int32), ("rows_resident", C.c_int32),
+                ("ewa_inertia", C.c_double), ("init_inertia", C.c_double), ("reserved", C.c_int64 * 4)]
+
+
 class Stats(C.Structure):
     _fields_ = [("calls_search", C.c_int64), ("queries", C.c_int64), ("kernels_launched", C.c_int64),
                 ("coarse_tc_queries", C.c_int64), ("coarse_candidates", C.c_int64),
@@ -80,6 +86,8 @@ SIGNATURES = {
     "rvcr_retrieve_blend": (C.c_int, [_H, _P, _I64, C.c_double, _P, _P, _P]),
     "rvcr_retrieve_blend_upsample": (C.c_int, [_H, _P, _I64, C.c_double, _P, C.c_double, _P, _P, _P, _P]),
     "rvcr_upsample_protect": (C.c_int, [_P, _P, _P, _I64, _I32, C.c_double, _P, C.c_int, _P]),
+    "rvcr_final_proj": (C.c_int, [_P, _I64, _I32, _P, _P, _I32, _P, C.c_int, _P]),
+    "rvcr_final_proj_retrieve_blend": (C.c_int, [_H, _P, _I64, _I32, _P, _P, _P, C.c_double, _P, _P, _P]),
     "rvcr_retrieve_blend_host": (C.c_int, [_H, _P, _I64, C.c_double]),
     "rvcr_retrieve_blend_assigned": (C.c_int, [_H, _P, _I64, _P, C.c_double, _P, _P, _P]),
     "rvcr_retrieve_blend_assigned_push": (C.c_int, [_H, _P, _I64, _P, C.c_double, _P, _P, _P, _P]),
@@ -88,6 +96,9 @@ SIGNATURES = {
     "rvcr_peer_close": (C.c_int, [C.c_int, _P]),
     "rvcr_peer_free": (C.c_int, [C.c_int, _P]),
     "rvcr_peer_pull_rows": (C.c_int, [_P, _P, _P, _I64, _I32, _P, C.c_int, _P]),
+    "rvcr_peer_dispatch": (C.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P, _I64, C.c_int, _P]),
+    "rvcr_peer_barrier": (C.c_int, [_P, _I32, _I32, _I32, C.c_int, _P]),
+    "rvcr_retrieve_blend_inbox_push": (C.c_int, [_H, _P, _I64, _P, C.c_double, _P, _P]),
     "rvcr_search_assigned": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P]),
     "rvcr_reconstruct_n": (C.c_int, [_H, _I64, _I64, _P, C.c_int]),
     "rvcr_merge_coarse": (C.c_int, [_P, _P, _I32, _I64, _P, C.c_int, _P]),
@@ -96,6 +107,8 @@ SIGNATURES = {
     "rvcr_get_option": (C.c_int, [_H, C.c_char_p, C.POINTER(_I64)]),
     "rvcr_get_stats": (C.c_int, [_H, C.POINTER(Stats)]),
     "rvcr_get_phase_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "rvcr_minibatch_kmeans": (C.c_int, [_P, _I64, _I32, _I64, _I64, _I64, _I64, C.c_double, _I64, C.c_uint64, C.c_int, C.c_int, _P,
+                                        C.POINTER(MbkStats)]),
     "rvcr_debug_rand_perm": (C.c_int, [_I64, _I64, _P]),
     "rvcr_debug_split_clusters": (C.c_int, [_I32, _I64, _I64, _P, _P, C.POINTER(_I32)]),
     "rvcr_debug_coarse_tc": (C.c_int, [_H, _P, _I64, _I32, _I32, _I32, _P, _P, C.POINTER(_I32), _P,

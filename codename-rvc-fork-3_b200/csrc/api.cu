@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <random>
 
 #include "common.cuh"
 
@@ -74,6 +75,24 @@ int stream_leave(rvcr_index* h, cudaStream_t s) {
     return RVCR_OK;
 }
 
+// Every entry point that touches the handle's shared scratch enters the stream BEFORE its first access (host variants
+// included: their memcpys into ws_q would otherwise race with a previous asynchronous call on another stream) and records
+// the leave event on every way out, error returns too, so last_stream / last_done never go stale.
+struct StreamScope {
+    rvcr_index* h;
+    cudaStream_t s;
+    bool entered = false;
+    StreamScope(rvcr_index* h_, cudaStream_t s_) : h(h_), s(s_) {}
+    int enter() {
+        const int rc = stream_enter(h, s);
+        entered = rc == RVCR_OK;
+        return rc;
+    }
+    ~StreamScope() {
+        if (entered) stream_leave(h, s);
+    }
+};
+
 int check_searchable(rvcr_index* h, int32_t k) {
     if (!h->trained) {
         set_error("index is not trained (no centroids)");
@@ -119,8 +138,9 @@ int search_device(rvcr_index* h, float* feats_or_q, int64_t n, const int32_t* as
     }
     RVCR_TRY(check_searchable(h, RVCR_K));
     if (n == 0) return RVCR_OK;
+    StreamScope scope(h, s);
+    RVCR_TRY(scope.enter());
     RVCR_TRY(finalize_pending(h, s));
-    RVCR_TRY(stream_enter(h, s));
     // a caller-supplied assignment came from an earlier rvcr_assign call: keep its coarse phase timings
     for (int i = assign_in ? RVCR_PHASE_GROUP : 0; i < RVCR_NUM_PHASES; ++i) h->pev_used[i] = false;
     if (h->nprobe > 1 && h->nlist > 1) {
@@ -128,8 +148,7 @@ int search_device(rvcr_index* h, float* feats_or_q, int64_t n, const int32_t* as
             set_error("a caller-supplied list assignment carries one list per query; this index has nprobe=%lld", (long long)h->nprobe);
             return RVCR_ERR_UNSUPPORTED;
         }
-        RVCR_TRY(search_multiprobe(h, feats_or_q, n, blend, index_rate, D_dev, I_dev, s));
-        return stream_leave(h, s);
+        return search_multiprobe(h, feats_or_q, n, blend, index_rate, D_dev, I_dev, s);
     }
     const int32_t* assign = assign_in;
     if (!assign) {
@@ -164,7 +183,7 @@ int search_device(rvcr_index* h, float* feats_or_q, int64_t n, const int32_t* as
     }
     h->stats.calls_search += 1;
     h->stats.queries += n;
-    return stream_leave(h, s);
+    return RVCR_OK;
 }
 
 // Append n rows (ids ntotal .. ntotal+n-1) with their list assignment to the id-ordered staging
@@ -209,6 +228,12 @@ int stage_rows(rvcr_index* h, const float* x_dev, int64_t n, const int32_t* assi
 int coarse_dispatch_for_train(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, cudaStream_t s) {
     return coarse_dispatch(h, q, n, list_out, nullptr, s);
 }
+// minibatch_kmeans.cu's E-step: nearest centre and its canonical distance
+int coarse_dispatch_dist(rvcr_index* h, const float* q, int64_t n, int32_t* list_out, float* dist_out, cudaStream_t s) {
+    return coarse_dispatch(h, q, n, list_out, dist_out, s);
+}
+int minibatch_kmeans(rvcr_index* h, const float* x_host, int64_t n, int64_t batch_size, int64_t max_iter, int64_t max_no_improvement,
+                     double reassignment_ratio, int64_t n_init, uint64_t seed, int verbose, float* centers_out, rvcr_mbk_stats* st_out);
 }  // namespace rvcr
 
 using namespace rvcr;
@@ -315,6 +340,12 @@ int rvcr_index_read_shard(const char* path, int device, int rank, int world, rvc
 int rvcr_index_write(rvcr_index* h, const char* path) {
     RVCR_ENTER(h);
     if (!path) return RVCR_ERR_INVALID;
+    if (!h->trained) {
+        // faiss would serialise an empty quantizer; the reference never does (train comes before write, extract_index.py:
+        // 65-71) and this library's own reader refuses such a file, so say so here instead of writing one
+        set_error("write_index on an untrained index (no centroids): train or set the centroids first");
+        return RVCR_ERR_STATE;
+    }
     RVCR_TRY(finalize_pending(h, nullptr));
     RVCR_CUDA(cudaDeviceSynchronize());
     return write_index_file(h, path);
@@ -433,6 +464,25 @@ int rvcr_index_train(rvcr_index* h, const float* x_host, int64_t n) {
     return kmeans_train(h, x_host, n, nullptr);
 }
 
+int rvcr_minibatch_kmeans(const float* x_host, int64_t n, int32_t d, int64_t k, int64_t batch_size, int64_t max_iter,
+                          int64_t max_no_improvement, double reassignment_ratio, int64_t n_init, uint64_t seed, int device, int verbose,
+                          float* centers_out_host, rvcr_mbk_stats* stats_out) {
+    if (!x_host || !centers_out_host || n <= 0 || d <= 0 || k <= 0) {
+        set_error("minibatch_kmeans: bad arguments");
+        return RVCR_ERR_INVALID;
+    }
+    rvcr_index* h = nullptr;
+    RVCR_TRY(rvcr_index_create(d, k, device, &h));
+    if (seed == 0) {
+        std::random_device rd;
+        seed = ((uint64_t)rd() << 32) ^ (uint64_t)rd() ^ 0x9e3779b97f4a7c15ull;
+    }
+    const int rc = minibatch_kmeans(h, x_host, n, batch_size, max_iter, max_no_improvement, reassignment_ratio, n_init, seed, verbose,
+                                    centers_out_host, stats_out);
+    rvcr_index_free(h);
+    return rc;
+}
+
 int rvcr_debug_rand_perm(int64_t n, int64_t seed, int64_t* perm_out_host) {
     if (n < 0 || (n > 0 && !perm_out_host)) return RVCR_ERR_INVALID;
     kmeans_debug_rand_perm(n, seed, perm_out_host);
@@ -467,7 +517,8 @@ int rvcr_index_add(rvcr_index* h, const float* x, int64_t n, int x_on_device, vo
         set_error("index.add on an untrained index");
         return RVCR_ERR_STATE;
     }
-    RVCR_TRY(stream_enter(h, s));
+    StreamScope scope(h, s);
+    RVCR_TRY(scope.enter());
     const float* xd = x;
     if (!x_on_device) {
         RVCR_TRY(h->ws_q.reserve((size_t)n * h->d * sizeof(float)));
@@ -478,7 +529,6 @@ int rvcr_index_add(rvcr_index* h, const float* x, int64_t n, int x_on_device, vo
     int32_t* assign = h->ws_assign.as<int32_t>();
     RVCR_TRY(coarse_dispatch(h, xd, n, assign, nullptr, s));
     RVCR_TRY(stage_rows(h, xd, n, assign, s));
-    RVCR_TRY(stream_leave(h, s));
     // a pageable host buffer may be reused by the caller as soon as we return
     if (!x_on_device) RVCR_CUDA(cudaStreamSynchronize(s));
     return RVCR_OK;
@@ -545,10 +595,10 @@ int rvcr_assign(rvcr_index* h, const float* x_dev, int64_t n, int32_t* list_out_
         return RVCR_ERR_STATE;
     }
     if (n == 0) return RVCR_OK;
-    RVCR_TRY(stream_enter(h, s));
+    StreamScope scope(h, s);
+    RVCR_TRY(scope.enter());
     for (int i = 0; i < RVCR_NUM_PHASES; ++i) h->pev_used[i] = false;
-    RVCR_TRY(coarse_dispatch(h, x_dev, n, list_out_dev, dist_out_dev, s));
-    return stream_leave(h, s);
+    return coarse_dispatch(h, x_dev, n, list_out_dev, dist_out_dev, s);
 }
 
 int rvcr_search(rvcr_index* h, const float* q_dev, int64_t n, int32_t k, float* D_dev, int64_t* I_dev, void* stream) {
@@ -564,6 +614,8 @@ int rvcr_search_host(rvcr_index* h, const float* q_host, int64_t n, int32_t k, f
     RVCR_TRY(check_searchable(h, k));
     if (n <= 0) return n < 0 ? RVCR_ERR_INVALID : RVCR_OK;
     cudaStream_t s = nullptr;
+    StreamScope scope(h, s);
+    RVCR_TRY(scope.enter());
     RVCR_TRY(h->ws_q.reserve((size_t)n * h->d * sizeof(float)));
     RVCR_TRY(h->ws_D.reserve((size_t)n * RVCR_K * 4));
     RVCR_TRY(h->ws_I.reserve((size_t)n * RVCR_K * 8));
@@ -618,6 +670,31 @@ int rvcr_upsample_protect(const float* feats_dev, const float* feats0_dev, const
     return upsample_protect(feats_dev, feats0_dev, pitchf_dev, n, d, protect, out_dev, (cudaStream_t)stream);
 }
 
+int rvcr_final_proj(const float* x_dev, int64_t n, int32_t d_in, const float* w_dev, const float* b_dev, int32_t d_out,
+                    float* out_dev, int device, void* stream) {
+    if (n < 0 || d_in < 1 || d_out < 1 || (n > 0 && (!x_dev || !w_dev || !out_dev))) return RVCR_ERR_INVALID;
+    DeviceGuard g(device);
+    if (!g.ok) {
+        set_error("cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return RVCR_ERR_CUDA;
+    }
+    return final_proj(x_dev, n, d_in, w_dev, b_dev, d_out, out_dev, (cudaStream_t)stream);
+}
+
+int rvcr_final_proj_retrieve_blend(rvcr_index* h, const float* x_dev, int64_t n, int32_t d_in, const float* w_dev,
+                                   const float* b_dev, float* feats_out_dev, double index_rate, float* D_dev, int64_t* I_dev,
+                                   void* stream) {
+    RVCR_ENTER(h);
+    if (n < 0 || d_in < 1 || (n > 0 && (!x_dev || !w_dev || !feats_out_dev))) return RVCR_ERR_INVALID;
+    if (n > 0 && (const float*)feats_out_dev == x_dev) {
+        set_error("final_proj_retrieve_blend: the projected rows (n x %d) must not alias the encoder rows (n x %d)", h->d, d_in);
+        return RVCR_ERR_INVALID;
+    }
+    RVCR_TRY(final_proj(x_dev, n, d_in, w_dev, b_dev, h->d, feats_out_dev, (cudaStream_t)stream));
+    count_launch(h);
+    return search_device(h, feats_out_dev, n, nullptr, true, index_rate, D_dev, I_dev, (cudaStream_t)stream);
+}
+
 int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double index_rate) {
     RVCR_ENTER(h);
     if (n > 0 && !feats_host) return RVCR_ERR_INVALID;
@@ -628,12 +705,13 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     // independent).  The list scan needs the whole batch grouped by list, so it starts after the last
     // chunk; the blended rows come back with one device -> host copy.
     cudaStream_t s = nullptr;
+    StreamScope scope(h, s);
+    RVCR_TRY(scope.enter());
     const size_t rowb = (size_t)h->d * sizeof(float);
     RVCR_TRY(h->ws_q.reserve((size_t)n * rowb));
     RVCR_TRY(h->ws_assign.reserve((size_t)n * 4));
     RVCR_TRY(finalize_pending(h, s));
     if (h->nprobe > 1 && h->nlist > 1) {   // interop path (multiprobe.cu): plain copy in, search + blend, copy out
-        RVCR_TRY(stream_enter(h, s));
         RVCR_CUDA(cudaMemcpyAsync(h->ws_q.p, feats_host, (size_t)n * rowb, cudaMemcpyHostToDevice, s));
         RVCR_TRY(search_device(h, h->ws_q.as<float>(), n, nullptr, true, index_rate, nullptr, nullptr, s));
         RVCR_CUDA(cudaMemcpyAsync(feats_host, h->ws_q.p, (size_t)n * rowb, cudaMemcpyDeviceToHost, s));
@@ -658,7 +736,6 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
         RVCR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         h->copy_events.push_back(e);
     }
-    RVCR_TRY(stream_enter(h, s));
     for (int i = 0; i < RVCR_NUM_PHASES; ++i) h->pev_used[i] = false;
     char* dq = reinterpret_cast<char*>(h->ws_q.p);
     const bool trace = getenv("RVCR_HOST_TRACE") != nullptr;
@@ -697,7 +774,7 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     // on a second stream, so the PCIe write-back of wave k overlaps the scan of wave k+1.
     cudaPointerAttributes pat;
     const bool mapped = cudaPointerGetAttributes(&pat, feats_host) == cudaSuccess && pat.type == cudaMemoryTypeHost &&
-                        pat.devicePointer != nullptr && (h->opt.scan_impl == 0 || h->opt.scan_impl == 4 || h->opt.scan_impl == 5);
+                        pat.devicePointer != nullptr;
     cudaGetLastError();
     if (!mapped) {
         RVCR_TRY(search_device(h, h->ws_q.as<float>(), n, h->ws_assign.as<int32_t>(), true, index_rate, nullptr, nullptr, s));
@@ -764,7 +841,6 @@ int rvcr_retrieve_blend_host(rvcr_index* h, float* feats_host, int64_t n, double
     h->stats.queries += n;
     RVCR_CUDA(cudaStreamSynchronize(h->out_stream));
     RVCR_CUDA(cudaStreamSynchronize(s));
-    RVCR_TRY(stream_leave(h, s));
     return RVCR_OK;
 }
 
@@ -793,6 +869,57 @@ int rvcr_retrieve_blend_assigned_push(rvcr_index* h, const float* rows_dev, int6
     return rc;
 }
 
+int rvcr_peer_dispatch(const int32_t* assign_dev, int64_t n, int64_t row0, int32_t my_rank, int32_t G, const int32_t* bounds_dev,
+                       void* const* inbox_bases_dev, int64_t cap, int device, void* stream) {
+    if (n < 0 || cap <= 0 || my_rank < 0 || my_rank >= G || !inbox_bases_dev || (n > 0 && !assign_dev) || (G > 1 && !bounds_dev))
+        return RVCR_ERR_INVALID;
+    DeviceGuard g(device);
+    if (!g.ok) {
+        set_error("cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return RVCR_ERR_CUDA;
+    }
+    return peer_dispatch(assign_dev, n, row0, my_rank, G, bounds_dev, reinterpret_cast<unsigned char* const*>(inbox_bases_dev), cap,
+                         (cudaStream_t)stream);
+}
+
+int rvcr_peer_barrier(void* const* inbox_bases_dev, int32_t my_rank, int32_t G, int32_t epoch, int device, void* stream) {
+    if (!inbox_bases_dev || my_rank < 0 || my_rank >= G) return RVCR_ERR_INVALID;
+    DeviceGuard g(device);
+    if (!g.ok) {
+        set_error("cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return RVCR_ERR_CUDA;
+    }
+    return peer_barrier(reinterpret_cast<unsigned char* const*>(inbox_bases_dev), my_rank, G, epoch, (cudaStream_t)stream);
+}
+
+int rvcr_retrieve_blend_inbox_push(rvcr_index* h, void* inbox_dev, int64_t cap, float* rows_scratch_dev, double index_rate,
+                                   float* const* feat_bases_dev, void* stream) {
+    RVCR_ENTER(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!inbox_dev || cap <= 0 || !rows_scratch_dev || !feat_bases_dev) return RVCR_ERR_INVALID;
+    if (h->d % 4 != 0) {
+        set_error("d=%d unsupported (must be a multiple of 4)", h->d);
+        return RVCR_ERR_UNSUPPORTED;
+    }
+    unsigned char* ib = reinterpret_cast<unsigned char*>(inbox_dev);
+    int32_t* count = reinterpret_cast<int32_t*>(ib + RVCR_PEER_INBOX_COUNT_OFF);
+    int32_t* assign = reinterpret_cast<int32_t*>(ib + RVCR_PEER_INBOX_HEADER);
+    int32_t* src_rank = assign + cap;
+    int32_t* src_row = assign + 2 * cap;
+    RVCR_TRY(peer_inbox_seal(assign, count, cap, s));
+    RVCR_TRY(peer_pull_rows(feat_bases_dev, src_rank, src_row, cap, h->d, rows_scratch_dev, s, count));
+    count_launch(h, 2);
+    // the blend epilogues write row qi to feat_bases[src_rank[qi]] + src_row[qi] * d; sealed entries form no work
+    h->fuse.push.bases = feat_bases_dev;
+    h->fuse.push.rank = src_rank;
+    h->fuse.push.row = src_row;
+    const int rc = search_device(h, rows_scratch_dev, cap, assign, true, index_rate, nullptr, nullptr, s);
+    h->fuse.push = PushArgs{};
+    RVCR_TRY(rc);
+    RVCR_CUDA(cudaMemsetAsync(count, 0, 4, s));
+    return RVCR_OK;
+}
+
 int rvcr_peer_alloc(int device, int64_t bytes, void** ptr_out, unsigned char* handle64_out) {
     if (bytes <= 0 || !ptr_out || !handle64_out) return RVCR_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -807,6 +934,13 @@ int rvcr_peer_alloc(int device, int64_t bytes, void** ptr_out, unsigned char* ha
         set_error("peer buffer of %lld bytes: %s", (long long)bytes, cudaGetErrorString(e));
         cudaGetLastError();
         return RVCR_ERR_OOM;
+    }
+    e = cudaMemset(p, 0, (size_t)bytes);   // inboxes start empty; feature rows are overwritten anyway
+    if (e != cudaSuccess) {
+        set_error("clearing the peer buffer failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        cudaFree(p);
+        return RVCR_ERR_CUDA;
     }
     cudaIpcMemHandle_t hd;
     e = cudaIpcGetMemHandle(&hd, p);
@@ -883,6 +1017,8 @@ int rvcr_reconstruct_n(rvcr_index* h, int64_t i0, int64_t ni, float* out, int ou
     }
     if (ni == 0) return RVCR_OK;
     cudaStream_t s = nullptr;
+    StreamScope scope(h, s);          // ws_stage below is shared scratch (it is also the coarse re-check's fallback list)
+    RVCR_TRY(scope.enter());
     RVCR_TRY(finalize_pending(h, s));
     if (out_on_device) {
         RVCR_TRY(reconstruct(h, i0, ni, out, s));
@@ -1032,7 +1168,8 @@ int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t s
         set_error("index is not trained");
         return RVCR_ERR_STATE;
     }
-    RVCR_TRY(stream_enter(h, s));
+    StreamScope scope(h, s);
+    RVCR_TRY(scope.enter());
     float *topv, *topd, *qnorm, *qmargin;
     int* topj;
     int nsplit = 0;
@@ -1052,7 +1189,7 @@ int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t s
     if (dropped_host) RVCR_CUDA(cudaMemcpyAsync(dropped_host, topd, (size_t)n * (pairs / 8) * 4, cudaMemcpyDeviceToHost, s));
     RVCR_CUDA(cudaStreamSynchronize(s));
     if (cmax_out) *cmax_out = h->cent_norm_max;
-    return stream_leave(h, s);
+    return RVCR_OK;
 }
 
 }  // extern "C"

@@ -395,7 +395,9 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                     m = key[i];
                                     mi = i;
                                 }
-                            if (!(m >= thr)) break;
+                            // -inf keys are pad centroids (norm +inf) or consumed elements: never candidates, and with no finite
+                            // best yet (thr = -inf) they would pass the test for ever
+                            if (!(m >= thr) || m == __int_as_float(0xff800000)) break;
                             cand_insert(ck, cj, best, thr, dropped, margin, m, jb + mi);
 #pragma unroll
                             for (int i = 0; i < 32; ++i)

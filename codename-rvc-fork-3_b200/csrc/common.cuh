@@ -12,6 +12,9 @@
 #include "../../include/rvcr.h"
 
 #define RVCR_FLT_MAX 3.402823466e+38f
+#define PEER_INBOX_COUNT_OFF RVCR_PEER_INBOX_COUNT_OFF
+#define PEER_INBOX_FLAGS_OFF RVCR_PEER_INBOX_FLAGS_OFF
+#define PEER_INBOX_HEADER RVCR_PEER_INBOX_HEADER
 #define RVCR_K 8  // k of index.search(npy, k=8), rvc/infer/pipeline.py:499
 
 namespace rvcr {
@@ -84,8 +87,8 @@ struct Options {
     int64_t nan_on_zero_score = 1;
     int64_t profile = 0;      // record CUDA events around each phase's kernels
     int64_t scan_impl = 0;    // 0 auto (default): 5 for batches of >= scan_tc_min_queries, else 4; 5 tcgen05 tf32 + exact
-                              // re-check; exact FFMA scans: 1 scalar 8-lane, 2 packed f32x2
-                              // TQx4, 3 same with 16 warps, 4 packed TQx8 tile
+                              // re-check; 4 exact FFMA scan (packed f32x2, TQx8 tile; 1-3 select it too: the round-1
+                              // kernel generations they named were removed)
     int64_t tc_cluster = 2;   // tcgen05 path: 1 = one CTA per SM, 2 = CTA pairs (cta_group::2)
     int64_t fused_blend = 1;  // scan_impl 5: re-check kernel also does the gather + weights + blend
     // Size rules of the auto modes, set from measurements (profiles/r01_small_dispatch.json, B200).  The tensor-core scan has
@@ -248,7 +251,14 @@ int gather_blend(rvcr_index* h, float* feats, int64_t n, const float* D, const i
                  cudaStream_t s);
 // peer.cu : peer-memory (cudaIpc over NVLink) plumbing of the sharded path
 int peer_pull_rows(const float* const* bases, const int32_t* src_rank, const int32_t* src_row, int64_t m, int d, float* out,
-                   cudaStream_t s);
+                   cudaStream_t s, const int32_t* m_dev = nullptr);
+// inbox of the device-driven sharded step (layout: RVCR_PEER_INBOX_* in rvcr.h)
+int peer_dispatch(const int32_t* assign, int64_t n, int64_t row0, int my_rank, int G, const int32_t* bounds,
+                  unsigned char* const* inbox_bases, int64_t cap, cudaStream_t s);
+int peer_barrier(unsigned char* const* inbox_bases, int my_rank, int G, int epoch, cudaStream_t s);
+int peer_inbox_seal(int32_t* assign, const int32_t* count, int64_t cap, cudaStream_t s);
+// final_proj.cu : the v1 query producer, out = x W^T + b (pipeline.py:451-453)
+int final_proj(const float* x, int64_t n, int din, const float* w, const float* b, int dout, float* out, cudaStream_t s);
 // post.cu : standalone 2x upsample + protect mix (pipeline.py:463-481) for callers that skipped retrieval
 int upsample_protect(const float* feats, const float* feats0, const float* pitchf, int64_t n, int d, double protect, float* out,
                      cudaStream_t s);

@@ -195,8 +195,7 @@ int parse_index_impl(FileReader& r, const char* path, bool want_centroids, Parse
         char four[4];
         if (!r.rd(four, 4)) PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated inverted-list header", path);
         if (memcmp(four, "il00", 4) == 0) {
-            uint64_t a, b;
-            if (!r.get(a) || !r.get(b)) PARSE_FAIL(RVCR_ERR_FORMAT, "'%s': truncated inverted-list header", path);
+            // faiss write_InvertedLists(nullptr) emits the fourcc and nothing else ("inverted lists not stored with IVF object")
             p.list_encoding = 2;
         } else if (memcmp(four, "ilar", 4) == 0) {
             uint64_t il_nlist = 0, code_size = 0, cnt = 0;

@@ -190,7 +190,14 @@ int kmeans_train(rvcr_index* h, const float* x_host, int64_t n, cudaStream_t s) 
     }
     const size_t rowb = (size_t)d * sizeof(float);
     DevBuf xd, cent_new, assign, keys, vals, keys2, vals2, counts, seg, tmp, idx;
+    bool success = false;
     auto cleanup = [&]() {
+        // a failure part-way (an OOM in the coarse scratch, say) must not leave a "trained" index holding the initial or
+        // half-iterated centroids: callers that catch the error (extract_index.py:74-78 does) would add / write garbage
+        if (!success) {
+            h->trained = false;
+            coarse_tc_invalidate(h);
+        }
         xd.release(); cent_new.release(); assign.release(); keys.release(); vals.release(); keys2.release(); vals2.release();
         counts.release(); seg.release(); tmp.release(); idx.release();
     };
@@ -299,6 +306,7 @@ int kmeans_train(rvcr_index* h, const float* x_host, int64_t n, cudaStream_t s) 
         KM_CUDA(cudaStreamSynchronize(s));
         KM_TRY(coarse_tc_invalidate(h));   // the bf16 operand copy of the centroids is stale
     }
+    success = true;
     cleanup();
 #undef KM_TRY
 #undef KM_CUDA

@@ -266,6 +266,32 @@ class IndexIVFFlat:
         out = out.unsqueeze(0) if feats.dim() == 3 else out
         return (out, D, I) if want_neighbours else out
 
+    def final_proj_retrieve_blend(self, x, weight, bias, index_rate: float, want_neighbours: bool = False):
+        """The step before the path as the query producer (pipeline.py:451-453 + 497-507): for a v1 model,
+        `model.final_proj(feats[0])` -- out = x W^T + b, nn.Linear(768, 256) -- then retrieval + blend on the projected rows,
+        one call, nothing returns to the host in between.  x: (n, d_in) or (1, n, d_in) CUDA float32 encoder output;
+        weight (d, d_in) / bias (d,) = `model.final_proj.weight` / `.bias` on the same device.  Returns a NEW (n, d) /
+        (1, n, d) tensor holding the blended projected features."""
+        import torch
+        inf = self._info()
+        t = x[0] if x.dim() == 3 else x
+        if x.dim() == 3 and x.shape[0] != 1:
+            raise AssertionError("final_proj_retrieve_blend: batch dimension must be 1")
+        w, b = _check_linear(t, weight, bias, int(inf.d))
+        n = t.shape[0]
+        out = torch.empty((n, inf.d), dtype=torch.float32, device=t.device)
+        D = I = None
+        if want_neighbours:
+            D = torch.empty((n, 8), dtype=torch.float32, device=t.device)
+            I = torch.empty((n, 8), dtype=torch.int64, device=t.device)
+        check(lib().rvcr_final_proj_retrieve_blend(
+            self.handle, C.c_void_p(t.data_ptr()), n, int(t.shape[1]), C.c_void_p(w.data_ptr()),
+            C.c_void_p(b.data_ptr()) if b is not None else None, C.c_void_p(out.data_ptr()), float(index_rate),
+            C.c_void_p(D.data_ptr()) if D is not None else None, C.c_void_p(I.data_ptr()) if I is not None else None,
+            _stream_of(t)))
+        out = out.unsqueeze(0) if x.dim() == 3 else out
+        return (out, D, I) if want_neighbours else out
+
     def retrieve_blend_host_(self, feats: np.ndarray, index_rate: float) -> np.ndarray:
         """Same, on a host (n, d) float32 C-contiguous array, in place (H2D / D2H inside)."""
         inf = self._info()
@@ -447,6 +473,86 @@ def upsample_protect(feats, feats0=None, pitchf=None, protect: float = 0.5):
                                       C.c_void_p(pf.data_ptr()) if mix else None, n, d, float(protect),
                                       C.c_void_p(out.data_ptr()), int(t.device.index), _stream_of(t)))
     return out.unsqueeze(0) if feats.dim() == 3 else out
+
+
+def _check_linear(t, weight, bias, d_out):
+    import torch
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.is_contiguous()):
+        raise AssertionError("final_proj: need a contiguous float32 CUDA tensor (n, d_in) or (1, n, d_in)")
+    w = weight.detach()
+    if not (w.is_cuda and w.device == t.device and w.dtype == torch.float32 and w.is_contiguous()
+            and tuple(w.shape) == (d_out, t.shape[1])):
+        raise AssertionError(f"final_proj: weight must be a contiguous float32 ({d_out}, {t.shape[1]}) tensor on {t.device}")
+    b = None
+    if bias is not None:
+        b = bias.detach()
+        if not (b.is_cuda and b.device == t.device and b.dtype == torch.float32 and b.is_contiguous() and tuple(b.shape) == (d_out,)):
+            raise AssertionError(f"final_proj: bias must be a contiguous float32 ({d_out},) tensor on {t.device}")
+    return w, b
+
+
+def final_proj(x, weight, bias=None):
+    """`model.final_proj(feats[0])` (pipeline.py:451-453) alone: x (n, d_in) or (1, n, d_in) CUDA float32, weight
+    (d_out, d_in), bias (d_out,) -> new (n, d_out) / (1, n, d_out) tensor.  fp32 FFMA, ascending k (csrc/final_proj.cu)."""
+    import torch
+    t = x[0] if x.dim() == 3 else x
+    w, b = _check_linear(t, weight, bias, int(weight.shape[0]))
+    out = torch.empty((t.shape[0], w.shape[0]), dtype=torch.float32, device=t.device)
+    check(lib().rvcr_final_proj(C.c_void_p(t.data_ptr()), t.shape[0], int(t.shape[1]), C.c_void_p(w.data_ptr()),
+                                C.c_void_p(b.data_ptr()) if b is not None else None, int(w.shape[0]),
+                                C.c_void_p(out.data_ptr()), int(t.device.index), _stream_of(t)))
+    return out.unsqueeze(0) if x.dim() == 3 else out
+
+
+class MiniBatchKMeans:
+    """Drop-in for the one use the reference makes of sklearn.cluster.MiniBatchKMeans (rvc/train/process/extract_index.py:
+    43-56, the default "Auto" build path above 200 000 rows):
+
+        big_npy = MiniBatchKMeans(n_clusters=10000, verbose=True, batch_size=256 * cpu_count(), compute_labels=False,
+                                  init="random").fit(big_npy).cluster_centers_
+
+    Same algorithm (scikit-learn's mini-batch k-means: 3 random inits scored on a validation subset, per-centre learning
+    rates, random reassignment of starved centres, early stop on the smoothed inertia), with the nearest-centre step of
+    every mini-batch on the GPU coarse kernels (csrc/minibatch_kmeans.cu).  Like the reference's call it is unseeded unless
+    `random_state` is given; runs agree in distribution, not bit for bit.  Only what that call uses is implemented:
+    init="random", compute_labels=False, dense float32 rows."""
+
+    def __init__(self, n_clusters=8, *, init="random", max_iter=100, batch_size=1024, verbose=0, compute_labels=False,
+                 random_state=None, tol=0.0, max_no_improvement=10, init_size=None, n_init="auto", reassignment_ratio=0.01,
+                 device: int = 0):
+        if init != "random":
+            raise NotImplementedError('only init="random" (the reference call, extract_index.py:52) is implemented')
+        if compute_labels:
+            raise NotImplementedError("compute_labels=True is not implemented (the reference passes False)")
+        if tol != 0.0 or init_size is not None:
+            raise NotImplementedError("tol / init_size: only the estimator's defaults are implemented")
+        self.n_clusters, self.max_iter, self.batch_size, self.verbose = int(n_clusters), int(max_iter), int(batch_size), verbose
+        self.random_state, self.max_no_improvement = random_state, max_no_improvement
+        self.n_init = 3 if n_init == "auto" else int(n_init)
+        self.reassignment_ratio, self.device = float(reassignment_ratio), int(device)
+        self.cluster_centers_ = None
+
+    def fit(self, X, y=None, sample_weight=None):
+        from ._ffi import MbkStats
+        if sample_weight is not None:
+            raise NotImplementedError("sample_weight is not implemented")
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        if X.ndim != 2:
+            raise ValueError("Expected 2D array")
+        n, d = X.shape
+        seed = 0 if self.random_state is None else (int(self.random_state) % (2 ** 63)) + 1
+        out = np.empty((self.n_clusters, d), np.float32)
+        st = MbkStats()
+        check(lib().rvcr_minibatch_kmeans(X.ctypes.data_as(C.c_void_p), n, d, self.n_clusters, self.batch_size, self.max_iter,
+                                          0 if self.max_no_improvement is None else int(self.max_no_improvement),
+                                          self.reassignment_ratio, self.n_init, seed, self.device, 1 if self.verbose else 0,
+                                          out.ctypes.data_as(C.c_void_p), C.byref(st)))
+        self.cluster_centers_ = out
+        self.n_steps_ = int(st.n_steps)
+        self.n_iter_ = int(np.ceil(st.n_steps * st.batch_size / n))
+        self.n_features_in_ = d
+        self.stats_ = {k: getattr(st, k) for k, _ in MbkStats._fields_ if k != "reserved"}
+        return self
 
 
 def _stream_of(t):

@@ -15,13 +15,19 @@ from .faiss_compat import IndexIVFFlat
 
 
 def retrieve_speaker_embeddings(feats, index: IndexIVFFlat, big_npy=None, index_rate: float = 0.75,
-                                inplace: bool = True):
-    """feats: (1, n, d) float32 CUDA tensor (HuBERT / ContentVec last_hidden_state)."""
+                                inplace: bool = False):
+    """feats: (1, n, d) float32 CUDA tensor (HuBERT / ContentVec last_hidden_state).  Like the reference function it
+    returns a NEW tensor and leaves `feats` alone; inplace=True blends into `feats` itself (what `patch_pipeline` installs:
+    inside `voice_conversion` the un-blended features were cloned before the call, pipeline.py:455) and raises if that is
+    impossible (a non-contiguous view) instead of silently working on a copy."""
     if not isinstance(index, IndexIVFFlat):
         raise TypeError("index must come from codename-rvc-fork-3_b200.read_index / index_factory")
-    f = feats if inplace else feats.clone()
-    if not f.is_contiguous():
-        f = f.contiguous()
+    if inplace:
+        if not feats.is_contiguous():
+            raise ValueError("inplace=True needs a contiguous tensor")
+        f = feats
+    else:
+        f = feats.clone(memory_format=__import__("torch").contiguous_format)
     index.retrieve_blend_(f, index_rate)
     return f
 
@@ -35,10 +41,13 @@ def convert_features(feats, index, index_rate: float, pitchf=None, protect: floa
         feats = F.interpolate(..., scale_factor=2)   # :463-465
         feats0 = F.interpolate(...); pitchff = ...; feats = feats * pitchff + feats0 * (1 - pitchff)   # :468-481
 
-    `pitchf` is the (1, p_len) F0 track already cut to p_len = 2n (pipeline.py:466,474), or None without pitch
-    guidance.  With `index` None / falsy or index_rate <= 0 (pipeline.py:553) only the post step runs.
-    Returns a new (1, 2n, d) tensor."""
+    `pitchf` is the (1, p_len) F0 track cut to p_len (pipeline.py:466,474), or None without pitch guidance.  The protect
+    mix is applied only when protect < 0.5 (pipeline.py:475) and then needs p_len == 2n exactly, like the reference's
+    broadcast `feats * pitchff.unsqueeze(-1)` does; with protect >= 0.5 the track is not looked at (any length).  With
+    `index` None / falsy or index_rate <= 0 (pipeline.py:553) only the post step runs.  Returns a new (1, 2n, d) tensor."""
     from .faiss_compat import upsample_protect
+    if pitchf is not None and protect >= 0.5:
+        pitchf = None                      # pipeline.py:475: no mix, the F0 track plays no role in this step
     if index and index_rate > 0:
         if not isinstance(index, IndexIVFFlat):
             raise TypeError("index must come from codename-rvc-fork-3_b200.read_index / index_factory")
@@ -48,7 +57,9 @@ def convert_features(feats, index, index_rate: float, pitchf=None, protect: floa
 
 
 def _method(self, feats, index, big_npy, index_rate):
-    return retrieve_speaker_embeddings(feats, index, big_npy, index_rate)
+    # inside Pipeline.voice_conversion `feats0 = feats.clone()` was taken before this call (pipeline.py:455) and `feats` is
+    # rebound to the return value, so blending in place is safe there and saves a (1, n, d) copy
+    return retrieve_speaker_embeddings(feats, index, big_npy, index_rate, inplace=bool(getattr(feats, "is_contiguous", lambda: False)()))
 
 
 def patch_pipeline(pipeline_cls_or_module, faiss_module_name: str = "faiss", cache: bool = True,

@@ -21,12 +21,14 @@ One retrieve_blend step, queries sharded by "home" rank (each rank brings its ow
 (real candidates only for the lists it owns), the candidates are all-gathered (96 B / query / shard)
 and merged by (distance, id).
 
-With peer memory enabled (`ShardedIndex.enable_peer`: every rank's feature buffer is a cudaMalloc allocation mapped
-into all other ranks with cudaIpc over NVLink / NVSwitch) steps 2 and 4 need no collective: after a 4-byte-per-query
-all-gather of the list ids (which is also the barrier that says every rank finished step 1), the owner PULLS its
-rows out of their home ranks' buffers (one gather kernel over peer pointers) and the blend epilogue of step 3 PUSHES
-each blended row straight into its home rank's buffer -- compute and combine in one kernel, no send / recv staging,
-no scatter pass.  The NCCL all-to-all transport stays for tensors outside the peer buffer.
+With peer memory enabled (`ShardedIndex.enable_peer`: every rank's feature buffer and an INBOX are cudaMalloc
+allocations mapped into all other ranks with cudaIpc over NVLink / NVSwitch) steps 2 and 4 need no collective and no
+host synchronisation: the home rank's dispatch kernel files (list id, home rank, home row) into the owner's inbox
+(remote atomics reserve the slots, NVLink stores fill them), a flag barrier kernel says "everyone has dispatched", the
+owner PULLS its rows out of their home ranks' buffers and the blend epilogue of step 3 PUSHES each blended row
+straight into its home rank's buffer -- compute and combine in one kernel, no send / recv staging, no scatter pass --
+and a second flag barrier says "every row is home" (csrc/peer.cu).  The NCCL all-to-all transport stays for tensors
+outside the peer buffer and for callers that want the neighbour lists back.
 
 No floating-point reduction crosses ranks, so G-GPU results equal 1-GPU results bit for bit.
 """
@@ -84,6 +86,15 @@ class CudaShardBackend:
             C.c_void_p(peer.bases_dev.data_ptr()), C.c_void_p(dst_rank.data_ptr()), C.c_void_p(dst_row.data_ptr()),
             self._stream(rows)))
 
+    def scan_inbox_push(self, peer, index_rate):
+        """Steps 3 + 4 of the device-driven step: seal the inbox, pull the filed rows, scan + top-8 + gather + blend with
+        the epilogue writing every row to its home buffer; counts stay on the device."""
+        import torch
+        st = C.c_void_p(torch.cuda.current_stream(peer.rows_scratch.device).cuda_stream)
+        self._check(self._lib().rvcr_retrieve_blend_inbox_push(
+            self.index.handle, C.c_void_p(peer.inbox_ptrs[peer.rank]), peer.inbox_cap, C.c_void_p(peer.rows_scratch.data_ptr()),
+            float(index_rate), C.c_void_p(peer.bases_dev.data_ptr()), st))
+
     def merge_topk(self, D_all, I_all):
         import torch
         G, n, k = D_all.shape
@@ -103,7 +114,12 @@ class CudaPeer:
     rank's buffer through the peer mapping.  Construction is collective; it raises on every rank if any rank cannot
     map its peers (no NVLink / P2P between the GPUs, IPC disabled), so the caller can stay on the NCCL transport."""
 
-    def __init__(self, capacity_rows: int, d: int, device: int, group=None):
+    INBOX_HEADER = 1024          # RVCR_PEER_INBOX_HEADER (include/rvcr.h)
+
+    def __init__(self, capacity_rows: int, d: int, device: int, group=None, max_batch_rows: int | None = None):
+        """capacity_rows: rows of this rank's feature buffer.  max_batch_rows: the largest batch ANY rank passes to one
+        retrieve_blend_ step (default: capacity_rows); the inbox and the owner's row scratch hold world x that many
+        entries, so no step can overflow them whatever the query mass looks like."""
         import torch
         import torch.distributed as dist
         from ._ffi import check, lib
@@ -113,28 +129,38 @@ class CudaPeer:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.capacity_rows = int(capacity_rows)
         self.nbytes = self.capacity_rows * self.d * 4
+        self.max_batch_rows = int(max_batch_rows if max_batch_rows is not None else capacity_rows)
+        self.inbox_cap = self.world * self.max_batch_rows
+        self.inbox_bytes = self.INBOX_HEADER + 12 * self.inbox_cap
         self._own = C.c_void_p()
+        self._own_inbox = C.c_void_p()
         self._opened = []
-        handle = (C.c_ubyte * 64)()
+        handle, handle_in = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
         err = None
         try:
             check(lib().rvcr_peer_alloc(self.device, self.nbytes, C.byref(self._own), handle))
+            check(lib().rvcr_peer_alloc(self.device, self.inbox_bytes, C.byref(self._own_inbox), handle_in))
         except Exception as ex:                                    # keep the collective below in step on every rank
             err = ex
-        mine = (bytes(handle), self.nbytes, err is None)
+        mine = (bytes(handle), self.nbytes, err is None, bytes(handle_in), self.inbox_cap)
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
         self.ptrs = [0] * self.world
+        self.inbox_ptrs = [0] * self.world
+        if err is None and all(e[2] for e in everyone) and any(e[4] != self.inbox_cap for e in everyone):
+            err = RuntimeError("the ranks disagree on max_batch_rows")
         if err is None and all(e[2] for e in everyone):
-            for r, (hd, nb, _) in enumerate(everyone):
+            for r, (hd, nb, _, hd_in, _) in enumerate(everyone):
                 if r == self.rank:
                     self.ptrs[r] = self._own.value
+                    self.inbox_ptrs[r] = self._own_inbox.value
                     continue
-                p = C.c_void_p()
                 try:
-                    check(lib().rvcr_peer_open(self.device, (C.c_ubyte * 64).from_buffer_copy(hd), C.byref(p)))
-                    self._opened.append(p)
-                    self.ptrs[r] = p.value
+                    for hdl, dst in ((hd, self.ptrs), (hd_in, self.inbox_ptrs)):
+                        p = C.c_void_p()
+                        check(lib().rvcr_peer_open(self.device, (C.c_ubyte * 64).from_buffer_copy(hdl), C.byref(p)))
+                        self._opened.append(p)
+                        dst[r] = p.value
                 except Exception as ex:
                     err = ex
                     break
@@ -147,7 +173,32 @@ class CudaPeer:
             raise RuntimeError(f"peer memory unavailable: {err if err else 'another rank failed to map its peers'}")
         self.sizes = [e[1] for e in everyone]
         self.bases_dev = torch.tensor(self.ptrs, dtype=torch.int64, device=f"cuda:{self.device}")
+        self.inbox_bases_dev = torch.tensor(self.inbox_ptrs, dtype=torch.int64, device=f"cuda:{self.device}")
+        self.rows_scratch = torch.empty((self.inbox_cap, self.d), dtype=torch.float32, device=f"cuda:{self.device}")
         self._flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{self.device}")
+        self._epoch = 0
+        dist.barrier(group=group)                                 # every inbox is zeroed and mapped before the first step
+
+    def dispatch(self, assign, row0: int, bounds):
+        """File this rank's queries (list ids `assign`, rows row0.. of the own feature buffer) into their owners' inboxes."""
+        import torch
+        n = assign.shape[0]
+        if n > self.max_batch_rows:
+            raise ValueError(f"batch of {n} rows exceeds max_batch_rows={self.max_batch_rows} given to enable_peer")
+        if n == 0:
+            return
+        st = C.c_void_p(torch.cuda.current_stream(assign.device).cuda_stream)
+        self._check(self._lib().rvcr_peer_dispatch(C.c_void_p(assign.data_ptr()), n, int(row0), self.rank, self.world,
+                                                   C.c_void_p(bounds.data_ptr()) if self.world > 1 else None,
+                                                   C.c_void_p(self.inbox_bases_dev.data_ptr()), self.inbox_cap, self.device, st))
+
+    def barrier(self):
+        """Stream-ordered barrier over the ranks (a kernel that stores / spins on flags in peer memory; no host sync)."""
+        import torch
+        self._epoch += 1
+        st = C.c_void_p(torch.cuda.current_stream(torch.device(f"cuda:{self.device}")).cuda_stream)
+        self._check(self._lib().rvcr_peer_barrier(C.c_void_p(self.inbox_bases_dev.data_ptr()), self.rank, self.world,
+                                                  self._epoch, self.device, st))
 
     def rows(self, n: int, row0: int = 0):
         """(n, d) float32 tensor over rows [row0, row0 + n) of this rank's buffer (no copy)."""
@@ -197,6 +248,9 @@ class CudaPeer:
         if self._own.value:
             self._lib().rvcr_peer_free(self.device, self._own)
             self._own = C.c_void_p()
+        if getattr(self, "_own_inbox", None) is not None and self._own_inbox.value:
+            self._lib().rvcr_peer_free(self.device, self._own_inbox)
+            self._own_inbox = C.c_void_p()
 
 
 class ShardedIndex:
@@ -251,21 +305,46 @@ class ShardedIndex:
             assign, _ = self.be.assign(feats)                                            # 1
         else:
             assign = torch.empty(0, dtype=torch.int32, device=feats.device)
-        if self.peer is not None:
+        if self.peer is not None and hasattr(self.peer, "dispatch"):
+            # device-driven step.  The transport choice must be the same on every rank and nothing is exchanged to agree on
+            # it: neighbours wanted -> everyone takes the NCCL route (the flag is part of the call); rows outside the peer
+            # buffer are an error, not a silent fallback.
+            if want_neighbours:
+                return self._route_scan_combine(feats, assign, index_rate, True)
+            row0 = 0 if n == 0 else self.peer.row_offset(feats)
+            if row0 is None:
+                raise ValueError("peer transport: the rows must live in this rank's peer buffer (ShardedIndex.peer.rows(n, row0))")
+            return self._peer_inbox_step(feats, assign, row0, index_rate)
+        if self.peer is not None:                                  # host-driven variant (stand-in transports of the CPU tests)
             row0 = None if want_neighbours else (0 if n == 0 else self.peer.row_offset(feats))   # an empty batch fits anywhere
             return self._peer_scan_push(feats, assign, -1 if row0 is None else row0, index_rate, want_neighbours)
         return self._route_scan_combine(feats, assign, index_rate, want_neighbours)
 
-    def enable_peer(self, capacity_rows: int, d: int | None = None, transport=None):
-        """Collective.  Allocate a peer-mapped feature buffer of `capacity_rows` rows on every rank; tensors handed out
-        by `self.peer.rows(n, row0)` then take the pull / push path in `retrieve_blend_`.  Raises (on every rank) when
-        the GPUs cannot map each other's memory."""
-        self.peer = transport if transport is not None else CudaPeer(capacity_rows, d or self.be.d, self.be.device, self.group)
+    def _peer_inbox_step(self, feats, assign, row0, index_rate):
+        """Steps 2-4 with no host synchronisation and no collective (csrc/peer.cu): dispatch kernel -> flag barrier -> owner
+        seals its inbox, pulls, scans, blends and pushes -> flag barrier.  feats = rows [row0, row0 + n) of this rank's peer
+        buffer, blended in place by whichever ranks own the lists."""
+        p = self.peer
+        p.dispatch(assign, row0, self.bounds)                      # 2: (list, home rank, home row) -> the owner's inbox
+        p.barrier()                                                # everyone's coarse step and dispatch are done
+        self.be.scan_inbox_push(p, index_rate)                     # 3 + 4 fused
+        p.barrier()                                                # every blended row has landed in its home buffer
+        return feats
+
+    def enable_peer(self, capacity_rows: int, d: int | None = None, transport=None, max_batch_rows: int | None = None):
+        """Collective.  Allocate a peer-mapped feature buffer of `capacity_rows` rows (and an inbox for world x
+        `max_batch_rows` entries) on every rank; tensors handed out by `self.peer.rows(n, row0)` then take the pull / push
+        path in `retrieve_blend_`.  Raises (on every rank) when the GPUs cannot map each other's memory."""
+        self.peer = transport if transport is not None else CudaPeer(capacity_rows, d or self.be.d, self.be.device, self.group,
+                                                                     max_batch_rows=max_batch_rows)
         return self.peer
 
     def transport_name(self) -> str:
         if self.peer is None:
             return "nccl all-to-all (dispatch + combine)"
+        if hasattr(self.peer, "dispatch"):
+            return ("peer memory over NVLink (cudaIpc), device-driven: dispatch kernel files (list, home row) into the owner's inbox, "
+                    "flag barrier, owner pulls rows, blend epilogue pushes them home, flag barrier; no host sync, no collective")
         return "peer memory over NVLink (cudaIpc): owner pulls rows, blend epilogue pushes them home"
 
     def _peer_scan_push(self, feats, assign, row0, index_rate, want_neighbours=False):
@@ -338,7 +417,12 @@ class ShardedIndex:
             main.wait_event(ev)
             parts.append(self.be.assign(feats[a:b])[0])                                  # 1, chunk by chunk
         assign = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int32, device=dev)
-        if self.peer is not None:
+        if self.peer is not None and hasattr(self.peer, "dispatch"):
+            row0 = 0 if n == 0 else self.peer.row_offset(feats)
+            if row0 is None:
+                raise ValueError("peer transport: device_rows must be rows of this rank's peer buffer")
+            self._peer_inbox_step(feats, assign, row0, index_rate)
+        elif self.peer is not None:
             row0 = 0 if n == 0 else self.peer.row_offset(feats)
             self._peer_scan_push(feats, assign, -1 if row0 is None else row0, index_rate)
         else:

@@ -247,6 +247,42 @@ RVCR_API int rvcr_peer_pull_rows(const float* const* bases_dev, const int32_t* s
 RVCR_API int rvcr_retrieve_blend_assigned_push(rvcr_index* h, const float* rows_dev, int64_t m, const int32_t* assign_dev,
                                       double index_rate, float* const* dst_bases_dev, const int32_t* dst_rank_dev,
                                       const int32_t* dst_row_dev, void* stream);
+/* model.final_proj(feats[0])                                rvc/infer/pipeline.py:451-453 (v1 models)
+ * The step before the path as the query producer: out_dev (n x d_out) = x_dev (n x d_in) W^T + b with W (d_out x d_in,
+ * the nn.Linear weight as torch stores it) and b (d_out, nullable) on the device; fp32 FFMA, products accumulated in
+ * ascending k.  d_in % 16 == 0, d_out % 64 == 0 (768 -> 256 in RVC).  Floating point: equals the reference's cuBLAS
+ * sgemm within 1e-5 relative, not bit for bit (a GEMM library's summation order is unspecified).
+ * rvcr_final_proj_retrieve_blend chains it with rvcr_retrieve_blend on the same stream: the projected rows are written to
+ * feats_out_dev (n x d_out, d_out == the index's d) and blended there in place; D_dev / I_dev as in rvcr_retrieve_blend. */
+RVCR_API int rvcr_final_proj(const float* x_dev, int64_t n, int32_t d_in, const float* w_dev, const float* b_dev, int32_t d_out,
+                             float* out_dev, int device, void* stream);
+RVCR_API int rvcr_final_proj_retrieve_blend(rvcr_index* h, const float* x_dev, int64_t n, int32_t d_in, const float* w_dev,
+                                            const float* b_dev, float* feats_out_dev, double index_rate, float* D_dev,
+                                            int64_t* I_dev, void* stream);
+/* ---- the device-driven sharded step: inboxes in peer memory, no host synchronisation, no collective ----
+ * Each rank allocates (rvcr_peer_alloc, zero-filled) and peer-maps an INBOX of RVCR_PEER_INBOX_BYTES(cap) bytes:
+ *   +RVCR_PEER_INBOX_COUNT_OFF  int32   entries filed in the current step
+ *   +RVCR_PEER_INBOX_FLAGS_OFF  int32[] arrival flag of every rank (rvcr_peer_barrier)
+ *   +RVCR_PEER_INBOX_HEADER     int32[cap] list id | int32[cap] home rank | int32[cap] row in the home rank's feature buffer
+ * rvcr_peer_dispatch (home rank, after rvcr_assign): files query i -- list assign_dev[i], row row0 + i of this rank's
+ *   feature buffer -- into the inbox of the rank that owns the list (bounds_dev[r - 1] = first list of rank r); slots are
+ *   reserved with one remote atomicAdd per CTA and owner, entries are plain NVLink stores.
+ * rvcr_peer_barrier: stream-ordered barrier across the G ranks (flag stores with release, spin with acquire, system
+ *   scope); `epoch` must increase by one per call, identically on every rank.  After it, everything the other ranks
+ *   enqueued before their call of the same epoch is visible.  Every rank must call it.
+ * rvcr_retrieve_blend_inbox_push (owner): seals the unused tail of the own inbox, pulls the filed rows out of their home
+ *   buffers (feat_bases_dev, into rows_scratch_dev: cap x d floats), runs scan + top-8 + gather + blend whose epilogue
+ *   pushes every blended row to its home buffer, and clears the entry count for the next step.
+ * A step = assign, dispatch, barrier, inbox_push, barrier; cap must be >= the number of queries all ranks file per step. */
+#define RVCR_PEER_INBOX_COUNT_OFF 0
+#define RVCR_PEER_INBOX_FLAGS_OFF 256
+#define RVCR_PEER_INBOX_HEADER 1024
+#define RVCR_PEER_INBOX_BYTES(cap) (RVCR_PEER_INBOX_HEADER + 12 * (int64_t)(cap))
+RVCR_API int rvcr_peer_dispatch(const int32_t* assign_dev, int64_t n, int64_t row0, int32_t my_rank, int32_t G,
+                                const int32_t* bounds_dev, void* const* inbox_bases_dev, int64_t cap, int device, void* stream);
+RVCR_API int rvcr_peer_barrier(void* const* inbox_bases_dev, int32_t my_rank, int32_t G, int32_t epoch, int device, void* stream);
+RVCR_API int rvcr_retrieve_blend_inbox_push(rvcr_index* h, void* inbox_dev, int64_t cap, float* rows_scratch_dev,
+                                            double index_rate, float* const* feat_bases_dev, void* stream);
 /* Merge G shards' top-8 candidate lists (G x n x 8, after an all-gather) into the global
  * top-8 by (distance, id). */
 RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, int32_t G, int64_t n, int32_t k,
@@ -292,6 +328,24 @@ RVCR_API int rvcr_get_phase_ms(rvcr_index* h, float* ms_out);
 RVCR_API int rvcr_debug_coarse_tc(rvcr_index* h, const float* q_dev, int64_t n, int32_t split, int32_t cluster,
                                   int32_t cap_pairs, float* v_host, int32_t* j_host, int32_t* pairs_out,
                                   float* qnorm2_host, float* cmax_out, float* margin_host, float* dropped_host, void* stream);
+
+/* MiniBatchKMeans(n_clusters=10000, batch_size=256 * cpu_count(), init="random", compute_labels=False).fit(big_npy)
+ * .cluster_centers_                                         rvc/train/process/extract_index.py:43-56   
+ * scikit-learn's mini-batch k-means with the E-step on the coarse kernels: n_init random centre sets scored on a
+ * validation subset, steps of `batch_size` rows drawn with replacement, per-centre learning rates, random reassignment of
+ * starved centres, early stop on the smoothed inertia (csrc/minibatch_kmeans.cu).  x_host: n x d float32 host rows;
+ * centers_out_host: k x d.  The reference does not seed it: results are comparable in distribution only.  seed = 0 draws
+ * one from std::random_device.  Defaults of the estimator: max_iter 100, max_no_improvement 10, reassignment_ratio 0.01,
+ * n_init 3 (init="random"). */
+typedef struct rvcr_mbk_stats {
+    int64_t n_steps, max_steps, batch_size, init_size, n_reassigned, kernels_launched;
+    int32_t converged, rows_resident;
+    double ewa_inertia, init_inertia;
+    int64_t reserved[4];
+} rvcr_mbk_stats;
+RVCR_API int rvcr_minibatch_kmeans(const float* x_host, int64_t n, int32_t d, int64_t k, int64_t batch_size, int64_t max_iter,
+                                   int64_t max_no_improvement, double reassignment_ratio, int64_t n_init, uint64_t seed,
+                                   int device, int verbose, float* centers_out_host, rvcr_mbk_stats* stats_out);
 
 /* Host-only pieces of rvcr_index_train, exposed so that they can be checked without a GPU: faiss rand_perm
  * (identity, then swap(perm[i], perm[i + mt() % (n - i)]) with std::mt19937(seed)) and faiss split_clusters

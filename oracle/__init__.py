@@ -17,6 +17,8 @@ Functions mirror the reference call sites:
     retrieve           the whole of _retrieve_speaker_embeddings      pipeline.py:497-507
     build_lists        IndexIVFFlat::add_core                         extract_index.py:67-69
     kmeans_train       index.train -> faiss Clustering::train (A9)    extract_index.py:65   (PARITY UNPINNED)
+    final_proj         v1 query producer, nn.Linear(768, 256)         pipeline.py:451-453  (PINNED within 1e-5)
+    coarse_topn / scan_topk_multi   index.search with nprobe > 1      SURVEY A3 / 8f-4     (PARITY UNPINNED)
     upsample_protect   2x nearest upsample + pitch-protect mix        pipeline.py:463-481  (PINNED:
                        tests/golden/post_*.npz are outputs of the reference's own statements, make_golden_post.py)
 """
@@ -287,6 +289,16 @@ def upsample_protect(feats, feats0=None, pitchf=None, protect: float = 0.5):
     pf[pitchf < 1] = np.float32(protect)
     om = (np.float32(1) - pf).astype(np.float32)
     return (up * pf[:, None]).astype(np.float32) + (up0 * om[:, None]).astype(np.float32)
+
+
+def final_proj(x, weight, bias=None):
+    """`model.final_proj(feats[0])` for v1 models (pipeline.py:451-453): nn.Linear, out = x W^T + b in float32.  Floating
+    point: numpy's BLAS sums in its own order, like torch's -- comparisons use a 1e-5 relative tolerance (PINNED within that
+    on tests/golden/final_proj_v1.npz, produced by the reference statement itself)."""
+    out = _f32(x) @ _f32(weight).T
+    if bias is not None:
+        out = out + _f32(bias)[None, :]
+    return out.astype(np.float32)
 
 
 def build_lists(x, assign, nlist: int):

@@ -201,8 +201,7 @@ def read_index(path_or_bytes) -> IVFFlatData:
             (hn,) = _rd(f, "<Q")
             f.read(16 * hn)
         il = f.read(4)
-        if il == b"il00":
-            _rd(f, "<QQ")
+        if il == b"il00":                      # faiss write_InvertedLists(nullptr): the fourcc and nothing else
             sizes = np.zeros(nlist, np.int64)
         elif il == b"ilar":
             il_nlist, code_size = _rd(f, "<QQ")

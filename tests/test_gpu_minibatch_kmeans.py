@@ -1,0 +1,79 @@
+"""GPU: MiniBatchKMeans on the coarse kernels (rvc/train/process/extract_index.py:43-56 -- the reference's default
+"Auto" build path above 200 000 rows).  The reference call is unseeded, so parity is distributional: the centres must be as
+good as scikit-learn's on the same rows (inertia within a few per cent), finite, and the build downstream of them -- n_ivf
+from the centre count, train, add, write (extract_index.py:59-71) -- must be the bit-exact path."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def inertia(x, c):
+    cn = (c.astype(np.float64) ** 2).sum(1)
+    tot = 0.0
+    for s in range(0, len(x), 8192):
+        xb = x[s:s + 8192].astype(np.float64)
+        d = (xb ** 2).sum(1)[:, None] + cn[None, :] - 2.0 * xb @ c.astype(np.float64).T
+        tot += d.min(1).sum()
+    return tot
+
+
+def test_minibatch_kmeans_matches_sklearn_in_distribution(rvcr):
+    from sklearn.cluster import MiniBatchKMeans as SkMBK
+    synth = importlib.import_module("codename-rvc-fork-3_b200.synth")
+    rng = np.random.default_rng(7)
+    x, _, _ = synth.mixture_points(rng, 60_000, 256, 300)
+    k, batch = 500, 2048
+    ours = [rvcr.MiniBatchKMeans(n_clusters=k, batch_size=batch, init="random", compute_labels=False, random_state=s).fit(x)
+            for s in (1, 2, 3)]
+    sk = [SkMBK(n_clusters=k, batch_size=batch, init="random", compute_labels=False, random_state=s).fit(x) for s in (1, 2, 3)]
+    io = np.array([inertia(x, m.cluster_centers_) for m in ours])
+    isk = np.array([inertia(x, m.cluster_centers_) for m in sk])
+    print("inertia ours", io, "sklearn", isk, "steps ours", [m.n_steps_ for m in ours], "sklearn", [m.n_steps_ for m in sk])
+    for m in ours:
+        c = m.cluster_centers_
+        assert c.shape == (k, 256) and c.dtype == np.float32 and np.isfinite(c).all()
+        assert m.stats_["kernels_launched"] > 0 and m.n_steps_ >= 10
+    # as good as scikit-learn's, run to run spread included
+    assert io.mean() <= 1.05 * isk.mean() and io.max() <= 1.10 * isk.min()
+    # seeded runs repeat; unseeded runs (the reference's call) differ
+    again = rvcr.MiniBatchKMeans(n_clusters=k, batch_size=batch, random_state=1).fit(x)
+    assert np.array_equal(again.cluster_centers_, ours[0].cluster_centers_)
+    u1 = rvcr.MiniBatchKMeans(n_clusters=k, batch_size=batch).fit(x).cluster_centers_
+    u2 = rvcr.MiniBatchKMeans(n_clusters=k, batch_size=batch).fit(x).cluster_centers_
+    assert not np.array_equal(u1, u2)
+    with pytest.raises(rvcr.RvcrError):
+        rvcr.MiniBatchKMeans(n_clusters=1000).fit(x[:500])          # fewer rows than centres (scikit-learn raises too)
+    with pytest.raises(NotImplementedError):
+        rvcr.MiniBatchKMeans(n_clusters=8, init="k-means++")
+
+
+def test_auto_build_flow_downstream_of_the_centres_is_bit_exact(rvcr, oracle, tmp_path):
+    """extract_index.py:43-71 with index_algorithm = "Auto" at a reduced size: rows -> MiniBatchKMeans centres -> n_ivf ->
+    factory / nprobe / train / add / write, against the oracle run on the SAME centres."""
+    synth = importlib.import_module("codename-rvc-fork-3_b200.synth")
+    rng = np.random.default_rng(11)
+    big_npy, _, _ = synth.mixture_points(rng, 50_000, 768, 120)
+    big_npy = rvcr.MiniBatchKMeans(n_clusters=2000, verbose=False, batch_size=256 * 8, compute_labels=False,
+                                   init="random", random_state=5).fit(big_npy).cluster_centers_
+    n_ivf = min(int(16 * np.sqrt(big_npy.shape[0])), big_npy.shape[0] // 39)          # :59
+    assert n_ivf == 51
+    index = rvcr.index_factory(768, f"IVF{n_ivf},Flat")
+    rvcr.extract_index_ivf(index).nprobe = 1
+    index.train(big_npy)
+    for i in range(0, big_npy.shape[0], 8192):
+        index.add(big_npy[i:i + 8192])
+    path = str(tmp_path / "auto.index")
+    rvcr.write_index(index, path)
+    cent = oracle.kmeans_train(big_npy, n_ivf)
+    assert np.array_equal(index.get_centroids(), cent)
+    oidx = oracle.OracleIndex.from_vectors(big_npy, cent)
+    ref = str(tmp_path / "ref.index")
+    oracle.write_index(oidx.to_data(), ref)
+    assert open(path, "rb").read() == open(ref, "rb").read()
+    q = (big_npy[:300] + 0.02 * rng.standard_normal((300, 768))).astype(np.float32)
+    D, I = index.search(q, k=8)
+    Do, Io = oidx.search(q, k=8)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)

@@ -47,10 +47,16 @@ def test_golden_search_and_blend(rvcr, oracle, golden, tmp_path, name):
     # quantizer assignment + canonical coarse distance
     lst, dist = index.assign(torch.from_numpy(g["q"]).cuda())
     assert np.array_equal(lst.cpu().numpy(), g["assign"]) and np.array_equal(dist.cpu().numpy(), g["coarse_dist"])
-    # fused _retrieve_speaker_embeddings (pipeline.py:497-507), in place on the device
+    # fused _retrieve_speaker_embeddings (pipeline.py:497-507): like the reference, a new tensor by default ...
     feats = torch.from_numpy(g["q"].copy()).cuda().unsqueeze(0)
     out = rvcr.retrieve_speaker_embeddings(feats, index, None, float(g["index_rate"]))
+    assert out.data_ptr() != feats.data_ptr() and out.shape == feats.shape and np.array_equal(feats[0].cpu().numpy(), g["q"])
+    assert np.array_equal(out[0].cpu().numpy(), g["out"], equal_nan=True)
+    # ... in place on request (what patch_pipeline installs), refusing a view it could not blend in place
+    out = rvcr.retrieve_speaker_embeddings(feats, index, None, float(g["index_rate"]), inplace=True)
     assert out.data_ptr() == feats.data_ptr() and out.shape == feats.shape
+    with pytest.raises(ValueError):
+        rvcr.retrieve_speaker_embeddings(torch.zeros((1, 8, 2 * index.d), device="cuda")[:, :, ::2], index, None, 0.5, inplace=True)
     got = out[0].cpu().numpy()
     assert_blend_close(got, g["out"])
     assert np.array_equal(got, g["out"], equal_nan=True)          # in fact bit-exact

@@ -1,5 +1,7 @@
-"""GPU, 2 ranks on one box (NCCL over NVLink): the sharded path through the C ABI equals the single-GPU
-path bit for bit -- assignments, neighbour ids, distances and blended rows.  Skipped with < 2 GPUs."""
+"""GPU, min(8, device count) ranks on one box (NVLink peer memory + NCCL): the sharded path through the C ABI equals the
+single-GPU path bit for bit -- assignments, neighbour ids, distances and blended rows -- over both transports (the
+device-driven inbox step of csrc/peer.cu and the NCCL all-to-all route), with ragged and empty home batches and with a
+query mass that lands almost entirely on one shard.  Skipped with < 2 GPUs."""
 import os
 import socket
 import sys
@@ -80,17 +82,39 @@ def _worker(rank, world, port, tmp):
         hp = torch.from_numpy(q.copy()).pin_memory()
         sh.retrieve_blend_host_(hp, 0.75, chunk_rows=400, device_rows=peer.rows(len(q), 2000))
         assert np.array_equal(hp.numpy(), ref.cpu().numpy(), equal_nan=True)
-    # a tensor outside the peer buffer still works (every rank falls back to the all-to-all route together)
+    # a tensor outside the peer buffer is refused locally (no rank starts a collective, nothing to agree on) ...
     got = torch.from_numpy(q.copy()).cuda()
-    sh.retrieve_blend_(got, 0.75)
+    with pytest.raises(ValueError):
+        sh.retrieve_blend_(got, 0.75)
+    # ... and asking for the neighbour lists takes the NCCL route on every rank, peer buffer or not
+    _, Dn, In = sh.retrieve_blend_(got, 0.75, want_neighbours=True)
     assert np.array_equal(got.cpu().numpy(), ref.cpu().numpy(), equal_nan=True)
+    # skewed query mass: (almost) every query of every rank probes a list of shard 0 -- one inbox takes the whole step
+    own0 = shard.info["owned_end"] if rank == 0 else None
+    t = torch.tensor([own0 or 0], device="cuda")
+    dist.broadcast(t, src=0)
+    a_all = full.assign(torch.from_numpy(q_all).cuda())[0].cpu().numpy()
+    heavy = q_all[(a_all >= 0) & (a_all < int(t.item()))]
+    qs = heavy[rank::world][:1500]
+    qs = np.concatenate([qs, q[:5]]).astype(np.float32)          # plus a few queries for the other shards
+    ref = torch.from_numpy(qs.copy()).cuda()
+    full.retrieve_blend_(ref, 0.75)
+    fs = peer.rows(len(qs), 64)
+    fs.copy_(torch.from_numpy(qs))
+    for _ in range(3):                                           # back-to-back steps reuse the inbox (count reset, epochs)
+        fs.copy_(torch.from_numpy(qs))
+        sh.retrieve_blend_(fs, 0.75)
+    torch.cuda.synchronize()
+    assert np.array_equal(fs.cpu().numpy(), ref.cpu().numpy(), equal_nan=True)
     # an empty home batch on one rank, over both transports
     q2 = q[:0] if rank == world - 1 else q[:7]
     fp = peer.rows(len(q2), 100)
     fp.copy_(torch.from_numpy(q2))
     sh.retrieve_blend_(fp, 0.3)
     f2 = torch.from_numpy(q2.copy()).cuda()
+    sh.peer, keep = None, sh.peer                                # the NCCL all-to-all transport
     sh.retrieve_blend_(f2, 0.3)
+    sh.peer = keep
     torch.cuda.synchronize()
     assert np.array_equal(fp.cpu().numpy(), f2.cpu().numpy(), equal_nan=True)
     if len(q2):
@@ -103,11 +127,12 @@ def _worker(rank, world, port, tmp):
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
 
 
-def test_two_shards_equal_one_gpu(rvcr, oracle, tmp_path):
+def test_shards_equal_one_gpu(rvcr, oracle, tmp_path):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    world = min(8, torch.cuda.device_count())
     from importlib import import_module
     synth = import_module("codename-rvc-fork-3_b200.synth")
     pr = synth.make_host_problem(40_000, 768, 2000, 512, seed=9, dup_frac=0.005)
@@ -115,5 +140,5 @@ def test_two_shards_equal_one_gpu(rvcr, oracle, tmp_path):
     oidx = oracle.OracleIndex.from_vectors(pr.x, pr.centroids)
     oracle.write_index(oidx.to_data(), str(tmp_path / "full.index"))
     np.savez(tmp_path / "problem.npz", q=pr.q)
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
-    assert all((tmp_path / f"ok{r}").exists() for r in range(2))
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))

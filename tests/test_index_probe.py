@@ -114,10 +114,13 @@ def test_probe_other_writers_and_refusals(rvcr, oracle, tmp_path):
     assert i4["nprobe"] == 4 and i4["searchable"] == 1             # honoured by the multi-probe search path
     # trailing bytes after the payload are ignored, like faiss
     assert rvcr.probe_index(write(tmp_path, "trail.index", raw + b"xyz" * 11))["nvectors"] == n
-    # an empty-lists object ("il00")
-    f7 = bytearray(raw[:o["il"]]) + b"il00" + struct.pack("<QQ", data.nlist, 4 * data.d)
+    # an empty-lists object: faiss write_InvertedLists(nullptr) emits the 4-byte fourcc "il00" and NOTHING else, so a genuine
+    # file ends right there (round-1 parsers wanted 16 more bytes and refused it)
+    f7 = bytearray(raw[:o["il"]]) + b"il00"
     i7 = rvcr.probe_index(write(tmp_path, "il00.index", f7))
-    assert i7["list_encoding"] == 2 and i7["nvectors"] == 0
+    assert i7["list_encoding"] == 2 and i7["nvectors"] == 0 and i7["file_bytes"] == o["il"] + 4
+    d7 = oracle.read_index(bytes(f7))
+    assert d7.nlist == data.nlist and int(d7.list_sizes.sum()) == 0 and np.array_equal(d7.centroids, data.centroids)
     # refused: the legacy fourcc on a current-layout body, inner product, truncation, unknown fourccs
     f5 = bytearray(raw)
     f5[0:4] = b"IvFl"
