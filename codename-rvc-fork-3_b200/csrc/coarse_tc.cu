@@ -48,10 +48,14 @@ constexpr int EPI_WARP0 = 4;
 constexpr int NCG = 4;         // column groups of the epilogue: 4 lane quarters x NCG warps drain one accumulator tile
 constexpr int THREADS = (EPI_WARP0 + 4 * NCG) * 32;   // 640
 
-// Candidate list of one (query, split, column group): up to TOPT (key, centroid) pairs with key >= best - margin, unsorted.
-// A passing element takes a free slot (key -inf) or evicts the smallest key kept if it beats it; whatever passed the test
-// but is not kept (evicted or turned away) is remembered by its largest key in `dropped`, so the re-check can tell whether
-// the list may be missing a candidate (dropped >= final best - margin -> the exact kernel answers the query).
+// Candidate list of one (query, split, column group): up to TOPT (key, centroid) pairs, unsorted.  An element is looked at
+// only if its key reaches thr = max(best - margin, smallest key kept once the list is full): it must be within the margin
+// of the running best AND among the TOPT largest keys seen -- the first test alone lets everything through until the
+// query's own neighbourhood shows up when the margin is as wide as the spread of the far centroids (e4m3), the second
+// alone is round 1's sorted top-8.  A passing element takes a free slot (key -inf) or evicts the smallest key kept;
+// whatever was evicted is remembered by its largest key in `dropped`.  At the end of the item a full list whose smallest
+// key is itself inside the margin may have turned candidates away: it reports that key as dropped too, and the re-check
+// hands the query to the exact kernel.
 __device__ __forceinline__ void cand_insert(float (&ck)[TOPT], int (&cj)[TOPT], float& best, float& thr, float& dropped,
                                             float margin, float x, int j) {
     float vk = ck[0];
@@ -73,10 +77,9 @@ __device__ __forceinline__ void cand_insert(float (&ck)[TOPT], int (&cj)[TOPT], 
     } else {
         dropped = fmaxf(dropped, x);
     }
-    if (x > best) {
-        best = x;
-        thr = best - margin;
-    }
+    best = fmaxf(best, x);
+    const float kmin = fminf(fminf(fminf(ck[0], ck[1]), fminf(ck[2], ck[3])), fminf(fminf(ck[4], ck[5]), fminf(ck[6], ck[7])));
+    thr = fmaxf(best - margin, kmin);   // kmin = -inf while a slot is free
 }
 
 // tcgen05.wait::ld with the loaded registers as in/out operands: nothing that reads them can be scheduled above the wait
@@ -359,7 +362,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + cg * CGW;
                 const float4* sn4 = reinterpret_cast<const float4*>(sNorm + as * BLOCK_N + cg * CGW);
                 const int j0 = t * BLOCK_N + cg * CGW;
-                mbar_wait_warp(&tmem_full_bar[as], aphase, lane);
+                mbar_wait_warp_parked(&tmem_full_bar[as], aphase, lane);   // the long wait of this warp: parked, not polled
                 tc_fence_after();
                 mbar_wait_warp(&norm_full_bar[as], aphase, lane);
 #pragma unroll 1
@@ -387,10 +390,10 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         const int jb = j0 + c * 32;
 #pragma unroll 1
                         for (;;) {                 // largest first: the threshold rises before the rest is looked at
-                            float m = key[0];
+                            float m = __int_as_float(0xff800000);   // a NaN key (NaN centroid element) is never picked
                             int mi = 0;
 #pragma unroll
-                            for (int i = 1; i < 32; ++i)
+                            for (int i = 0; i < 32; ++i)
                                 if (key[i] > m) {
                                     m = key[i];
                                     mi = i;
@@ -416,6 +419,10 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             // write this (query, split, column group)'s candidates as v = -key (free slots: +inf, -1) and the largest v-wise
             // nearest thing it had to let go
+            {   // a full list whose smallest key is inside the margin may have turned candidates away (see cand_insert)
+                const float kmin = fminf(fminf(fminf(ck[0], ck[1]), fminf(ck[2], ck[3])), fminf(fminf(ck[4], ck[5]), fminf(ck[6], ck[7])));
+                if (kmin >= best - margin) dropped = fmaxf(dropped, kmin);
+            }
             const int64_t ol = (q * nsplit + sp) * NCG + cg;
             float4* ov = reinterpret_cast<float4*>(topv + ol * TOPT);
             int4* oj = reinterpret_cast<int4*>(topj + ol * TOPT);

@@ -83,6 +83,26 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
     }
 }
 
+// Waits that are expected to be LONG (an epilogue warp waiting for the next accumulator): try_wait with a suspend-time hint
+// parks the thread in hardware for up to `ns` instead of re-issuing the poll -- at the 1 kW power cap every spinning warp
+// costs tensor clock (round 2: 16 epilogue warps polling flat out took 7 % off the coarse kernel).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_warp_parked(uint64_t* bar, uint32_t parity, int lane) {
+    if (lane == 0)
+        for (uint32_t it = 0; !mbar_try_wait_hint(bar, parity, 20000u); ++it)
+            if (it > (1u << 22)) __trap();
+    __syncwarp();
+    mbar_wait(bar, parity);
+}
+
 // Warp-collective barrier wait: one lane polls (32x less shared-memory polling traffic), then every lane
 // performs its own (immediately successful) wait so that each thread has acquire semantics of its own.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
