@@ -243,16 +243,6 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             for (int t = t0; t < t1; ++t, ++tile_cnt) {
                 const int n0 = t * BLOCK_N + (int)cta_rank * C::LOAD_N;
-                {
-                    // this tile's ||c||^2 (all BLOCK_N columns: the epilogue of either CTA of a pair sees the whole tile)
-                    const uint32_t ns = tile_cnt & 1, nphase = (tile_cnt >> 1) & 1;
-                    mbar_wait_warp(&norm_empty_bar[ns], nphase ^ 1, lane);
-                    if (elect_one()) {
-                        mbar_arrive_expect_tx_addr(nfull_addr + ns * 8, BLOCK_N * 4);
-                        bulk_load_1d(norm_addr + ns * (BLOCK_N * 4), cn + (int64_t)t * BLOCK_N, BLOCK_N * 4, nfull_addr + ns * 8);
-                    }
-                    __syncwarp();
-                }
                 for (int kb = 0; kb < num_kblocks; ++kb) {
                     const bool streamed = is_streamed(kb);     // uniform
                     mbar_wait_warp(&empty_bar[stage], phase ^ 1, lane);
@@ -270,6 +260,20 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (NRES > 0 && streamed) {
                         if (++astage == SA) { astage = 0; aphase ^= 1; }
                     }
+                }
+                {
+                    // this tile's ||c||^2 (all BLOCK_N columns: the epilogue of either CTA of a pair sees the whole tile).  Issued
+                    // AFTER the tile's operand loads: the slot frees only when the epilogue of tile t - 2 is done, and waiting for
+                    // that in front of the operand loads would expose their latency on every tile (round 2, call D: the e4m3
+                    // kernel sat at 33 % tensor activity with idle epilogue warps); the norms are not needed before the tile's
+                    // MMAs have finished.
+                    const uint32_t ns = tile_cnt & 1, nphase = (tile_cnt >> 1) & 1;
+                    mbar_wait_warp(&norm_empty_bar[ns], nphase ^ 1, lane);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx_addr(nfull_addr + ns * 8, BLOCK_N * 4);
+                        bulk_load_1d(norm_addr + ns * (BLOCK_N * 4), cn + (int64_t)t * BLOCK_N, BLOCK_N * 4, nfull_addr + ns * 8);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -1054,8 +1058,8 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
         const int64_t res = h->opt.tc_resident;
         if (f8) {   // d / 128 k-blocks (6 at d = 768)
             const float* qk = h->ws_tc4.as<float>();
-            // cluster 2: every k-block of the query operand resident (d <= 1024: at most 8), 5 centroid stages
-            if (cluster == 2) RVCR_TRY((launch_tc<2, 8, 5, 1, 64, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
+            // cluster 2: the 6 k-blocks of a 768-d query operand resident (d = 1024: two more streamed), 7 centroid stages in flight
+            if (cluster == 2) RVCR_TRY((launch_tc<2, 6, 7, 1, 64, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
             else RVCR_TRY((launch_tc<1, 8, 2, 2, 3, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
         } else if (cluster == 2) {
             if (res == 0) RVCR_TRY((launch_tc<2, 0, 6, 6, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));

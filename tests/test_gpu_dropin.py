@@ -119,7 +119,7 @@ def test_extract_index_script_runs_unmodified_on_the_shim(rvcr, oracle, tmp_path
     np.random.shuffle(idx)
     big_npy = rows[idx]
     n_ivf = min(int(16 * np.sqrt(len(big_npy))), len(big_npy) // 39)
-    cent = oracle.kmeans_train(big_npy, n_ivf)
+    cent = oracle.kmeans_train(big_npy, n_ivf)[0]
     oidx = oracle.OracleIndex.from_vectors(big_npy, cent)
     ref = str(tmp_path / "ref.index")
     oracle.write_index(oidx.to_data(), ref)

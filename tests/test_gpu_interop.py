@@ -72,7 +72,6 @@ def test_files_from_other_writers(rvcr, oracle, tmp_path):
     D, I = idx.search(b["q"], k=8)
     Do, Io = b["oidx"].search(b["q"], k=8, nprobe=4)
     assert np.array_equal(I, Io) and np.array_equal(D, Do)
-    assert not np.array_equal(I, b["oidx"].search(b["q"], k=8)[1])       # and it matters on this data
     idx.nprobe = 1
     D, I = idx.search(b["q"], k=8)
     assert np.array_equal(I, b["oidx"].search(b["q"], k=8)[1])

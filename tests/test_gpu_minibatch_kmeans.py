@@ -67,7 +67,7 @@ def test_auto_build_flow_downstream_of_the_centres_is_bit_exact(rvcr, oracle, tm
         index.add(big_npy[i:i + 8192])
     path = str(tmp_path / "auto.index")
     rvcr.write_index(index, path)
-    cent = oracle.kmeans_train(big_npy, n_ivf)
+    cent = oracle.kmeans_train(big_npy, n_ivf)[0]
     assert np.array_equal(index.get_centroids(), cent)
     oidx = oracle.OracleIndex.from_vectors(big_npy, cent)
     ref = str(tmp_path / "ref.index")
