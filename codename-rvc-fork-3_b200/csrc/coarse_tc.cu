@@ -40,12 +40,16 @@ namespace rvcr {
 namespace tc {
 
 constexpr int BLOCK_M = 128;   // queries per CTA
-constexpr int BLOCK_N = 256;   // centroids per accumulator tile
+constexpr int BLOCK_N = 128;   // centroids per accumulator tile
+constexpr int ACC = 4;         // accumulator stages in TMEM (ACC x BLOCK_N = all 512 columns).  Round 1 had 2 x 256: with S
+                               // stages a tile takes max(M, (M + E) / S) (M = its MMAs, E = draining it), and once e4m3 operands
+                               // halved M the kernel sat at (M + E) / 2 with the tensor pipe 38 % busy; 4 x 128 columns give the
+                               // epilogue twice the slack for the same TMEM
 constexpr int BLOCK_K = 64;    // bf16 elements per stage row = 128 B = one swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int TOPT = 8;        // approximate nearest centroids kept per (query, split, column group)
 constexpr int EPI_WARP0 = 4;
-constexpr int NCG = 4;         // column groups of the epilogue: 4 lane quarters x NCG warps drain one accumulator tile
+constexpr int NCG = 4;         // column groups of the epilogue: 4 lane quarters x NCG warps drain one accumulator tile (32 columns each)
 constexpr int THREADS = (EPI_WARP0 + 4 * NCG) * 32;   // 640
 
 // Candidate list of one (query, split, column group): up to TOPT (key, centroid) pairs, unsorted.  An element is looked at
@@ -117,14 +121,14 @@ struct Cfg {
     static constexpr int B_BYTES = LOAD_N * BLOCK_K * 2;                  // 32 KB / 16 KB
     static constexpr int RES_BYTES = NRES * A_BYTES;
     static constexpr int RING_BYTES = SB * B_BYTES + SA * A_BYTES;
-    static constexpr int NORM_BYTES = 2 * BLOCK_N * 4;                    // ||c||^2 of the tile in each accumulator stage
+    static constexpr int NORM_BYTES = ACC * BLOCK_N * 4;                  // ||c||^2 of the tile in each accumulator stage
     static constexpr int BAR_BYTES = 512;
     // the dynamic shared memory of a kernel without static shared memory starts 1024-byte aligned (the kernel traps if not)
     static constexpr int SMEM_BYTES = RES_BYTES + RING_BYTES + NORM_BYTES + BAR_BYTES;
     static constexpr int UMMA_M = BLOCK_M * CLUSTER;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(NRES > 0 || SA == SB, "fully streamed: one A slot per B stage");
-    static_assert((2 * SB + SA + 11) * 8 + 8 <= BAR_BYTES, "barrier block");
+    static_assert((2 * SB + SA + 2 + 4 * ACC) * 8 + 8 <= BAR_BYTES, "barrier block");
 };
 
 // grid = persistent CTAs (multiple of CLUSTER); work item = (m-block of 128*CLUSTER queries, split
@@ -164,11 +168,11 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* aempty_bar = empty_bar + SB;          // [SA]  MMA -> TMA: streamed A slot free (each CTA its own)
     uint64_t* ares_full_bar = aempty_bar + SA;      // [1]   TMA -> MMA: resident A loaded (leader CTA's is used)
     uint64_t* ares_empty_bar = ares_full_bar + 1;   // [1]   MMA -> TMA: the item's MMAs are complete (each CTA its own)
-    uint64_t* tmem_full_bar = ares_empty_bar + 1;   // [2]   MMA -> epilogue  (each CTA its own)
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]   epilogue -> MMA  (leader CTA's are used)
-    uint64_t* norm_full_bar = tmem_empty_bar + 2;   // [2]   bulk copy -> epilogue (each CTA its own)
-    uint64_t* norm_empty_bar = norm_full_bar + 2;   // [2]   epilogue -> producer (each CTA its own)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(norm_empty_bar + 2);
+    uint64_t* tmem_full_bar = ares_empty_bar + 1;     // [ACC] MMA -> epilogue  (each CTA its own)
+    uint64_t* tmem_empty_bar = tmem_full_bar + ACC;   // [ACC] epilogue -> MMA  (leader CTA's are used)
+    uint64_t* norm_full_bar = tmem_empty_bar + ACC;   // [ACC] bulk copy -> epilogue (each CTA its own)
+    uint64_t* norm_empty_bar = norm_full_bar + ACC;   // [ACC] epilogue -> producer (each CTA its own)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(norm_empty_bar + ACC);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -194,7 +198,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int i = 0; i < SA; ++i) mbar_init(&aempty_bar[i], 1);
         mbar_init(ares_full_bar, CLUSTER);
         mbar_init(ares_empty_bar, 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < ACC; ++i) {
             mbar_init(&tmem_full_bar[i], 1);                  // one tcgen05.commit
             mbar_init(&tmem_empty_bar[i], CLUSTER * 4 * NCG); // every epilogue warp of the pair
             mbar_init(&norm_full_bar[i], 1);                  // the producer's arrive (+ tx bytes)
@@ -267,7 +271,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     // that in front of the operand loads would expose their latency on every tile (round 2, call D: the e4m3
                     // kernel sat at 33 % tensor activity with idle epilogue warps); the norms are not needed before the tile's
                     // MMAs have finished.
-                    const uint32_t ns = tile_cnt & 1, nphase = (tile_cnt >> 1) & 1;
+                    const uint32_t ns = tile_cnt % ACC, nphase = (tile_cnt / ACC) & 1;
                     mbar_wait_warp(&norm_empty_bar[ns], nphase ^ 1, lane);
                     if (elect_one()) {
                         mbar_arrive_expect_tx_addr(nfull_addr + ns * 8, BLOCK_N * 4);
@@ -297,7 +301,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     tc_fence_after();
                 }
                 for (int t = t0; t < t1; ++t, ++tile_cnt) {
-                    const uint32_t as = tile_cnt & 1, aphase = (tile_cnt >> 1) & 1;
+                    const uint32_t as = tile_cnt % ACC, aphase = (tile_cnt / ACC) & 1;
                     mbar_wait_warp(&tmem_empty_bar[as], aphase ^ 1, lane);   // epilogue drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tbase + as * BLOCK_N;
@@ -362,7 +366,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float nkr = 2.f;   // key = -v = nkr * acc - ||c||^2
             if constexpr (F8) nkr = -__ldg(qk + q);
             for (int t = t0; t < t1; ++t, ++tile_cnt) {
-                const uint32_t as = tile_cnt & 1, aphase = (tile_cnt >> 1) & 1;
+                const uint32_t as = tile_cnt % ACC, aphase = (tile_cnt / ACC) & 1;
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + cg * CGW;
                 const float4* sn4 = reinterpret_cast<const float4*>(sNorm + as * BLOCK_N + cg * CGW);
                 const int j0 = t * BLOCK_N + cg * CGW;
@@ -1058,18 +1062,17 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
         const int64_t res = h->opt.tc_resident;
         if (f8) {   // d / 128 k-blocks (6 at d = 768)
             const float* qk = h->ws_tc4.as<float>();
-            // cluster 2: the 6 k-blocks of a 768-d query operand resident (d = 1024: two more streamed), 7 centroid stages in flight
-            if (cluster == 2) RVCR_TRY((launch_tc<2, 6, 7, 1, 64, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
-            else RVCR_TRY((launch_tc<1, 8, 2, 2, 3, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
+            // cluster 2: the 6 k-blocks of a 768-d query operand resident (d = 1024: two more streamed), 14 x 8 KB centroid stages in flight
+            if (cluster == 2) RVCR_TRY((launch_tc<2, 6, 14, 1, 64, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
+            else RVCR_TRY((launch_tc<1, 8, 4, 2, 3, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
         } else if (cluster == 2) {
-            if (res == 0) RVCR_TRY((launch_tc<2, 0, 6, 6, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
-            else if (res == 6) RVCR_TRY((launch_tc<2, 6, 5, 3, 2>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
-            else if (res == 8) RVCR_TRY((launch_tc<2, 8, 4, 2, 3>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
-            else if (res == 9) RVCR_TRY((launch_tc<2, 9, 4, 1, 4>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
-            else RVCR_TRY((launch_tc<2, 10, 3, 1, 6>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            // tc_resident 0 streams both operands; every other value pins 9 of the 12 query k-blocks (the variants with 6 / 8 /
+            // 10 resident blocks measured within 2 % of it in round 1 and were removed)
+            if (res == 0) RVCR_TRY((launch_tc<2, 0, 9, 9, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            else RVCR_TRY((launch_tc<2, 9, 8, 1, 4>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
         } else {
-            if (res == 0) RVCR_TRY((launch_tc<1, 0, 4, 4, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
-            else RVCR_TRY((launch_tc<1, 8, 2, 2, 3>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            if (res == 0) RVCR_TRY((launch_tc<1, 0, 6, 6, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            else RVCR_TRY((launch_tc<1, 8, 4, 2, 3>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
         }
         count_launch(h);
     }
