@@ -40,16 +40,16 @@ namespace rvcr {
 namespace tc {
 
 constexpr int BLOCK_M = 128;   // queries per CTA
-constexpr int BLOCK_N = 128;   // centroids per accumulator tile
-constexpr int ACC = 4;         // accumulator stages in TMEM (ACC x BLOCK_N = all 512 columns).  Round 1 had 2 x 256: with S
-                               // stages a tile takes max(M, (M + E) / S) (M = its MMAs, E = draining it), and once e4m3 operands
-                               // halved M the kernel sat at (M + E) / 2 with the tensor pipe 38 % busy; 4 x 128 columns give the
-                               // epilogue twice the slack for the same TMEM
+constexpr int BLOCK_N = 256;   // centroids per accumulator tile
+constexpr int ACC = 2;         // accumulator stages in TMEM (ACC x BLOCK_N = all 512 columns).  With S stages a tile takes
+                               // max(M, (M + E) / S) (M = its MMAs, E = draining it).  4 x 128 columns were tried for the extra
+                               // slack (round 2, call F) and lost badly -- bf16 106 -> 160 ms, e4m3 83 -> 93 ms: at N = 128 every
+                               // MMA re-reads the A operand from shared memory for half the columns -- so E has to come down instead
 constexpr int BLOCK_K = 64;    // bf16 elements per stage row = 128 B = one swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int TOPT = 8;        // approximate nearest centroids kept per (query, split, column group)
 constexpr int EPI_WARP0 = 4;
-constexpr int NCG = 4;         // column groups of the epilogue: 4 lane quarters x NCG warps drain one accumulator tile (32 columns each)
+constexpr int NCG = 4;         // column groups of the epilogue: 4 lane quarters x NCG warps drain one accumulator tile (64 columns each)
 constexpr int THREADS = (EPI_WARP0 + 4 * NCG) * 32;   // 640
 
 // Candidate list of one (query, split, column group): up to TOPT (key, centroid) pairs, unsorted.  An element is looked at
@@ -60,8 +60,8 @@ constexpr int THREADS = (EPI_WARP0 + 4 * NCG) * 32;   // 640
 // whatever was evicted is remembered by its largest key in `dropped`.  At the end of the item a full list whose smallest
 // key is itself inside the margin may have turned candidates away: it reports that key as dropped too, and the re-check
 // hands the query to the exact kernel.
-__device__ __forceinline__ void cand_insert(float (&ck)[TOPT], int (&cj)[TOPT], float& best, float& thr, float& dropped,
-                                            float margin, float x, int j) {
+__device__ __forceinline__ float cand_insert(float (&ck)[TOPT], int (&cj)[TOPT], float& best, float& thr, float& dropped,
+                                             float margin, float x, int j) {
     float vk = ck[0];
     int vs = 0;
 #pragma unroll
@@ -84,6 +84,17 @@ __device__ __forceinline__ void cand_insert(float (&ck)[TOPT], int (&cj)[TOPT], 
     best = fmaxf(best, x);
     const float kmin = fminf(fminf(fminf(ck[0], ck[1]), fminf(ck[2], ck[3])), fminf(fminf(ck[4], ck[5]), fminf(ck[6], ck[7])));
     thr = fmaxf(best - margin, kmin);   // kmin = -inf while a slot is free
+    return kmin;
+}
+
+// Order-preserving map float -> uint32 (so atomicMax on the mapped value is a float max); 0 is below every float and
+// un-maps to a NaN, which fmaxf() ignores: "no floor yet".
+__device__ __forceinline__ uint32_t key_map(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_unmap(uint32_t m) {
+    return __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);
 }
 
 // tcgen05.wait::ld with the loaded registers as in/out operands: nothing that reads them can be scheduled above the wait
@@ -122,9 +133,10 @@ struct Cfg {
     static constexpr int RES_BYTES = NRES * A_BYTES;
     static constexpr int RING_BYTES = SB * B_BYTES + SA * A_BYTES;
     static constexpr int NORM_BYTES = ACC * BLOCK_N * 4;                  // ||c||^2 of the tile in each accumulator stage
+    static constexpr int FLOOR_BYTES = BLOCK_M * 4;                       // per-row floor shared by the NCG column-group warps
     static constexpr int BAR_BYTES = 512;
     // the dynamic shared memory of a kernel without static shared memory starts 1024-byte aligned (the kernel traps if not)
-    static constexpr int SMEM_BYTES = RES_BYTES + RING_BYTES + NORM_BYTES + BAR_BYTES;
+    static constexpr int SMEM_BYTES = RES_BYTES + RING_BYTES + NORM_BYTES + FLOOR_BYTES + BAR_BYTES;
     static constexpr int UMMA_M = BLOCK_M * CLUSTER;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(NRES > 0 || SA == SB, "fully streamed: one A slot per B stage");
@@ -162,7 +174,8 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* sB = smem + C::RES_BYTES;                   // SB stages
     uint8_t* sA = sB + SB * C::B_BYTES;                  // SA slots (streamed A k-blocks)
     float* sNorm = reinterpret_cast<float*>(smem + C::RES_BYTES + C::RING_BYTES);   // [2][BLOCK_N]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RES_BYTES + C::RING_BYTES + C::NORM_BYTES);
+    uint32_t* sFloor = reinterpret_cast<uint32_t*>(smem + C::RES_BYTES + C::RING_BYTES + C::NORM_BYTES);   // [BLOCK_M], order-mapped keys
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RES_BYTES + C::RING_BYTES + C::NORM_BYTES + C::FLOOR_BYTES);
     uint64_t* full_bar = bars;                      // [SB]  TMA -> MMA       (leader CTA's are used)
     uint64_t* empty_bar = full_bar + SB;            // [SB]  MMA -> TMA       (each CTA its own)
     uint64_t* aempty_bar = empty_bar + SB;          // [SA]  MMA -> TMA: streamed A slot free (each CTA its own)
@@ -365,6 +378,14 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float thr = margin == margin ? __int_as_float(0xff800000) : margin;   // -inf: the first columns all pass
             float nkr = 2.f;   // key = -v = nkr * acc - ||c||^2
             if constexpr (F8) nkr = -__ldg(qk + q);
+            // The NCG warps that share these 32 rows (one per column group) also share a per-row floor: the largest "8th key" any
+            // of their lists holds.  A key below it has 8 larger keys in that list, so it is not among the row's 8 best; testing
+            // against the shared floor cuts the insertions per row from NCG x 8 ln(n / 8 NCG) to about 8 ln(n / 8).  (A candidate
+            // turned away by it implies the list that set the floor is full of candidates, which that list reports itself.)
+            named_bar_sync(1 + ew, NCG * 32);              // everybody is done with the previous item's floors
+            if (cg == 0) sFloor[row] = 0u;
+            named_bar_sync(1 + ew, NCG * 32);
+            volatile uint32_t* myfloor = sFloor + row;
             for (int t = t0; t < t1; ++t, ++tile_cnt) {
                 const uint32_t as = tile_cnt % ACC, aphase = (tile_cnt / ACC) & 1;
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + cg * CGW;
@@ -394,8 +415,11 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int i = 0; i < 8; ++i) a8[i] = fmaxf(fmaxf(key[i], key[i + 8]), fmaxf(key[i + 16], key[i + 24]));
                         mx = fmaxf(fmaxf(fmaxf(a8[0], a8[1]), fmaxf(a8[2], a8[3])), fmaxf(fmaxf(a8[4], a8[5]), fmaxf(a8[6], a8[7])));
                     }
-                    if (mx >= thr) {               // one branch per 32 columns; a few dozen times per row and item
+                    const float gfl = key_unmap(*myfloor);
+                    float thr_e = fmaxf(thr, gfl);  // (a NaN -- no floor yet, or a NaN margin in thr -- is ignored by fmaxf)
+                    if (mx >= thr_e) {             // one branch per 32 columns; a few dozen times per row and item
                         const int jb = j0 + c * 32;
+                        float kmin = __int_as_float(0xff800000);
 #pragma unroll 1
                         for (;;) {                 // largest first: the threshold rises before the rest is looked at
                             float m = __int_as_float(0xff800000);   // a NaN key (NaN centroid element) is never picked
@@ -408,12 +432,14 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 }
                             // -inf keys are pad centroids (norm +inf) or consumed elements: never candidates, and with no finite
                             // best yet (thr = -inf) they would pass the test for ever
-                            if (!(m >= thr) || m == __int_as_float(0xff800000)) break;
-                            cand_insert(ck, cj, best, thr, dropped, margin, m, jb + mi);
+                            if (!(m >= thr_e) || m == __int_as_float(0xff800000)) break;
+                            kmin = cand_insert(ck, cj, best, thr, dropped, margin, m, jb + mi);
+                            thr_e = fmaxf(thr, gfl);
 #pragma unroll
                             for (int i = 0; i < 32; ++i)
                                 if (i == mi) key[i] = __int_as_float(0xff800000);
                         }
+                        if (!(kmin <= gfl)) atomicMax(sFloor + row, key_map(kmin));   // this list's 8th key raises the row's floor
                     }
                 }
                 // accumulator columns and norms of this warp fully read: hand the stage back (leader CTA's barrier / own barrier)
@@ -1062,17 +1088,17 @@ int coarse_tc_top8(rvcr_index* h, const float* q, int64_t n, int split, int clus
         const int64_t res = h->opt.tc_resident;
         if (f8) {   // d / 128 k-blocks (6 at d = 768)
             const float* qk = h->ws_tc4.as<float>();
-            // cluster 2: the 6 k-blocks of a 768-d query operand resident (d = 1024: two more streamed), 14 x 8 KB centroid stages in flight
-            if (cluster == 2) RVCR_TRY((launch_tc<2, 6, 14, 1, 64, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
-            else RVCR_TRY((launch_tc<1, 8, 4, 2, 3, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
+            // cluster 2: the 6 k-blocks of a 768-d query operand resident (d = 1024: two more streamed), 7 centroid stages in flight
+            if (cluster == 2) RVCR_TRY((launch_tc<2, 6, 7, 1, 64, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
+            else RVCR_TRY((launch_tc<1, 8, 2, 2, 3, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s, qk)));
         } else if (cluster == 2) {
             // tc_resident 0 streams both operands; every other value pins 9 of the 12 query k-blocks (the variants with 6 / 8 /
             // 10 resident blocks measured within 2 % of it in round 1 and were removed)
-            if (res == 0) RVCR_TRY((launch_tc<2, 0, 9, 9, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
-            else RVCR_TRY((launch_tc<2, 9, 8, 1, 4>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            if (res == 0) RVCR_TRY((launch_tc<2, 0, 6, 6, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            else RVCR_TRY((launch_tc<2, 9, 4, 1, 4>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
         } else {
-            if (res == 0) RVCR_TRY((launch_tc<1, 0, 6, 6, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
-            else RVCR_TRY((launch_tc<1, 8, 4, 2, 3>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            if (res == 0) RVCR_TRY((launch_tc<1, 0, 4, 4, 1>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
+            else RVCR_TRY((launch_tc<1, 8, 2, 2, 3>(h, ta, tb, num_mblocks, num_ntiles, nsplit, tps, nkb, tv, tj, s)));
         }
         count_launch(h);
     }
