@@ -391,7 +391,11 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + cg * CGW;
                 const float4* sn4 = reinterpret_cast<const float4*>(sNorm + as * BLOCK_N + cg * CGW);
                 const int j0 = t * BLOCK_N + cg * CGW;
-                mbar_wait_warp_parked(&tmem_full_bar[as], aphase, lane);   // the long wait of this warp: parked, not polled
+                // the long wait of this warp.  bf16 (power-bound): parked in hardware, not polled.  e4m3 (the epilogue is on the
+                // critical path and the chip has power to spare): polled -- a parked warp was seen to resume late (call G: tiles
+                // took (M + E) / 2 with E = 11 k cycles although the epilogue warps slept most of the time)
+                if constexpr (F8) mbar_wait_warp(&tmem_full_bar[as], aphase, lane);
+                else mbar_wait_warp_parked(&tmem_full_bar[as], aphase, lane);
                 tc_fence_after();
                 mbar_wait_warp(&norm_full_bar[as], aphase, lane);
 #pragma unroll 1
