@@ -98,10 +98,12 @@ struct Options {
     int64_t coarse_tc_min_flops = 64000000;     // coarse_mode 0: tcgen05 path from 64 MFLOP per call
     int64_t scan_tc_min_queries = 1024;         // scan_impl 0: tcgen05 scan from 1 Ki queries per call
     int64_t kmeans_niter = 10; // index.train: Lloyd iterations (faiss ClusteringParameters::niter of the Level1Quantizer)
-    int64_t coarse_f8_auto = 0; // coarse_mode 0 only: 1 = on the first call of >= 65 536 queries per centroid set, run the first
-                              // 8 192 of them with e4m3 operands (coarse_mode 4) and keep e4m3 for this centroid set if at most
-                              // 0.5 % of the probe fell back to the exact kernel, else stay on bf16.  Off until coarse_mode 4
-                              // has been validated on a B200.
+    int64_t coarse_f8_auto = 1; // coarse_mode 0 only: on the first call of >= 65 536 queries per centroid set, run the first 8 192 of
+                              // them with e4m3 operands (coarse_mode 4) and keep e4m3 for this centroid set if at most 0.5 % of the
+                              // probe fell back to the exact kernel, else stay on bf16 (and go back to bf16 if a later call sends
+                              // more than 2 % of its queries to the exact kernel).  Results are identical either way: both feed the
+                              // same exact re-check with a margin built from the exact residual norms of the operands.  On since
+                              // round 2 (validated on a B200: tests/test_gpu_coarse_f8.py; C5 coarse step 102 -> 74 ms).
     int64_t tc_resident = 9;  // coarse tcgen05 kernel: query-operand k-blocks pinned in shared memory per work item (0, 6, 8, 9, 10)
 };
 
