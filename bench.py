@@ -707,8 +707,29 @@ def main():
             t = torch.tensor([sec], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sec = float(t.item())
+        # what the host link gives this rank while every rank copies at once (plain pinned copies of the same size, H2D then
+        # D2H): the floor under the e2e step whatever the kernels do
+        link = None
+        try:
+            dbuf = slot(SLOT_SCRATCH)
+            barrier()
+            t0 = time.perf_counter()
+            dbuf.copy_(host, non_blocking=True)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            host.copy_(dbuf, non_blocking=True)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            tt = torch.tensor([t1 - t0, t2 - t1], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            gb = n_home * d * 4 / 1e9
+            link = {"h2d_ms": float(tt[0]) * 1e3, "d2h_ms": float(tt[1]) * 1e3, "h2d_gbs_per_rank": gb / float(tt[0]),
+                    "d2h_gbs_per_rank": gb / float(tt[1]), "note": "slowest rank, all ranks copying concurrently"}
+        except Exception:
+            pass
         e2e = {"value": nq / sec, "unit": UNIT, "h2d_bytes_per_step": int(nq) * d * 4, "d2h_bytes_per_step": int(nq) * d * 4,
-               "ms_per_step": sec * 1e3, "api": "IndexIVFFlat.retrieve_blend_host_ (rvcr_retrieve_blend_host), pinned host buffers"
+               "ms_per_step": sec * 1e3, "host_link": link, "api": "IndexIVFFlat.retrieve_blend_host_ (rvcr_retrieve_blend_host), pinned host buffers"
                if sh is None else "ShardedIndex.retrieve_blend_host_, pinned host buffers per rank"}
         del host, src
 
