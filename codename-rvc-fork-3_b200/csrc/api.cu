@@ -896,7 +896,7 @@ int rvcr_retrieve_blend_inbox_push(rvcr_index* h, void* inbox_dev, int64_t cap, 
                                    float* const* feat_bases_dev, void* stream) {
     RVCR_ENTER(h);
     cudaStream_t s = (cudaStream_t)stream;
-    if (!inbox_dev || cap <= 0 || !rows_scratch_dev || !feat_bases_dev) return RVCR_ERR_INVALID;
+    if (!inbox_dev || cap <= 0 || !feat_bases_dev) return RVCR_ERR_INVALID;
     if (h->d % 4 != 0) {
         set_error("d=%d unsupported (must be a multiple of 4)", h->d);
         return RVCR_ERR_UNSUPPORTED;
@@ -907,12 +907,16 @@ int rvcr_retrieve_blend_inbox_push(rvcr_index* h, void* inbox_dev, int64_t cap, 
     int32_t* src_rank = assign + cap;
     int32_t* src_row = assign + 2 * cap;
     RVCR_TRY(peer_inbox_seal(assign, count, cap, s));
-    RVCR_TRY(peer_pull_rows(feat_bases_dev, src_rank, src_row, cap, h->d, rows_scratch_dev, s, count));
-    count_launch(h, 2);
+    // rows_scratch_dev == NULL: the scan kernels read the query rows of their work items straight out of the home ranks'
+    // buffers (PushArgs::direct); else they are first pulled into the scratch (the round-2 first version, kept for A/B runs)
+    const bool direct = rows_scratch_dev == nullptr;
+    if (!direct) RVCR_TRY(peer_pull_rows(feat_bases_dev, src_rank, src_row, cap, h->d, rows_scratch_dev, s, count));
+    count_launch(h, direct ? 1 : 2);
     // the blend epilogues write row qi to feat_bases[src_rank[qi]] + src_row[qi] * d; sealed entries form no work
     h->fuse.push.bases = feat_bases_dev;
     h->fuse.push.rank = src_rank;
     h->fuse.push.row = src_row;
+    h->fuse.push.direct = direct ? 1 : 0;
     const int rc = search_device(h, rows_scratch_dev, cap, assign, true, index_rate, nullptr, nullptr, s);
     h->fuse.push = PushArgs{};
     RVCR_TRY(rc);

@@ -75,7 +75,7 @@ gather_blend_kernel(float* __restrict__ feats, int64_t n, int d, const float* __
             wk[k] = sw[k];
             rows[k] = spos[k] >= 0 ? reinterpret_cast<const float4*>(vecs + (int64_t)spos[k] * d) : nullptr;
         }
-        const float4* f4 = reinterpret_cast<const float4*>(feats + qi * d);
+        const float4* f4 = reinterpret_cast<const float4*>(query_row(feats, push, qi, d));
         float4* o4 = MODE == 2 ? push_row_ptr(push, qi, d) : reinterpret_cast<float4*>((out ? out : feats) + qi * d);
         for (int c = tid; c < nvec; c += blockDim.x) {
             float4 v[RVCR_K];

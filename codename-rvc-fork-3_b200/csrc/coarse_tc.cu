@@ -422,26 +422,27 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const float gfl = key_unmap(*myfloor);
                     float thr_e = fmaxf(thr, gfl);  // (a NaN -- no floor yet, or a NaN margin in thr -- is ignored by fmaxf)
                     if (mx >= thr_e) {             // one branch per 32 columns; a few dozen times per row and item
+                        // Which of the 32?  Per group of 4 columns one test on the group maximum, and inside a hit group a
+                        // rolled loop over its 4 keys (picked with selects: the group index is static), so the insertion code
+                        // exists 8 times, not 32, and a lane with one passing element runs ~140 instructions (the extraction
+                        // loop this replaces ran two 32-way arg-max searches and a 32-way consume per element: ~320).
                         const int jb = j0 + c * 32;
                         float kmin = __int_as_float(0xff800000);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const float k0 = key[4 * g], k1 = key[4 * g + 1], k2 = key[4 * g + 2], k3 = key[4 * g + 3];
+                            if (fmaxf(fmaxf(k0, k1), fmaxf(k2, k3)) >= thr_e) {
 #pragma unroll 1
-                        for (;;) {                 // largest first: the threshold rises before the rest is looked at
-                            float m = __int_as_float(0xff800000);   // a NaN key (NaN centroid element) is never picked
-                            int mi = 0;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (key[i] > m) {
-                                    m = key[i];
-                                    mi = i;
+                                for (int e = 0; e < 4; ++e) {
+                                    const float x = e == 0 ? k0 : e == 1 ? k1 : e == 2 ? k2 : k3;
+                                    // -inf keys are pad centroids (norm +inf): never candidates (and with no finite best yet,
+                                    // thr = -inf, they would pass); a NaN key fails the comparison
+                                    if (x >= thr_e && x != __int_as_float(0xff800000)) {
+                                        kmin = cand_insert(ck, cj, best, thr, dropped, margin, x, jb + 4 * g + e);
+                                        thr_e = fmaxf(thr, gfl);
+                                    }
                                 }
-                            // -inf keys are pad centroids (norm +inf) or consumed elements: never candidates, and with no finite
-                            // best yet (thr = -inf) they would pass the test for ever
-                            if (!(m >= thr_e) || m == __int_as_float(0xff800000)) break;
-                            kmin = cand_insert(ck, cj, best, thr, dropped, margin, m, jb + mi);
-                            thr_e = fmaxf(thr, gfl);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (i == mi) key[i] = __int_as_float(0xff800000);
+                            }
                         }
                         if (!(kmin <= gfl)) atomicMax(sFloor + row, key_map(kmin));   // this list's 8th key raises the row's floor
                     }

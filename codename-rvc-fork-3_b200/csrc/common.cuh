@@ -123,6 +123,8 @@ struct PushArgs {
     float* const* bases = nullptr;   // device array of G peer-mapped base pointers (own buffer included); nullptr = off
     const int32_t* rank = nullptr;   // per local row: home rank
     const int32_t* row = nullptr;    // per local row: row index inside the home rank's buffer
+    int direct = 0;                  // 1: the QUERY rows are read from there too (no pull pass: the scan kernels load the
+                                     // rows of their work item straight out of the home ranks' buffers over NVLink)
 };
 
 }  // namespace rvcr
@@ -346,6 +348,10 @@ __device__ __forceinline__ void post_store(const PostArgs& pa, int64_t qi, int d
     }
 }
 
+// where the query row of local index qi is read from: the local batch, or (PushArgs::direct) its home rank's buffer
+__device__ __forceinline__ const float* query_row(const float* q, const PushArgs& pa, int64_t qi, int d) {
+    return (pa.bases && pa.direct) ? pa.bases[pa.rank[qi]] + (int64_t)pa.row[qi] * d : q + qi * d;
+}
 // destination of the blended row of local query qi when the epilogue pushes to peer memory
 __device__ __forceinline__ float4* push_row_ptr(const PushArgs& pa, int64_t qi, int d) {
     return reinterpret_cast<float4*>(pa.bases[pa.rank[qi]] + (int64_t)pa.row[qi] * d);

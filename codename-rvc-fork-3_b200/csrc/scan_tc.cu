@@ -41,7 +41,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                int nstage, float ymax, float acc_rel, float abs_margin, int item_begin, int item_end,
                int32_t* __restrict__ cand, int32_t* __restrict__ candcnt, int32_t* __restrict__ fb_list,
                int32_t* __restrict__ fb_count, unsigned long long* __restrict__ totals /*[0] fallbacks, [1] candidates*/,
-               float2* __restrict__ stage_buf /*[grid][16][SCAP]*/, int dbg_flags) {
+               float2* __restrict__ stage_buf /*[grid][16][SCAP]*/, int dbg_flags, PushArgs push) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nkb = d / KB;
@@ -245,7 +245,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
         Item cur = S->items[0];
         mbar_arrive_warp(&S->iempty[0], lane);
         if (cur.idx < nitems) {
-            load_queries(sQ, q, qorder, cur, d, nkb, et);
+            load_queries(sQ, q, push, qorder, cur, d, nkb, et);
             cp_async_commit();
             cp_async_wait<0>();
             convert_queries(sQ, S->qnorm[0], nkb, et);
@@ -263,7 +263,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
             }
             const bool have_next = nxt.idx < nitems;
             // buffer (it+1)&1 was last read by item it-1, whose MMAs and selection are complete
-            if (have_next) load_queries(sQ + (size_t)((it + 1) & 1) * qbuf_bytes, q, qorder, nxt, d, nkb, et);
+            if (have_next) load_queries(sQ + (size_t)((it + 1) & 1) * qbuf_bytes, q, push, qorder, nxt, d, nkb, et);
             cp_async_commit();
             bool next_published = !have_next;
 
@@ -463,7 +463,7 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
         int tp = 0x7fffffff;
         if (nc > 0 || BLEND) {
             __syncwarp();
-            const float4* q4 = reinterpret_cast<const float4*>(q + qi * d);
+            const float4* q4 = reinterpret_cast<const float4*>(query_row(q, ba.push, qi, d));
             for (int c = lane; c < nvec; c += 32) reinterpret_cast<float4*>(sq)[c] = q4[c];
             __syncwarp();
         }
@@ -552,7 +552,10 @@ scan_exact_fallback_kernel(const float* __restrict__ q, const int32_t* __restric
             len = offsets[key + 1] - lb;
         }
         __syncthreads();
-        for (int c = tid; c < d; c += 256) sq[c] = q[qi * d + c];
+        {
+            const float* qr = query_row(q, ba.push, qi, d);
+            for (int c = tid; c < d; c += 256) sq[c] = qr[c];
+        }
         __syncthreads();
         float td = RVCR_FLT_MAX;
         int tp = 0x7fffffff;
@@ -736,7 +739,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
         h->ws_misc.as<int32_t>(), h->ws_misc.as<int32_t>() + ticket_slot, h->offsets, h->row_norm.as<float>(), (uint32_t)h->nlist, n, d,
         nstage, h->row_norm_max, rel, absm, item_begin, item_end, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
         h->ws_fb.as<int32_t>(), fb_count, reinterpret_cast<unsigned long long*>(h->ws_misc.as<int32_t>() + 48),
-        h->ws_cstage.as<float2>(), getenv("RVCR_STC_FLAGS") ? atoi(getenv("RVCR_STC_FLAGS")) : 0);
+        h->ws_cstage.as<float2>(), getenv("RVCR_STC_FLAGS") ? atoi(getenv("RVCR_STC_FLAGS")) : 0, h->fuse.push);
     RVCR_CHECK_LAUNCH();
     // fused tail (search_device sets h->fuse for rvcr_retrieve_blend*): the re-check / fallback kernels also blend
     const bool blend = h->fuse.active;

@@ -82,11 +82,11 @@ __device__ __forceinline__ void fetch_item(Item* out, int32_t* ticket, int item_
 // queries of an item -> K-major, 128B-swizzled operand tile [kb][16 rows][32 floats]; 8 threads per query, thread
 // (j, c) copies 16-byte chunk c of every k-block of query j (a 128 B contiguous read per 8 threads); rows >= cnt
 // replicate the last query (finite values; their accumulator columns are never read)
-__device__ __forceinline__ void load_queries(uint8_t* sQ, const float* __restrict__ q, const int32_t* __restrict__ qorder,
-                                             const Item& it, int d, int nkb, int et) {
+__device__ __forceinline__ void load_queries(uint8_t* sQ, const float* __restrict__ q, const PushArgs& push,
+                                             const int32_t* __restrict__ qorder, const Item& it, int d, int nkb, int et) {
     const int j = et >> 3, c16 = et & 7;
     const int jj = j < it.cnt ? j : it.cnt - 1;
-    const float* src = q + (int64_t)qorder[it.p0 + jj] * d + c16 * 4;
+    const float* src = query_row(q, push, qorder[it.p0 + jj], d) + c16 * 4;
     uint8_t* dst = sQ + (j >> 3) * 1024 + (j & 7) * 128 + ((c16 ^ (j & 7)) << 4);
     for (int kb = 0; kb < nkb; ++kb) cp_async16(dst + kb * QKB_BYTES, src + kb * KB);
 }

@@ -116,7 +116,7 @@ __device__ __forceinline__ void s4_load_stage(float* sdst, const float* __restri
 }
 
 template <int TQ>
-__device__ __forceinline__ void s4_run_item(const float* __restrict__ q, const int32_t* __restrict__ qorder, int64_t p0,
+__device__ __forceinline__ void s4_run_item(const float* __restrict__ q, const PushArgs& push, const int32_t* __restrict__ qorder, int64_t p0,
                                             int cnt, const float* __restrict__ lbase, int64_t lb, int64_t len, int d,
                                             float* sQ, float* sR, float* sD, float (&td)[2], int (&tp)[2]) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -131,7 +131,7 @@ __device__ __forceinline__ void s4_run_item(const float* __restrict__ q, const i
         const int nvec = d >> 2;
         for (int r = w; r < 4 * TQ; r += 8) {
             const int rr = r < cnt ? r : cnt - 1;
-            const float* src = q + (int64_t)qorder[p0 + rr] * d;
+            const float* src = query_row(q, push, qorder[p0 + rr], d);
             for (int c = lane; c < nvec; c += 32) cp_async16(sQ + r * QS + c * 4, src + c * 4);
         }
     }
@@ -262,7 +262,7 @@ scan_topk_kernel_v4(const float* __restrict__ q, const int32_t* __restrict__ qor
                     const int32_t* __restrict__ items, const int32_t* __restrict__ nitems_ptr, int32_t* __restrict__ ticket,
                     const float* __restrict__ vecs, const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets,
                     int64_t nstored, uint32_t nlist, int64_t n, int d, float* __restrict__ D, int32_t* __restrict__ P,
-                    int64_t* __restrict__ I, int item_begin, int item_end) {
+                    int64_t* __restrict__ I, int item_begin, int item_end, PushArgs push) {
     extern __shared__ __align__(16) float smem[];
     const int QS = d + 8;
     float* sQ = smem;                              // 16 x QS
@@ -288,10 +288,10 @@ scan_topk_kernel_v4(const float* __restrict__ q, const int32_t* __restrict__ qor
         int tp[2] = {0x7fffffff, 0x7fffffff};
         if (len > 0) {
             const float* lbase = vecs + lb * d;
-            if (cnt <= 4) s4_run_item<1>(q, qorder, p0, cnt, lbase, lb, len, d, sQ, sR, sD, td, tp);
-            else if (cnt <= 8) s4_run_item<2>(q, qorder, p0, cnt, lbase, lb, len, d, sQ, sR, sD, td, tp);
-            else if (cnt <= 12) s4_run_item<3>(q, qorder, p0, cnt, lbase, lb, len, d, sQ, sR, sD, td, tp);
-            else s4_run_item<4>(q, qorder, p0, cnt, lbase, lb, len, d, sQ, sR, sD, td, tp);
+            if (cnt <= 4) s4_run_item<1>(q, push, qorder, p0, cnt, lbase, lb, len, d, sQ, sR, sD, td, tp);
+            else if (cnt <= 8) s4_run_item<2>(q, push, qorder, p0, cnt, lbase, lb, len, d, sQ, sR, sD, td, tp);
+            else if (cnt <= 12) s4_run_item<3>(q, push, qorder, p0, cnt, lbase, lb, len, d, sQ, sR, sD, td, tp);
+            else s4_run_item<4>(q, push, qorder, p0, cnt, lbase, lb, len, d, sQ, sR, sD, td, tp);
         }
         if (lane < RVCR_K) {
 #pragma unroll
@@ -425,7 +425,7 @@ int scan_topk_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t*
     scan_topk_kernel_v4<<<grid, S4_THREADS, smem, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(),
                                                         h->ws_items.as<int32_t>(), h->ws_misc.as<int32_t>(),
                                                         h->ws_misc.as<int32_t>() + ticket_slot, h->vecs, h->ids, h->offsets,
-                                                        h->nstored, (uint32_t)h->nlist, n, h->d, D, P, I, item_begin, item_end);
+                                                        h->nstored, (uint32_t)h->nlist, n, h->d, D, P, I, item_begin, item_end, h->fuse.push);
     RVCR_CHECK_LAUNCH();
     count_launch(h, 2);
     return RVCR_OK;

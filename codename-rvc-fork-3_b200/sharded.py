@@ -90,9 +90,11 @@ class CudaShardBackend:
         """Steps 3 + 4 of the device-driven step: seal the inbox, pull the filed rows, scan + top-8 + gather + blend with
         the epilogue writing every row to its home buffer; counts stay on the device."""
         import torch
-        st = C.c_void_p(torch.cuda.current_stream(peer.rows_scratch.device).cuda_stream)
+        st = C.c_void_p(torch.cuda.current_stream(torch.device(f"cuda:{peer.device}")).cuda_stream)
+        scratch = peer.rows_scratch_tensor() if peer.pull_rows_first else None
         self._check(self._lib().rvcr_retrieve_blend_inbox_push(
-            self.index.handle, C.c_void_p(peer.inbox_ptrs[peer.rank]), peer.inbox_cap, C.c_void_p(peer.rows_scratch.data_ptr()),
+            self.index.handle, C.c_void_p(peer.inbox_ptrs[peer.rank]), peer.inbox_cap,
+            C.c_void_p(scratch.data_ptr()) if scratch is not None else None,
             float(index_rate), C.c_void_p(peer.bases_dev.data_ptr()), st))
 
     def merge_topk(self, D_all, I_all):
@@ -174,10 +176,17 @@ class CudaPeer:
         self.sizes = [e[1] for e in everyone]
         self.bases_dev = torch.tensor(self.ptrs, dtype=torch.int64, device=f"cuda:{self.device}")
         self.inbox_bases_dev = torch.tensor(self.inbox_ptrs, dtype=torch.int64, device=f"cuda:{self.device}")
-        self.rows_scratch = torch.empty((self.inbox_cap, self.d), dtype=torch.float32, device=f"cuda:{self.device}")
+        self.pull_rows_first = False      # True: the owner copies the filed rows into a local scratch before scanning (A/B knob)
+        self._rows_scratch = None
         self._flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{self.device}")
         self._epoch = 0
         dist.barrier(group=group)                                 # every inbox is zeroed and mapped before the first step
+
+    def rows_scratch_tensor(self):
+        import torch
+        if self._rows_scratch is None:
+            self._rows_scratch = torch.empty((self.inbox_cap, self.d), dtype=torch.float32, device=f"cuda:{self.device}")
+        return self._rows_scratch
 
     def dispatch(self, assign, row0: int, bounds):
         """File this rank's queries (list ids `assign`, rows row0.. of the own feature buffer) into their owners' inboxes."""
@@ -344,7 +353,8 @@ class ShardedIndex:
             return "nccl all-to-all (dispatch + combine)"
         if hasattr(self.peer, "dispatch"):
             return ("peer memory over NVLink (cudaIpc), device-driven: dispatch kernel files (list, home row) into the owner's inbox, "
-                    "flag barrier, owner pulls rows, blend epilogue pushes them home, flag barrier; no host sync, no collective")
+                    "flag barrier, owner's scan kernels read the rows over NVLink, blend epilogue pushes them home, flag barrier; "
+                    "no host sync, no collective")
         return "peer memory over NVLink (cudaIpc): owner pulls rows, blend epilogue pushes them home"
 
     def _peer_scan_push(self, feats, assign, row0, index_rate, want_neighbours=False):

@@ -270,9 +270,10 @@ RVCR_API int rvcr_final_proj_retrieve_blend(rvcr_index* h, const float* x_dev, i
  * rvcr_peer_barrier: stream-ordered barrier across the G ranks (flag stores with release, spin with acquire, system
  *   scope); `epoch` must increase by one per call, identically on every rank.  After it, everything the other ranks
  *   enqueued before their call of the same epoch is visible.  Every rank must call it.
- * rvcr_retrieve_blend_inbox_push (owner): seals the unused tail of the own inbox, pulls the filed rows out of their home
- *   buffers (feat_bases_dev, into rows_scratch_dev: cap x d floats), runs scan + top-8 + gather + blend whose epilogue
- *   pushes every blended row to its home buffer, and clears the entry count for the next step.
+ * rvcr_retrieve_blend_inbox_push (owner): seals the unused tail of the own inbox and runs scan + top-8 + gather + blend on
+ *   the filed queries: the scan kernels load each work item's query rows straight out of the home ranks' buffers
+ *   (feat_bases_dev, NVLink loads) and the blend epilogue pushes every blended row back to its home buffer; clears the
+ *   entry count for the next step.  rows_scratch_dev: NULL, or a cap x d buffer to PULL the rows into first (one extra pass).
  * A step = assign, dispatch, barrier, inbox_push, barrier; cap must be >= the number of queries all ranks file per step. */
 #define RVCR_PEER_INBOX_COUNT_OFF 0
 #define RVCR_PEER_INBOX_FLAGS_OFF 256

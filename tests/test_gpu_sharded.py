@@ -101,11 +101,13 @@ def _worker(rank, world, port, tmp):
     full.retrieve_blend_(ref, 0.75)
     fs = peer.rows(len(qs), 64)
     fs.copy_(torch.from_numpy(qs))
-    for _ in range(3):                                           # back-to-back steps reuse the inbox (count reset, epochs)
+    for it in range(4):                                          # back-to-back steps reuse the inbox (count reset, epochs)
+        peer.pull_rows_first = it == 3                           # last step: the variant that pulls the rows into a scratch first
         fs.copy_(torch.from_numpy(qs))
         sh.retrieve_blend_(fs, 0.75)
-    torch.cuda.synchronize()
-    assert np.array_equal(fs.cpu().numpy(), ref.cpu().numpy(), equal_nan=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(fs.cpu().numpy(), ref.cpu().numpy(), equal_nan=True), it
+    peer.pull_rows_first = False
     # an empty home batch on one rank, over both transports
     q2 = q[:0] if rank == world - 1 else q[:7]
     fp = peer.rows(len(q2), 100)
