@@ -755,14 +755,18 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
         // blend is serial inside a warp) and was removed.
         {
             const size_t rsm = (size_t)RC_WARPS * d * 4;
-            int per_sm = 10;   // = the register-limited occupancy (48 regs x 128 threads); measured r01 C5: 6 -> 16.5, 8 -> 14.6, 10 -> 12.5 ms
-            if (const char* e = getenv("RVCR_RC_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // tuning knob
+            // CTAs per SM x float4 loads in flight per lane, measured at C5 (ms for the kernel): r01 10 x 8: 12.5; r02 call I
+            // (RVCR_RC_CTAS x RVCR_RC_UNROLL): 2 x 16: 25.1, 3 x 16: 18.1, 4 x 16: 15.1, 4 x 8: 17.5, 6 x 16: 12.5, 10 x 8: 11.6,
+            // 8 x 16: 11.2 (twice) -> default.  Fewer resident warps do NOT buy L2 hits for the second read of the final 8 rows;
+            // the kernel wants bytes in flight.
+            int per_sm = 8, unr = 16;
+            if (const char* e = getenv("RVCR_RC_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // tuning knobs
+            if (const char* e = getenv("RVCR_RC_UNROLL")) unr = atoi(e) == 8 ? 8 : 16;
             int64_t rgrid = (int64_t)h->num_sms * per_sm;
             if (rgrid * RC_WARPS > n) rgrid = (n + RC_WARPS - 1) / RC_WARPS;
-            auto kern = bmode == 0 ? scan_recheck_kernel<0> : bmode == 1 ? scan_recheck_kernel<1> : bmode == 2 ? scan_recheck_kernel<2> : scan_recheck_kernel<3>;
-            if (const char* e = getenv("RVCR_RC_UNROLL"))   // tuning knob: fewer CTAs per SM (RVCR_RC_CTAS) with more loads in flight per lane
-                if (atoi(e) == 16)
-                    kern = bmode == 0 ? scan_recheck_kernel<0, 16> : bmode == 1 ? scan_recheck_kernel<1, 16> : bmode == 2 ? scan_recheck_kernel<2, 16> : scan_recheck_kernel<3, 16>;
+            auto kern = bmode == 0 ? scan_recheck_kernel<0, 16> : bmode == 1 ? scan_recheck_kernel<1, 16> : bmode == 2 ? scan_recheck_kernel<2, 16> : scan_recheck_kernel<3, 16>;
+            if (unr == 8)
+                kern = bmode == 0 ? scan_recheck_kernel<0> : bmode == 1 ? scan_recheck_kernel<1> : bmode == 2 ? scan_recheck_kernel<2> : scan_recheck_kernel<3>;
             kern<<<(unsigned)rgrid, RC_WARPS * 32, rsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), (uint32_t)h->nlist,
                                                              h->ws_items.as<int32_t>(), h->ws_misc.as<int32_t>(), item_begin, item_end, n,
                                                              d, h->vecs, h->ids, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),

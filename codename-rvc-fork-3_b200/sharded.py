@@ -35,6 +35,7 @@ No floating-point reduction crosses ranks, so G-GPU results equal 1-GPU results 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 FLT_MAX = 3.4028234663852886e38
 
@@ -176,7 +177,7 @@ class CudaPeer:
         self.sizes = [e[1] for e in everyone]
         self.bases_dev = torch.tensor(self.ptrs, dtype=torch.int64, device=f"cuda:{self.device}")
         self.inbox_bases_dev = torch.tensor(self.inbox_ptrs, dtype=torch.int64, device=f"cuda:{self.device}")
-        self.pull_rows_first = False      # True: the owner copies the filed rows into a local scratch before scanning (A/B knob)
+        self.pull_rows_first = os.environ.get("RVCR_PEER_PULL") == "1"   # True: the owner copies the filed rows into a local scratch before scanning (A/B knob)
         self._rows_scratch = None
         self._flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{self.device}")
         self._epoch = 0
