@@ -6,7 +6,7 @@
 # to gpurun_out/sanitize_<tool>.log; copy them to profiles/ with the findings explained.
 set -u
 mkdir -p gpurun_out
-for tool in memcheck racecheck synccheck initcheck; do
+for tool in ${SANITIZE_TOOLS:-memcheck racecheck synccheck initcheck}; do
   ( time timeout 420 compute-sanitizer --tool $tool --print-limit 40 --error-exitcode 99 \
       python tools/sanitize_case.py ) > gpurun_out/sanitize_$tool.log 2>&1
   echo "$tool rc=$?" >> gpurun_out/sanitize_$tool.log
