@@ -51,6 +51,14 @@ constexpr int TOPT = 8;        // approximate nearest centroids kept per (query,
 constexpr int EPI_WARP0 = 4;
 constexpr int NCG = 4;         // column groups of the epilogue: 4 lane quarters x NCG warps drain one accumulator tile (64 columns each)
 constexpr int THREADS = (EPI_WARP0 + 4 * NCG) * 32;   // 640
+#ifndef RVCR_EPI_SUBC
+#define RVCR_EPI_SUBC 16
+#endif
+#ifndef RVCR_EPI_QCAP
+#define RVCR_EPI_QCAP 4
+#endif
+constexpr int EPI_SUBC = RVCR_EPI_SUBC;   // accumulator columns per tcgen05.ld of an epilogue warp (16 or 32)
+constexpr int EPI_QCAP = RVCR_EPI_QCAP;   // passing keys an epilogue lane can remember per tile before it has to work them off
 
 // Candidate list of one (query, split, column group): up to TOPT (key, centroid) pairs, unsorted.  An element is looked at
 // only if its key reaches thr = max(best - margin, smallest key kept once the list is full): it must be within the margin
@@ -97,6 +105,31 @@ __device__ __forceinline__ float key_unmap(uint32_t m) {
     return __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);
 }
 
+// Work off a lane's queue of remembered keys (see the epilogue): each one that still reaches the threshold goes through
+// cand_insert.  Returns the list's smallest key after the last insertion (kmin_in if there was none).
+template <int QCAP>
+__device__ __forceinline__ float cand_flush(float (&qx)[QCAP], int (&qj)[QCAP], int& qn, float (&ck)[TOPT], int (&cj)[TOPT],
+                                            float& best, float& thr, float& dropped, float margin, float gfl, float& thr_e,
+                                            float kmin) {
+#pragma unroll 1
+    for (int i = 0; i < qn; ++i) {
+        float x = qx[0];
+        int j = qj[0];
+#pragma unroll
+        for (int u = 1; u < QCAP; ++u)
+            if (i == u) {
+                x = qx[u];
+                j = qj[u];
+            }
+        if (x >= thr_e) {
+            kmin = cand_insert(ck, cj, best, thr, dropped, margin, x, j);
+            thr_e = fmaxf(thr, gfl);
+        }
+    }
+    qn = 0;
+    return kmin;
+}
+
 // tcgen05.wait::ld with the loaded registers as in/out operands: nothing that reads them can be scheduled above the wait
 __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -107,6 +140,17 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
                  :
                  : "memory");
 }
+
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 
 // 1-D bulk copy global -> this CTA's shared memory, completing (bytes) on a local mbarrier
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst_addr, const void* src, uint32_t bytes, uint32_t bar_addr) {
@@ -356,7 +400,9 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp >= EPI_WARP0) {
         // ================================ epilogue =====================================
         constexpr int CGW = BLOCK_N / NCG;             // columns per column group
-        constexpr int NCH = CGW / 32;                  // 32-column chunks per warp and tile
+        constexpr int SUBC = EPI_SUBC;                 // columns per tcgen05.ld
+        constexpr int NCH = CGW / SUBC;                // loads per warp and tile
+        constexpr int QCAP = EPI_QCAP;
         const int ew = (warp - EPI_WARP0) & 3;         // == warp % 4: TMEM lane quarter of this warp
         const int cg = (warp - EPI_WARP0) >> 2;        // column group
         const int row = ew * 32 + lane;                // accumulator row == TMEM lane
@@ -398,15 +444,36 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 else mbar_wait_warp_parked(&tmem_full_bar[as], aphase, lane);
                 tc_fence_after();
                 mbar_wait_warp(&norm_full_bar[as], aphase, lane);
+                // Phase A -- the accumulator stage is held.  Read this warp's columns SUBC at a time; keys that reach the threshold are
+                // only REMEMBERED (register queue of QCAP (key, centroid) pairs, a few instructions each; a full queue is worked off
+                // on the spot).  The stage goes back to the MMA warp as soon as the last columns sit in registers, i.e. before any
+                // list maintenance: with two accumulator stages a tile takes max(M, (M + hold) / 2), and the hold time used to contain
+                // the slowest of the pair's 32 epilogue warps' insertions (e4m3, calls H / I: tiles took 6260 cycles against M = 3072
+                // with the epilogue warps ~40 % busy and the MMA warp waiting for tmem_empty).
+                float qx[QCAP];
+                int qj[QCAP];
+                int qn = 0;
+                const float gfl = key_unmap(*myfloor);
+                float thr_e = fmaxf(thr, gfl);   // (a NaN -- no floor yet, or a NaN margin in thr -- is ignored by fmaxf)
+                float kmin = __int_as_float(0xff800000);
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c * 32, r);
+                    uint32_t r[SUBC];
+                    tmem_ld_cols(taddr + c * SUBC, r);
                     tmem_ld_wait_regs(r);
-                    float key[32];
+                    if (c == NCH - 1) {
+                        // every accumulator column of this warp has been read: hand the stage back (leader CTA's barrier)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CLUSTER == 1 || leader) mbar_arrive_local(&tmem_empty_bar[as]);
+                            else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                        }
+                    }
+                    float key[SUBC];
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const float4 nn = sn4[c * 8 + g];   // same address in every lane: one broadcast LDS.128
+                    for (int g = 0; g < SUBC / 4; ++g) {
+                        const float4 nn = sn4[c * (SUBC / 4) + g];   // same address in every lane: one broadcast LDS.128
                         key[4 * g + 0] = fmaf(nkr, __uint_as_float(r[4 * g + 0]), -nn.x);
                         key[4 * g + 1] = fmaf(nkr, __uint_as_float(r[4 * g + 1]), -nn.y);
                         key[4 * g + 2] = fmaf(nkr, __uint_as_float(r[4 * g + 2]), -nn.z);
@@ -416,20 +483,19 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     {
                         float a8[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) a8[i] = fmaxf(fmaxf(key[i], key[i + 8]), fmaxf(key[i + 16], key[i + 24]));
+                        for (int i = 0; i < 8; ++i) {
+                            a8[i] = fmaxf(key[i], key[i + 8]);
+                            if constexpr (SUBC == 32) a8[i] = fmaxf(a8[i], fmaxf(key[(i + 16) % SUBC], key[(i + 24) % SUBC]));
+                        }
                         mx = fmaxf(fmaxf(fmaxf(a8[0], a8[1]), fmaxf(a8[2], a8[3])), fmaxf(fmaxf(a8[4], a8[5]), fmaxf(a8[6], a8[7])));
                     }
-                    const float gfl = key_unmap(*myfloor);
-                    float thr_e = fmaxf(thr, gfl);  // (a NaN -- no floor yet, or a NaN margin in thr -- is ignored by fmaxf)
-                    if (mx >= thr_e) {             // one branch per 32 columns; a few dozen times per row and item
-                        // Which of the 32?  Per group of 4 columns one test on the group maximum, and inside a hit group a
-                        // rolled loop over its 4 keys (picked with selects: the group index is static), so the insertion code
-                        // exists 8 times, not 32, and a lane with one passing element runs ~140 instructions (the extraction
-                        // loop this replaces ran two 32-way arg-max searches and a 32-way consume per element: ~320).
-                        const int jb = j0 + c * 32;
-                        float kmin = __int_as_float(0xff800000);
+                    if (mx >= thr_e) {             // one branch per SUBC columns; a few dozen times per row and item
+                        // Which ones?  Per group of 4 columns one test on the group maximum, and inside a hit group a rolled loop
+                        // over its 4 keys (picked with selects: the group index is static), so the queueing code exists SUBC / 4
+                        // times, not SUBC.
+                        const int jb = j0 + c * SUBC;
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) {
+                        for (int g = 0; g < SUBC / 4; ++g) {
                             const float k0 = key[4 * g], k1 = key[4 * g + 1], k2 = key[4 * g + 2], k3 = key[4 * g + 3];
                             if (fmaxf(fmaxf(k0, k1), fmaxf(k2, k3)) >= thr_e) {
 #pragma unroll 1
@@ -438,23 +504,28 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                     // -inf keys are pad centroids (norm +inf): never candidates (and with no finite best yet,
                                     // thr = -inf, they would pass); a NaN key fails the comparison
                                     if (x >= thr_e && x != __int_as_float(0xff800000)) {
-                                        kmin = cand_insert(ck, cj, best, thr, dropped, margin, x, jb + 4 * g + e);
-                                        thr_e = fmaxf(thr, gfl);
+                                        if (qn == QCAP)
+                                            kmin = cand_flush(qx, qj, qn, ck, cj, best, thr, dropped, margin, gfl, thr_e, kmin);
+#pragma unroll
+                                        for (int u = 0; u < QCAP; ++u)
+                                            if (qn == u) {
+                                                qx[u] = x;
+                                                qj[u] = jb + 4 * g + e;
+                                            }
+                                        ++qn;
                                     }
                                 }
                             }
                         }
-                        if (!(kmin <= gfl)) atomicMax(sFloor + row, key_map(kmin));   // this list's 8th key raises the row's floor
                     }
                 }
-                // accumulator columns and norms of this warp fully read: hand the stage back (leader CTA's barrier / own barrier)
-                tc_fence_before();
+                // Phase B -- the MMA warp already owns the stage again: list maintenance for what was queued
+                kmin = cand_flush(qx, qj, qn, ck, cj, best, thr, dropped, margin, gfl, thr_e, kmin);
+                if (kmin != __int_as_float(0xff800000) && !(kmin <= gfl))
+                    atomicMax(sFloor + row, key_map(kmin));   // this list's 8th key raises the row's floor
+                // the tile's norms are no longer needed either
                 __syncwarp();
-                if (lane == 0) {
-                    if (CLUSTER == 1 || leader) mbar_arrive_local(&tmem_empty_bar[as]);
-                    else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
-                    mbar_arrive_local(&norm_empty_bar[as]);
-                }
+                if (lane == 0) mbar_arrive_local(&norm_empty_bar[as]);
             }
             // write this (query, split, column group)'s candidates as v = -key (free slots: +inf, -1) and the largest v-wise
             // nearest thing it had to let go
