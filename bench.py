@@ -482,6 +482,7 @@ def main():
     ap.add_argument("--tc-resident", type=int, default=-1, help="coarse kernel: resident query k-blocks (0/8/9/10; -1 = library default)")
     ap.add_argument("--tc-cluster", type=int, default=-1, help="coarse kernel: 2 = CTA pairs (default), 1 = one CTA per SM")
     ap.add_argument("--fused-blend", type=int, default=-1, help="1 = re-check kernel also blends (default), 0 = separate gather_blend kernel")
+    ap.add_argument("--queries", type=int, default=0, help="tuning runs only: override the workload's query-frame count (e.g. the per-rank share of an N-GPU run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: use the NCCL all-to-all transport instead of peer memory")
@@ -494,6 +495,8 @@ def main():
 
     synth = importlib.import_module(PKG + ".synth")
     cfg = synth.CONFIGS[args.workload]
+    if args.queries > 0:
+        cfg = (cfg[0], cfg[1], args.queries, cfg[3])     # reported in config.query_frames
     if args.workload == "C4":
         import bench_build
         return bench_build.main(args, cfg)

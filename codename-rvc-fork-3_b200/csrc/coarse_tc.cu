@@ -51,14 +51,11 @@ constexpr int TOPT = 8;        // approximate nearest centroids kept per (query,
 constexpr int EPI_WARP0 = 4;
 constexpr int NCG = 4;         // column groups of the epilogue: 4 lane quarters x NCG warps drain one accumulator tile (64 columns each)
 constexpr int THREADS = (EPI_WARP0 + 4 * NCG) * 32;   // 640
-#ifndef RVCR_EPI_SUBC
-#define RVCR_EPI_SUBC 16
-#endif
-#ifndef RVCR_EPI_QCAP
-#define RVCR_EPI_QCAP 4
-#endif
-constexpr int EPI_SUBC = RVCR_EPI_SUBC;   // accumulator columns per tcgen05.ld of an epilogue warp (16 or 32)
-constexpr int EPI_QCAP = RVCR_EPI_QCAP;   // passing keys an epilogue lane can remember per tile before it has to work them off
+// Epilogue granularity, measured at C5 (round 2, call J; coarse_main ms, previous kernel on the same box: e4m3 64.6, bf16 102.3):
+//   columns per tcgen05.ld x queue slots     16 x 4         32 x 2         16 x 2
+//   e4m3 (epilogue on the critical path)     61.6           65.1           63.6
+//   bf16 (tensor pipe / power bound)         103.3          102.2          103.7
+template <int F8> struct EpiCfg { static constexpr int SUBC = F8 ? 16 : 32, QCAP = F8 ? 4 : 2; };
 
 // Candidate list of one (query, split, column group): up to TOPT (key, centroid) pairs, unsorted.  An element is looked at
 // only if its key reaches thr = max(best - margin, smallest key kept once the list is full): it must be within the margin
@@ -400,9 +397,9 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp >= EPI_WARP0) {
         // ================================ epilogue =====================================
         constexpr int CGW = BLOCK_N / NCG;             // columns per column group
-        constexpr int SUBC = EPI_SUBC;                 // columns per tcgen05.ld
+        constexpr int SUBC = EpiCfg<F8>::SUBC;         // columns per tcgen05.ld
         constexpr int NCH = CGW / SUBC;                // loads per warp and tile
-        constexpr int QCAP = EPI_QCAP;
+        constexpr int QCAP = EpiCfg<F8>::QCAP;         // passing keys a lane can remember per tile before it has to work them off
         const int ew = (warp - EPI_WARP0) & 3;         // == warp % 4: TMEM lane quarter of this warp
         const int cg = (warp - EPI_WARP0) >> 2;        // column group
         const int row = ew * 32 + lane;                // accumulator row == TMEM lane

@@ -712,6 +712,10 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     const size_t fixed = 2 * (size_t)nkb * stc::QKB_BYTES + stc::SV_BYTES + sizeof(stc::Smem) + 1024;
     int nstage = (int)((226 * 1024 - fixed) / stc::STAGE_BYTES);
     if (nstage > 8) nstage = 8;
+    if (const char* e = getenv("RVCR_STC_NSTAGE")) {   // tuning knob: fewer stages = fewer bytes in flight per SM
+        const int v = atoi(e);
+        if (v >= 2 && v < nstage) nstage = v;
+    }
     if (nstage < 2) {
         set_error("d=%d leaves no room for the row ring in shared memory", d);
         return RVCR_ERR_UNSUPPORTED;

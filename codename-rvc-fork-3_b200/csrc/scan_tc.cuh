@@ -30,7 +30,10 @@ constexpr int CONV_WARP0 = 8;
 constexpr int CONV_THREADS = 128;
 constexpr int CCAP = 64;                    // candidates handed to the re-check per query
 constexpr int SCAP = 256;                   // (v, position) pairs staged per query while a multi-chunk list streams
-constexpr int CHUNK_TILES = 4;              // the epilogue selects candidates per chunk of 4 tiles = 512 list rows
+#ifndef RVCR_STC_CHUNK_TILES
+#define RVCR_STC_CHUNK_TILES 4
+#endif
+constexpr int CHUNK_TILES = RVCR_STC_CHUNK_TILES;   // the epilogue selects candidates per chunk of 4 tiles = 512 list rows
 constexpr int CHUNK_ROWS = CHUNK_TILES * TILE_M;
 constexpr int SV_BYTES = QT * CHUNK_ROWS * 4;   // v of one chunk: [16 queries][512 rows] fp32 = 32 KB
 
