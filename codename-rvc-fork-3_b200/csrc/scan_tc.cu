@@ -46,9 +46,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nkb = d / KB;
     uint8_t* sR = smem;                                         // nstage x 16 KB
-    uint8_t* sQ = sR + (size_t)nstage * STAGE_BYTES;            // 2 x nkb x 2 KB
+    uint8_t* sQ = sR + (size_t)nstage * STAGE_BYTES;            // NQB x nkb x 2 KB
     const int qbuf_bytes = nkb * QKB_BYTES;
-    float* sV = reinterpret_cast<float*>(sQ + 2 * (size_t)qbuf_bytes);    // [16][CHUNK_ROWS]
+    float* sV = reinterpret_cast<float*>(sQ + NQB * (size_t)qbuf_bytes);  // [16][CHUNK_ROWS]
     Smem* S = reinterpret_cast<Smem*>(reinterpret_cast<uint8_t*>(sV) + SV_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,6 +79,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
         }
         tc::mbar_init(&S->qfull[0], EPI_THREADS / 32);
         tc::mbar_init(&S->qfull[1], EPI_THREADS / 32);
+        tc::mbar_init(&S->qempty, 1);
         tc::fence_mbar_init();
     } else if (warp == 2) {
         tc::tmem_alloc<1>(&S->tmem_ptr, TMEM_COLS);
@@ -151,8 +152,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
             mbar_arrive_warp(&S->iempty[slot], lane);
             if (!tc::warp_uniform(cur.idx < nitems ? 1 : 0)) break;
             const int ntiles = tc::warp_uniform((int)((cur.len + TILE_M - 1) / TILE_M));
-            mbar_wait_warp(&S->qfull[it & 1], (it >> 1) & 1, lane);        // this item's queries are in sQ[it & 1]
-            const uint32_t qaddr = sQ_addr + (it & 1) * (uint32_t)qbuf_bytes;
+            // this item's queries are in sQ[it % NQB] (one barrier per buffer)
+            mbar_wait_warp(&S->qfull[it % NQB], (it / NQB) & 1, lane);
+            const uint32_t qaddr = sQ_addr + (it % NQB) * (uint32_t)qbuf_bytes;
             for (int t = 0; t < ntiles; ++t, ++tile_cnt) {
                 const uint32_t as = tile_cnt % NACC, ause = tile_cnt / NACC;
                 mbar_wait_warp(&S->tempty[as], (ause & 1) ^ 1, lane);      // epilogue drained this accumulator
@@ -175,6 +177,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                     __syncwarp();
                     if (++ts == NTS) { ts = 0; tphase ^= 1; }
                 }
+            }
+            if constexpr (NQB == 1) {   // fires when every MMA of this item has retired (at once for an empty list)
+                if (tc::elect_one()) tc::umma_commit_addr(bar_addr + (uint32_t)offsetof(Smem, qempty));
+                __syncwarp();
             }
         }
     } else if (warp >= CONV_WARP0) {
@@ -262,9 +268,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                 mbar_arrive_warp(&S->iempty[slot], lane);
             }
             const bool have_next = nxt.idx < nitems;
-            // buffer (it+1)&1 was last read by item it-1, whose MMAs and selection are complete
-            if (have_next) load_queries(sQ + (size_t)((it + 1) & 1) * qbuf_bytes, q, push, qorder, nxt, d, nkb, et);
-            cp_async_commit();
+            uint8_t* sQn = sQ + (size_t)((it + 1) % NQB) * qbuf_bytes;
+            // NQB == 2: buffer (it+1)&1 was last read by item it-1, whose MMAs and selection are complete -- load at once.
+            // NQB == 1: the one buffer is this item's; the load waits for qempty after the last chunk's accumulators (below)
+            bool next_issued = NQB == 2;
+            if (NQB == 2 && have_next) load_queries(sQn, q, push, qorder, nxt, d, nkb, et);
+            if (NQB == 2) cp_async_commit();
             bool next_published = !have_next;
 
             const int cnt = cur.cnt;
@@ -303,19 +312,26 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                     for (int j = 0; j < QT; ++j)
                         if (j < cnt)   // warp-uniform
                             dst[j * CHUNK_ROWS] = valid ? fmaf(-2.f, __uint_as_float(r[j]), yn) : __int_as_float(0x7f800000);
-                    if (!next_published) {
+                    if (next_issued && !next_published) {
                         cp_async_wait<0>();
-                        convert_queries(sQ + (size_t)((it + 1) & 1) * qbuf_bytes, S->qnorm[(it + 1) & 1], nkb, et);
+                        convert_queries(sQn, S->qnorm[(it + 1) & 1], nkb, et);
                         tc::fence_proxy_async_smem();
-                        mbar_arrive_warp(&S->qfull[(it + 1) & 1], lane);
+                        mbar_arrive_warp(&S->qfull[(it + 1) % NQB], lane);
                         next_published = true;
                     }
                 }
-                if (!next_published) {
+                if (NQB == 1 && !next_issued && t1 >= ntiles) {
+                    // last chunk: every accumulator of the item has been read, so its MMAs are long complete
+                    mbar_wait_warp(&S->qempty, it & 1, lane);
+                    if (have_next) load_queries(sQn, q, push, qorder, nxt, d, nkb, et);
+                    cp_async_commit();
+                    next_issued = true;
+                }
+                if (next_issued && !next_published) {
                     cp_async_wait<0>();
-                    convert_queries(sQ + (size_t)((it + 1) & 1) * qbuf_bytes, S->qnorm[(it + 1) & 1], nkb, et);
+                    convert_queries(sQn, S->qnorm[(it + 1) & 1], nkb, et);
                     tc::fence_proxy_async_smem();
-                    mbar_arrive_warp(&S->qfull[(it + 1) & 1], lane);
+                    mbar_arrive_warp(&S->qfull[(it + 1) % NQB], lane);
                     next_published = true;
                 }
                 tc::named_bar_sync(1, EPI_THREADS);      // the chunk's v are in sV
@@ -709,9 +725,9 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     RVCR_TRY(ensure_row_norms(h, s));
     RVCR_TRY(ensure_scan_tmaps(h));
     const int d = h->d, nkb = d / stc::KB;
-    const size_t fixed = 2 * (size_t)nkb * stc::QKB_BYTES + stc::SV_BYTES + sizeof(stc::Smem) + 1024;
+    const size_t fixed = stc::NQB * (size_t)nkb * stc::QKB_BYTES + stc::SV_BYTES + sizeof(stc::Smem) + 1024;
     int nstage = (int)((226 * 1024 - fixed) / stc::STAGE_BYTES);
-    if (nstage > 8) nstage = 8;
+    if (nstage > stc::MAX_STAGES) nstage = stc::MAX_STAGES;
     if (const char* e = getenv("RVCR_STC_NSTAGE")) {   // tuning knob: fewer stages = fewer bytes in flight per SM
         const int v = atoi(e);
         if (v >= 2 && v < nstage) nstage = v;
