@@ -41,14 +41,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                int nstage, float ymax, float acc_rel, float abs_margin, int item_begin, int item_end,
                int32_t* __restrict__ cand, int32_t* __restrict__ candcnt, int32_t* __restrict__ fb_list,
                int32_t* __restrict__ fb_count, unsigned long long* __restrict__ totals /*[0] fallbacks, [1] candidates*/,
-               float2* __restrict__ stage_buf /*[grid][16][SCAP]*/, int dbg_flags, PushArgs push) {
+               float2* __restrict__ stage_buf /*[grid][16][SCAP]*/, int dbg_flags, PushArgs push, int pf_dist) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nkb = d / KB;
     uint8_t* sR = smem;                                         // nstage x 16 KB
-    uint8_t* sQ = sR + (size_t)nstage * STAGE_BYTES;            // NQB x nkb x 2 KB
+    uint8_t* sQ = sR + (size_t)nstage * STAGE_BYTES;            // 2 x nkb x 2 KB
     const int qbuf_bytes = nkb * QKB_BYTES;
-    float* sV = reinterpret_cast<float*>(sQ + NQB * (size_t)qbuf_bytes);  // [16][CHUNK_ROWS]
+    float* sV = reinterpret_cast<float*>(sQ + 2 * (size_t)qbuf_bytes);    // [16][CHUNK_ROWS]
     Smem* S = reinterpret_cast<Smem*>(reinterpret_cast<uint8_t*>(sV) + SV_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,7 +79,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
         }
         tc::mbar_init(&S->qfull[0], EPI_THREADS / 32);
         tc::mbar_init(&S->qfull[1], EPI_THREADS / 32);
-        tc::mbar_init(&S->qempty, 1);
         tc::fence_mbar_init();
     } else if (warp == 2) {
         tc::tmem_alloc<1>(&S->tmem_ptr, TMEM_COLS);
@@ -119,12 +118,40 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
             const int len = tc::warp_uniform((int)cur.len);       // < 2^31 rows per shard
             const int lb = tc::warp_uniform((int)cur.lb);
             const int ntiles = (len + TILE_M - 1) / TILE_M;
+            // L2 prefetch pf_dist stages ahead of the shared-memory ring (0 = off): the ring alone caps the bytes in flight at
+            // nstage x 16 KB per SM, and the kernel's time is inversely proportional to them (round 2, call K); a prefetch has
+            // nowhere to land but L2.  Past the end of this item the prefetches run into the next item's first stages.
+            int nlen = 0, nlb = 0;
+            if (pf_dist > 0) {
+                const uint32_t nslot = (it + 1) % IRING, nuse = (it + 1) / IRING;
+                mbar_wait_warp(&S->ifull[nslot], nuse & 1, lane);          // (released when it becomes the current item)
+                const Item nx = S->items[nslot];
+                if (nx.idx < nitems) {
+                    nlen = tc::warp_uniform((int)nx.len);
+                    nlb = tc::warp_uniform((int)nx.lb);
+                }
+            }
+            const int nst_item = ntiles * nkb;
             for (int t = 0; t < ntiles; ++t) {
                 const int left = len - t * TILE_M;
                 const int rows = left >= 97 ? 128 : left >= 65 ? 96 : left >= 33 ? 64 : 32;
                 const CUtensorMap* tm = rows == 128 ? &tm128 : rows == 96 ? &tm96 : rows == 64 ? &tm64 : &tm32;
                 const int row0 = lb + t * TILE_M;
                 for (int kb = 0; kb < nkb; ++kb) {
+                    if (pf_dist > 0) {
+                        int ps = t * nkb + kb + pf_dist, plen = len, plb = lb;
+                        if (ps >= nst_item) {
+                            ps -= nst_item;
+                            plen = nlen;
+                            plb = nlb;
+                        }
+                        const int pt = ps / nkb, pkb = ps - pt * nkb;
+                        const int pleft = plen - pt * TILE_M;
+                        if (pleft > 0 && tc::elect_one()) {
+                            const CUtensorMap* ptm = pleft >= 97 ? &tm128 : pleft >= 65 ? &tm96 : pleft >= 33 ? &tm64 : &tm32;
+                            tc::tma_prefetch_2d(ptm, pkb * KB, plb + pt * TILE_M);
+                        }
+                    }
                     mbar_wait_warp(&S->empty[stage], phase ^ 1, lane);
                     if (tc::elect_one()) {
                         const uint32_t fb = bar_addr + (uint32_t)offsetof(Smem, full) + stage * 8;
@@ -152,9 +179,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
             mbar_arrive_warp(&S->iempty[slot], lane);
             if (!tc::warp_uniform(cur.idx < nitems ? 1 : 0)) break;
             const int ntiles = tc::warp_uniform((int)((cur.len + TILE_M - 1) / TILE_M));
-            // this item's queries are in sQ[it % NQB] (one barrier per buffer)
-            mbar_wait_warp(&S->qfull[it % NQB], (it / NQB) & 1, lane);
-            const uint32_t qaddr = sQ_addr + (it % NQB) * (uint32_t)qbuf_bytes;
+            mbar_wait_warp(&S->qfull[it & 1], (it >> 1) & 1, lane);        // this item's queries are in sQ[it & 1]
+            const uint32_t qaddr = sQ_addr + (it & 1) * (uint32_t)qbuf_bytes;
             for (int t = 0; t < ntiles; ++t, ++tile_cnt) {
                 const uint32_t as = tile_cnt % NACC, ause = tile_cnt / NACC;
                 mbar_wait_warp(&S->tempty[as], (ause & 1) ^ 1, lane);      // epilogue drained this accumulator
@@ -177,10 +203,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                     __syncwarp();
                     if (++ts == NTS) { ts = 0; tphase ^= 1; }
                 }
-            }
-            if constexpr (NQB == 1) {   // fires when every MMA of this item has retired (at once for an empty list)
-                if (tc::elect_one()) tc::umma_commit_addr(bar_addr + (uint32_t)offsetof(Smem, qempty));
-                __syncwarp();
             }
         }
     } else if (warp >= CONV_WARP0) {
@@ -268,12 +290,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                 mbar_arrive_warp(&S->iempty[slot], lane);
             }
             const bool have_next = nxt.idx < nitems;
-            uint8_t* sQn = sQ + (size_t)((it + 1) % NQB) * qbuf_bytes;
-            // NQB == 2: buffer (it+1)&1 was last read by item it-1, whose MMAs and selection are complete -- load at once.
-            // NQB == 1: the one buffer is this item's; the load waits for qempty after the last chunk's accumulators (below)
-            bool next_issued = NQB == 2;
-            if (NQB == 2 && have_next) load_queries(sQn, q, push, qorder, nxt, d, nkb, et);
-            if (NQB == 2) cp_async_commit();
+            uint8_t* sQn = sQ + (size_t)((it + 1) & 1) * qbuf_bytes;
+            // buffer (it+1)&1 was last read by item it-1, whose MMAs and selection are complete.  (One buffer and three more row
+            // stages instead -- the load then waits for the item's last MMA -- measured slower: scan phase 32.4 vs 30.8 ms,
+            // round 2 call L.)
+            if (have_next) load_queries(sQn, q, push, qorder, nxt, d, nkb, et);
+            cp_async_commit();
             bool next_published = !have_next;
 
             const int cnt = cur.cnt;
@@ -312,26 +334,19 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                     for (int j = 0; j < QT; ++j)
                         if (j < cnt)   // warp-uniform
                             dst[j * CHUNK_ROWS] = valid ? fmaf(-2.f, __uint_as_float(r[j]), yn) : __int_as_float(0x7f800000);
-                    if (next_issued && !next_published) {
+                    if (!next_published) {
                         cp_async_wait<0>();
                         convert_queries(sQn, S->qnorm[(it + 1) & 1], nkb, et);
                         tc::fence_proxy_async_smem();
-                        mbar_arrive_warp(&S->qfull[(it + 1) % NQB], lane);
+                        mbar_arrive_warp(&S->qfull[(it + 1) & 1], lane);
                         next_published = true;
                     }
                 }
-                if (NQB == 1 && !next_issued && t1 >= ntiles) {
-                    // last chunk: every accumulator of the item has been read, so its MMAs are long complete
-                    mbar_wait_warp(&S->qempty, it & 1, lane);
-                    if (have_next) load_queries(sQn, q, push, qorder, nxt, d, nkb, et);
-                    cp_async_commit();
-                    next_issued = true;
-                }
-                if (next_issued && !next_published) {
+                if (!next_published) {
                     cp_async_wait<0>();
                     convert_queries(sQn, S->qnorm[(it + 1) & 1], nkb, et);
                     tc::fence_proxy_async_smem();
-                    mbar_arrive_warp(&S->qfull[(it + 1) % NQB], lane);
+                    mbar_arrive_warp(&S->qfull[(it + 1) & 1], lane);
                     next_published = true;
                 }
                 tc::named_bar_sync(1, EPI_THREADS);      // the chunk's v are in sV
@@ -461,7 +476,7 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
                     uint32_t nlist, const int32_t* __restrict__ items, const int32_t* __restrict__ nitems_ptr, int item_begin,
                     int item_end, int64_t n, int d, const float* __restrict__ vecs, const int64_t* __restrict__ ids,
                     const int32_t* __restrict__ cand, const int32_t* __restrict__ candcnt, float* __restrict__ D,
-                    int32_t* __restrict__ P, int64_t* __restrict__ I, BlendArgs ba) {
+                    int32_t* __restrict__ P, int64_t* __restrict__ I, BlendArgs ba, int l2_prefetch) {
     extern __shared__ __align__(16) float rc_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* sq = rc_smem + (size_t)w * d;
@@ -489,6 +504,12 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
                 const bool have = c < nc;
                 const int pos = cand[qi * stc::CCAP + (have ? c : 0)];
                 const float4* y4 = reinterpret_cast<const float4*>(vecs + (int64_t)pos * d) + h;
+                if (l2_prefetch && have) {
+                    // the whole candidate row towards L2 at once (each lane of the pair every other 128-byte line): the distance
+                    // loop below keeps only UNR x 32 B per row in flight, and the kernel is bound by bytes in flight
+                    const char* row = reinterpret_cast<const char*>(vecs + (int64_t)pos * d);
+                    for (int off = (l2_prefetch + h) * 128; off < d * 4; off += 256) tc::prefetch_l2(row + off);
+                }
                 const float4* x4 = reinterpret_cast<const float4*>(sq) + h;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll UNR
@@ -725,7 +746,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     RVCR_TRY(ensure_row_norms(h, s));
     RVCR_TRY(ensure_scan_tmaps(h));
     const int d = h->d, nkb = d / stc::KB;
-    const size_t fixed = stc::NQB * (size_t)nkb * stc::QKB_BYTES + stc::SV_BYTES + sizeof(stc::Smem) + 1024;
+    const size_t fixed = 2 * (size_t)nkb * stc::QKB_BYTES + stc::SV_BYTES + sizeof(stc::Smem) + 1024;
     int nstage = (int)((226 * 1024 - fixed) / stc::STAGE_BYTES);
     if (nstage > stc::MAX_STAGES) nstage = stc::MAX_STAGES;
     if (const char* e = getenv("RVCR_STC_NSTAGE")) {   // tuning knob: fewer stages = fewer bytes in flight per SM
@@ -753,13 +774,15 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     const float rel = 1.f / 1048576.f + (float)d / 2097152.f;
     const float absm = 1.f / 524288.f;
     int grid = h->num_sms;
+    int pf_dist = 0;   // RVCR_STC_PREFETCH = stages of L2 prefetch ahead of the ring
+    if (const char* e = getenv("RVCR_STC_PREFETCH")) pf_dist = atoi(e) > 0 ? atoi(e) : 0;
     const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(h->scan_tmaps);
     stc::scan_tc_kernel<<<grid, stc::THREADS, smem, s>>>(
         tm[0], tm[1], tm[2], tm[3], q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), h->ws_items.as<int32_t>(),
         h->ws_misc.as<int32_t>(), h->ws_misc.as<int32_t>() + ticket_slot, h->offsets, h->row_norm.as<float>(), (uint32_t)h->nlist, n, d,
         nstage, h->row_norm_max, rel, absm, item_begin, item_end, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
         h->ws_fb.as<int32_t>(), fb_count, reinterpret_cast<unsigned long long*>(h->ws_misc.as<int32_t>() + 48),
-        h->ws_cstage.as<float2>(), getenv("RVCR_STC_FLAGS") ? atoi(getenv("RVCR_STC_FLAGS")) : 0, h->fuse.push);
+        h->ws_cstage.as<float2>(), getenv("RVCR_STC_FLAGS") ? atoi(getenv("RVCR_STC_FLAGS")) : 0, h->fuse.push, pf_dist);
     RVCR_CHECK_LAUNCH();
     // fused tail (search_device sets h->fuse for rvcr_retrieve_blend*): the re-check / fallback kernels also blend
     const bool blend = h->fuse.active;
@@ -780,6 +803,8 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
             // 8 x 16: 11.2 (twice) -> default.  Fewer resident warps do NOT buy L2 hits for the second read of the final 8 rows;
             // the kernel wants bytes in flight.
             int per_sm = 8, unr = 16;
+            int rc_prefetch = 0;   // RVCR_RC_PREFETCH = n > 0: L2-prefetch each candidate row from its n-th 128-byte line on
+            if (const char* e = getenv("RVCR_RC_PREFETCH")) rc_prefetch = atoi(e) > 0 ? atoi(e) : 0;
             if (const char* e = getenv("RVCR_RC_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // tuning knobs
             if (const char* e = getenv("RVCR_RC_UNROLL")) unr = atoi(e) == 8 ? 8 : 16;
             int64_t rgrid = (int64_t)h->num_sms * per_sm;
@@ -790,7 +815,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
             kern<<<(unsigned)rgrid, RC_WARPS * 32, rsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), (uint32_t)h->nlist,
                                                              h->ws_items.as<int32_t>(), h->ws_misc.as<int32_t>(), item_begin, item_end, n,
                                                              d, h->vecs, h->ids, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
-                                                             D, P, I, ba);
+                                                             D, P, I, ba, rc_prefetch);
         }
         RVCR_CHECK_LAUNCH();
     }

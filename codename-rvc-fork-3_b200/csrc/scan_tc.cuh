@@ -36,13 +36,7 @@ constexpr int SCAP = 256;                   // (v, position) pairs staged per qu
 constexpr int CHUNK_TILES = RVCR_STC_CHUNK_TILES;   // the epilogue selects candidates per chunk of 4 tiles = 512 list rows
 constexpr int CHUNK_ROWS = CHUNK_TILES * TILE_M;
 constexpr int SV_BYTES = QT * CHUNK_ROWS * 4;   // v of one chunk: [16 queries][512 rows] fp32 = 32 KB
-#ifndef RVCR_STC_NQB
-#define RVCR_STC_NQB 2
-#endif
-constexpr int NQB = RVCR_STC_NQB;           // query operand buffers (d x 64 B each): 2 = the next item's queries load while this item's
-                                            // MMAs run; 1 = they load when the item's last MMA has retired, and the 48 KB (d = 768) go
-                                            // to the row ring instead (3 more stages in flight)
-constexpr int MAX_STAGES = 12;
+constexpr int MAX_STAGES = 8;
 
 struct Item {
     int idx;   // ticket; >= nitems: stop
@@ -56,7 +50,6 @@ struct Smem {
     uint64_t tfull[NACC], tempty[NACC];
     uint64_t ifull[IRING], iempty[IRING];
     uint64_t qfull[2];
-    uint64_t qempty;                       // NQB == 1: the item's MMAs have retired, the query buffer may be overwritten
     Item items[IRING];
     float2 qnorm[2][QT];      // (||q||^2, ||q - tf32(q)||^2) of the queries staged in sQ[buf]
     uint32_t tmem_ptr;
