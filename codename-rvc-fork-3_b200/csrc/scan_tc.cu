@@ -41,7 +41,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
                int nstage, float ymax, float acc_rel, float abs_margin, int item_begin, int item_end,
                int32_t* __restrict__ cand, int32_t* __restrict__ candcnt, int32_t* __restrict__ fb_list,
                int32_t* __restrict__ fb_count, unsigned long long* __restrict__ totals /*[0] fallbacks, [1] candidates*/,
-               float2* __restrict__ stage_buf /*[grid][16][SCAP]*/, int dbg_flags, PushArgs push, int pf_dist) {
+               float2* __restrict__ stage_buf /*[grid][16][SCAP]*/, int dbg_flags, PushArgs push) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nkb = d / KB;
@@ -118,40 +118,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
             const int len = tc::warp_uniform((int)cur.len);       // < 2^31 rows per shard
             const int lb = tc::warp_uniform((int)cur.lb);
             const int ntiles = (len + TILE_M - 1) / TILE_M;
-            // L2 prefetch pf_dist stages ahead of the shared-memory ring (0 = off): the ring alone caps the bytes in flight at
-            // nstage x 16 KB per SM, and the kernel's time is inversely proportional to them (round 2, call K); a prefetch has
-            // nowhere to land but L2.  Past the end of this item the prefetches run into the next item's first stages.
-            int nlen = 0, nlb = 0;
-            if (pf_dist > 0) {
-                const uint32_t nslot = (it + 1) % IRING, nuse = (it + 1) / IRING;
-                mbar_wait_warp(&S->ifull[nslot], nuse & 1, lane);          // (released when it becomes the current item)
-                const Item nx = S->items[nslot];
-                if (nx.idx < nitems) {
-                    nlen = tc::warp_uniform((int)nx.len);
-                    nlb = tc::warp_uniform((int)nx.lb);
-                }
-            }
-            const int nst_item = ntiles * nkb;
             for (int t = 0; t < ntiles; ++t) {
                 const int left = len - t * TILE_M;
                 const int rows = left >= 97 ? 128 : left >= 65 ? 96 : left >= 33 ? 64 : 32;
                 const CUtensorMap* tm = rows == 128 ? &tm128 : rows == 96 ? &tm96 : rows == 64 ? &tm64 : &tm32;
                 const int row0 = lb + t * TILE_M;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    if (pf_dist > 0) {
-                        int ps = t * nkb + kb + pf_dist, plen = len, plb = lb;
-                        if (ps >= nst_item) {
-                            ps -= nst_item;
-                            plen = nlen;
-                            plb = nlb;
-                        }
-                        const int pt = ps / nkb, pkb = ps - pt * nkb;
-                        const int pleft = plen - pt * TILE_M;
-                        if (pleft > 0 && tc::elect_one()) {
-                            const CUtensorMap* ptm = pleft >= 97 ? &tm128 : pleft >= 65 ? &tm96 : pleft >= 33 ? &tm64 : &tm32;
-                            tc::tma_prefetch_2d(ptm, pkb * KB, plb + pt * TILE_M);
-                        }
-                    }
                     mbar_wait_warp(&S->empty[stage], phase ^ 1, lane);
                     if (tc::elect_one()) {
                         const uint32_t fb = bar_addr + (uint32_t)offsetof(Smem, full) + stage * 8;
@@ -476,7 +448,7 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
                     uint32_t nlist, const int32_t* __restrict__ items, const int32_t* __restrict__ nitems_ptr, int item_begin,
                     int item_end, int64_t n, int d, const float* __restrict__ vecs, const int64_t* __restrict__ ids,
                     const int32_t* __restrict__ cand, const int32_t* __restrict__ candcnt, float* __restrict__ D,
-                    int32_t* __restrict__ P, int64_t* __restrict__ I, BlendArgs ba, int l2_prefetch) {
+                    int32_t* __restrict__ P, int64_t* __restrict__ I, BlendArgs ba) {
     extern __shared__ __align__(16) float rc_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* sq = rc_smem + (size_t)w * d;
@@ -504,12 +476,6 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
                 const bool have = c < nc;
                 const int pos = cand[qi * stc::CCAP + (have ? c : 0)];
                 const float4* y4 = reinterpret_cast<const float4*>(vecs + (int64_t)pos * d) + h;
-                if (l2_prefetch && have) {
-                    // the whole candidate row towards L2 at once (each lane of the pair every other 128-byte line): the distance
-                    // loop below keeps only UNR x 32 B per row in flight, and the kernel is bound by bytes in flight
-                    const char* row = reinterpret_cast<const char*>(vecs + (int64_t)pos * d);
-                    for (int off = (l2_prefetch + h) * 128; off < d * 4; off += 256) tc::prefetch_l2(row + off);
-                }
                 const float4* x4 = reinterpret_cast<const float4*>(sq) + h;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll UNR
@@ -749,7 +715,12 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     const size_t fixed = 2 * (size_t)nkb * stc::QKB_BYTES + stc::SV_BYTES + sizeof(stc::Smem) + 1024;
     int nstage = (int)((226 * 1024 - fixed) / stc::STAGE_BYTES);
     if (nstage > stc::MAX_STAGES) nstage = stc::MAX_STAGES;
-    if (const char* e = getenv("RVCR_STC_NSTAGE")) {   // tuning knob: fewer stages = fewer bytes in flight per SM
+    // Stages vs time of the streaming kernel at C5 (round 2, calls K - M): 3 / 4 / 5 / 6 stages -> 35.7 / 28.8 / 23.8 / 19.7 ms, but 9 stages
+    // (one query operand buffer instead of two) were slower (the per-item query load then stalls the MMAs), and a TMA L2
+    // prefetch (cp.async.bulk.prefetch.tensor) 3 .. 48 stages ahead of the ring cost +6 .. +11 ms: past 6 stages the kernel is
+    // bound by what the DRAM system delivers for 128-byte segments at a 3 KB stride (70 % of its cycles active), not by bytes
+    // in flight.
+    if (const char* e = getenv("RVCR_STC_NSTAGE")) {   // tuning knob
         const int v = atoi(e);
         if (v >= 2 && v < nstage) nstage = v;
     }
@@ -774,15 +745,13 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
     const float rel = 1.f / 1048576.f + (float)d / 2097152.f;
     const float absm = 1.f / 524288.f;
     int grid = h->num_sms;
-    int pf_dist = 0;   // RVCR_STC_PREFETCH = stages of L2 prefetch ahead of the ring
-    if (const char* e = getenv("RVCR_STC_PREFETCH")) pf_dist = atoi(e) > 0 ? atoi(e) : 0;
     const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(h->scan_tmaps);
     stc::scan_tc_kernel<<<grid, stc::THREADS, smem, s>>>(
         tm[0], tm[1], tm[2], tm[3], q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), h->ws_items.as<int32_t>(),
         h->ws_misc.as<int32_t>(), h->ws_misc.as<int32_t>() + ticket_slot, h->offsets, h->row_norm.as<float>(), (uint32_t)h->nlist, n, d,
         nstage, h->row_norm_max, rel, absm, item_begin, item_end, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
         h->ws_fb.as<int32_t>(), fb_count, reinterpret_cast<unsigned long long*>(h->ws_misc.as<int32_t>() + 48),
-        h->ws_cstage.as<float2>(), getenv("RVCR_STC_FLAGS") ? atoi(getenv("RVCR_STC_FLAGS")) : 0, h->fuse.push, pf_dist);
+        h->ws_cstage.as<float2>(), getenv("RVCR_STC_FLAGS") ? atoi(getenv("RVCR_STC_FLAGS")) : 0, h->fuse.push);
     RVCR_CHECK_LAUNCH();
     // fused tail (search_device sets h->fuse for rvcr_retrieve_blend*): the re-check / fallback kernels also blend
     const bool blend = h->fuse.active;
@@ -801,10 +770,8 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
             // CTAs per SM x float4 loads in flight per lane, measured at C5 (ms for the kernel): r01 10 x 8: 12.5; r02 call I
             // (RVCR_RC_CTAS x RVCR_RC_UNROLL): 2 x 16: 25.1, 3 x 16: 18.1, 4 x 16: 15.1, 4 x 8: 17.5, 6 x 16: 12.5, 10 x 8: 11.6,
             // 8 x 16: 11.2 (twice) -> default.  Fewer resident warps do NOT buy L2 hits for the second read of the final 8 rows;
-            // the kernel wants bytes in flight.
+            // the kernel wants bytes in flight.  (prefetch.global.L2 of every candidate row up front: 12.3 ms -- call M.)
             int per_sm = 8, unr = 16;
-            int rc_prefetch = 0;   // RVCR_RC_PREFETCH = n > 0: L2-prefetch each candidate row from its n-th 128-byte line on
-            if (const char* e = getenv("RVCR_RC_PREFETCH")) rc_prefetch = atoi(e) > 0 ? atoi(e) : 0;
             if (const char* e = getenv("RVCR_RC_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // tuning knobs
             if (const char* e = getenv("RVCR_RC_UNROLL")) unr = atoi(e) == 8 ? 8 : 16;
             int64_t rgrid = (int64_t)h->num_sms * per_sm;
@@ -815,7 +782,7 @@ int scan_tc_range(rvcr_index* h, const float* q, int64_t n, float* D, int32_t* P
             kern<<<(unsigned)rgrid, RC_WARPS * 32, rsm, s>>>(q, h->ws_vals2.as<int32_t>(), h->ws_keys2.as<uint32_t>(), (uint32_t)h->nlist,
                                                              h->ws_items.as<int32_t>(), h->ws_misc.as<int32_t>(), item_begin, item_end, n,
                                                              d, h->vecs, h->ids, h->ws_cand.as<int32_t>(), h->ws_candcnt.as<int32_t>(),
-                                                             D, P, I, ba, rc_prefetch);
+                                                             D, P, I, ba);
         }
         RVCR_CHECK_LAUNCH();
     }

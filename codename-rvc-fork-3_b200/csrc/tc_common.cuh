@@ -61,17 +61,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 }
 
 // ---- TMA -----------------------------------------------------------------------------------
-// L2 prefetch of one line / of a 2-D TMA box: a request that needs no register or shared memory to land in, so the
-// bytes in flight towards DRAM are not capped by either
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(p)) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int32_t c0, int32_t c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0),
-                 "r"(c1)
-                 : "memory");
-}
-
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
