@@ -649,11 +649,17 @@ def main():
     gpu_rows = gpu_rows_dev.cpu().numpy() if gpu_rows_dev is not None else None
     result_check = gpu_rows[:4] if gpu_rows is not None else None
 
-    # ---- per-phase device times (separate pass, same inputs) for the roofline --------------------
+    # ---- per-phase device times for the roofline: the library keeps the CUDA events of its LAST call only, and reading
+    # them needs a synchronize, so they cannot be collected inside the timed loop.  Each repetition therefore enqueues three
+    # steps back to back -- the same power / clock regime as the timed region (a lone step after an idle gap runs ~3 %
+    # faster: sw_power_cap has not pulled the clocks down yet) -- and reads the phases of the third.
     phase_acc = {}
     reps = max(1, min(args.steps, 3))
     for _ in range(reps):
-        scratch.copy_(q_home)
+        for b in (ring[0], ring[1 % R], scratch):
+            b.copy_(q_home)
+        step(ring[0])
+        step(ring[1 % R])
         step(scratch)
         torch.cuda.synchronize()
         for k, v in index.phase_ms().items():

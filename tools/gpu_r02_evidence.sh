@@ -30,4 +30,6 @@ PY
     -s 16 -c 4 -o gpurun_out/r02_full_c5 -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --query-skew 0 ) > gpurun_out/r02_ncu_full.log 2>&1
 ncu -i gpurun_out/r02_full_c5.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_c5.csv 2>/dev/null
 bash tools/sanitize.sh
+( time timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 ) > gpurun_out/r02_pytest_gpu_full.log 2>&1; echo "full gpu suite rc=$?"; tail -5 gpurun_out/r02_pytest_gpu_full.log
+( timeout 120 python -c 'import __graft_entry__ as g; g.smoke()' ) > gpurun_out/r02_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/r02_smoke.log
 ls -la gpurun_out | tail -6
