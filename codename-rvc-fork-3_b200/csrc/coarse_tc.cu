@@ -55,9 +55,6 @@ constexpr int THREADS = (EPI_WARP0 + 4 * NCG) * 32;   // 640
 //   columns per tcgen05.ld x queue slots     16 x 4         32 x 2         16 x 2
 //   e4m3 (epilogue on the critical path)     61.6           65.1           63.6
 //   bf16 (tensor pipe / power bound)         103.3          102.2          103.7
-#ifndef RVCR_TC_F8_PARK
-#define RVCR_TC_F8_PARK 0
-#endif
 template <int F8> struct EpiCfg { static constexpr int SUBC = F8 ? 16 : 32, QCAP = F8 ? 4 : 2; };
 
 // Candidate list of one (query, split, column group): up to TOPT (key, centroid) pairs, unsorted.  An element is looked at
@@ -437,11 +434,10 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + cg * CGW;
                 const float4* sn4 = reinterpret_cast<const float4*>(sNorm + as * BLOCK_N + cg * CGW);
                 const int j0 = t * BLOCK_N + cg * CGW;
-                // the long wait of this warp.  bf16 (power-bound): parked in hardware, not polled.  e4m3 (the epilogue is on the
-                // critical path and the chip has power to spare): polled -- a parked warp was seen to resume late (call G: tiles
-                // took (M + E) / 2 with E = 11 k cycles although the epilogue warps slept most of the time)
-                if constexpr (F8 && !RVCR_TC_F8_PARK) mbar_wait_warp(&tmem_full_bar[as], aphase, lane);
-                else mbar_wait_warp_parked(&tmem_full_bar[as], aphase, lane);
+                // the long wait of this warp: parked in hardware (mbarrier.try_wait with a suspend hint), not polled.  For e4m3 a polled
+                // wait was tried twice (calls H and N) on the suspicion that a parked warp resumes late: no difference either time
+                // (63.8 / 64.4 ms polled, 63.7 / 64.2 parked), and the spin loop was 36 % of the kernel's executed instructions.
+                mbar_wait_warp_parked(&tmem_full_bar[as], aphase, lane);
                 tc_fence_after();
                 mbar_wait_warp(&norm_full_bar[as], aphase, lane);
                 // Phase A -- the accumulator stage is held.  Read this warp's columns SUBC at a time; keys that reach the threshold are
