@@ -800,31 +800,41 @@ __global__ void tc_recheck_kernel(const float* __restrict__ q, int64_t n, int d,
     float bd = RVCR_FLT_MAX;
     int bj = -1;
     int ncand = 0;
-    for (int e0 = 0; e0 < total; e0 += 4) {
-        const int e = e0 + grp;
+    // 32 kept entries at a time: the ones inside the margin are compacted with a ballot and evaluated four at a time, 8 lanes
+    // each (canonical order: lane l8 owns accumulator l8), so a query with 4 candidates costs one pass over the row, not four
+    for (int e0 = 0; e0 < total; e0 += 32) {
+        const int e = e0 + lane;
         int j = -1;
         float v = 0.f;
         if (e < total) {
             j = tj[e];
             v = tv[e];
         }
-        const bool take = j >= 0 && j < nlist && v <= thr;
-        if (!__any_sync(0xffffffffu, take)) continue;
-        float acc = 0.f;
-        if (take) {
-            const float* crow = cent + (int64_t)j * d;
-            for (int i = 0; i < d; i += 8) {
-                const float t = __fsub_rn(qrow[i + l8], crow[i + l8]);
-                acc = __fmaf_rn(t, t, acc);
+        unsigned m = __ballot_sync(0xffffffffu, j >= 0 && j < nlist && v <= thr);
+        while (m) {
+            const unsigned src = __fns(m, 0, grp + 1);              // the (grp+1)-th candidate of this batch, if any
+            const int cj = __shfl_sync(0xffffffffu, j, src & 31);
+            const bool take = src != 0xffffffffu;
+            float acc = 0.f;
+            if (take) {
+                const float* crow = cent + (int64_t)cj * d;
+#pragma unroll 8
+                for (int i = 0; i < d; i += 8) {
+                    const float t = __fsub_rn(qrow[i + l8], __ldg(crow + i + l8));
+                    acc = __fmaf_rn(t, t, acc);
+                }
             }
-        }
-        acc = reduce8_canonical(acc);
-        if (take) {
-            ++ncand;
-            if (acc < bd || (acc == bd && j < bj)) {
-                bd = acc;
-                bj = j;
+            acc = reduce8_canonical(acc);
+            if (take) {
+                ++ncand;
+                if (acc < bd || (acc == bd && cj < bj)) {
+                    bd = acc;
+                    bj = cj;
+                }
             }
+            // drop the (up to) four candidates just evaluated
+#pragma unroll
+            for (int k = 0; k < 4; ++k) m &= m - 1;
         }
     }
     // merge the 4 groups (lanes 0, 8, 16, 24 hold distinct candidates) by (distance, id)
