@@ -8,10 +8,12 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 ( time timeout 400 python bench.py ) > gpurun_out/r02_bench_c5_n1.log 2>&1
 grep '^{' gpurun_out/r02_bench_c5_n1.log > gpurun_out/r02_bench_c5_n1.json; tail -c 300 gpurun_out/r02_bench_c5_n1.log
 ( timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline ) 2>/dev/null | grep '^{' > gpurun_out/r02_bench_c5_n1_steps20.json
+if [ -z "${SLIM:-}" ]; then   # SLIM=1: only the C5 lines and the ncu captures (a re-run after a small change)
 ( timeout 300 python bench.py --coarse-f8-auto 0 --steps 5 --no-cpu-baseline --query-skew 0 ) 2>/dev/null | grep '^{' > gpurun_out/r02_bench_c5_n1_bf16.json
 ( timeout 300 python bench.py --impl reference --steps 2 ) 2>/dev/null | grep '^{' > gpurun_out/r02_bench_c5_ref.json
 ( timeout 400 python bench.py --workload C4 --steps 3 ) 2>/dev/null | grep '^{' > gpurun_out/r02_bench_c4.json
 for w in C1 C2 C3; do ( timeout 200 python bench.py --workload $w --steps 20 --query-skew 0 ) 2>/dev/null | grep '^{' > gpurun_out/r02_bench_${w}.json; done
+fi
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/r02_bench_*.json")):
@@ -29,6 +31,7 @@ PY
     -k regex:'coarse_tc_kernel|scan_tc_kernel|scan_recheck_kernel|tc_recheck_kernel' \
     -s 16 -c 4 -o gpurun_out/r02_full_c5 -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --query-skew 0 ) > gpurun_out/r02_ncu_full.log 2>&1
 ncu -i gpurun_out/r02_full_c5.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_c5.csv 2>/dev/null
+if [ -n "${SLIM:-}" ]; then ls -la gpurun_out | tail -6; exit 0; fi
 bash tools/sanitize.sh
 ( time timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 ) > gpurun_out/r02_pytest_gpu_full.log 2>&1; echo "full gpu suite rc=$?"; tail -5 gpurun_out/r02_pytest_gpu_full.log
 ( timeout 120 python -c 'import __graft_entry__ as g; g.smoke()' ) > gpurun_out/r02_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/r02_smoke.log
