@@ -24,8 +24,9 @@
 //   warp 1   MMA issuer (one elected thread; leader CTA only): 4 x tcgen05.mma (K = 16) per stage
 //            into a 128 x 256 fp32 accumulator, double-buffered in TMEM (2 x 256 columns)
 //   warp 2   TMEM allocator
-//   warps 4-19 epilogue (4 lane quarters x 4 column groups): tcgen05.ld 32 columns at a time, key = 2 acc - ||c||^2,
-//            per row the candidates within margin(q) of the running best; overlaps the next tile's MMAs
+//   warps 4-19 epilogue (4 lane quarters x 4 column groups): tcgen05.ld 16 / 32 columns at a time, key = 2 acc - ||c||^2,
+//            per row the candidates within margin(q) of the running best (queued while the accumulator stage is held,
+//            worked into the row's list after it has been handed back); overlaps the next tile's MMAs
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
@@ -192,11 +193,12 @@ struct Cfg {
 // r01_ncu_summary.md) showed the tensor pipe idle 35 % of the time behind it (a third of the epilogue warps' samples on
 // the first FFMA after the loads, a quarter on branch resolution) -- and e4m3 operands, which halve the MMA time, gained
 // only 10 %.  Now 4 x NCG warps drain a tile (warp w: TMEM lane quarter w % 4, columns [cg 256/NCG, (cg + 1) 256/NCG) with
-// cg = (w - 4) / 4), the next 32-column load is in flight while the current one is processed, the tile's ||c||^2 arrive
-// in shared memory by one 1 KB bulk copy per tile (producer warp, double-buffered with the accumulator stages) and are
-// read as broadcast LDS.128, and a chunk is searched for insertions only if its maximum beats the row's current 8th
-// key (one branch per 32 columns).  Keys are -v = 2 <q', c'> - ||c||^2 (larger = nearer).  Each (query, split, column
-// group) writes its own top-8; the re-check merges them.
+// cg = (w - 4) / 4), the tile's ||c||^2 arrive in shared memory by one 1 KB bulk copy per tile (producer warp, double-
+// buffered with the accumulator stages) and are read as broadcast LDS.128, and the columns of one tcgen05.ld (16 for
+// e4m3, 32 for bf16: EpiCfg) are looked at one by one only if their maximum reaches the row's current threshold (one
+// branch per load).  A key that does is only remembered while the accumulator stage is held (register queue); the list
+// maintenance (cand_insert) runs after the stage has gone back to the MMA warp.  Keys are -v = 2 <q', c'> - ||c||^2
+// (larger = nearer).  Each (query, split, column group) writes its own list of up to 8; the re-check merges them.
 //
 // F8 = 1 (coarse_mode 4): e4m3 operands (kind::f8f6f4).  A 128-byte k-block then holds 128 elements
 // instead of 64, every tile / descriptor / byte count stays as it is, the instruction descriptor and the MMA kind
