@@ -434,25 +434,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__
 // distance of each candidate -- two lanes per candidate, lane h owns accumulators 4h..4h+3 (float4 loads),
 // sequential over the row exactly like fvec_L2sqr -- then top-8 by (distance, position).
 constexpr int RC_WARPS = 4;
-#ifndef RVCR_RC_CS
-#define RVCR_RC_CS 0
-#endif
-// L2 replacement hints of the tail kernel (RVCR_RC_CS): 1 = what is touched for the last time -- the query row, the gather of
-// the final 8 rows, the output row -- is loaded / stored evict-first (ld.global.cs / st.global.cs), so that it does not push
-// out the candidate rows other warps still have to gather; 2 = additionally the candidate rows are loaded evict-last.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ float4 ldg_l2_hint(const float4* p, uint64_t pol) {
-    float4 v;
-    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-        : "l"(p), "l"(pol));
-    return v;
-}
-
 // BLEND: the warp that has just found a query's exact top-8 also gathers those 8 rows (it read them a moment ago:
 // L1 / L2 hits instead of a second trip to HBM), applies the 1/score^2 weights and the index_rate blend and writes
 // the output row -- rvc/infer/pipeline.py:500-506 without a separate gather kernel.
@@ -475,7 +456,6 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
     const int64_t last = item_end < nit ? (int64_t)items[item_end] : n;
     const int h = lane & 1;
     const int nvec = d >> 2;
-    const uint64_t pol_last = RVCR_RC_CS == 2 ? l2_policy_evict_last() : 0;
     for (int64_t p = first + (int64_t)blockIdx.x * RC_WARPS + w; p < last; p += (int64_t)gridDim.x * RC_WARPS) {
         if (keys[p] == nlist + 1u) continue;   // another shard's query (sorted last; forms no work item)
         const int64_t qi = qorder[p];
@@ -486,7 +466,7 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
         if (nc > 0 || BLEND) {
             __syncwarp();
             const float4* q4 = reinterpret_cast<const float4*>(query_row(q, ba.push, qi, d));
-            for (int c = lane; c < nvec; c += 32) reinterpret_cast<float4*>(sq)[c] = RVCR_RC_CS ? __ldcs(q4 + c) : q4[c];
+            for (int c = lane; c < nvec; c += 32) reinterpret_cast<float4*>(sq)[c] = __ldcs(q4 + c);   // (streaming: see the gather below)
             __syncwarp();
         }
         if (nc > 0) {
@@ -499,7 +479,7 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll UNR
                 for (int i = 0; i < (d >> 3); ++i) {
-                    const float4 y = RVCR_RC_CS == 2 ? ldg_l2_hint(y4 + 2 * i, pol_last) : __ldg(y4 + 2 * i);
+                    const float4 y = __ldg(y4 + 2 * i);
                     const float4 x = x4[2 * i];
                     const float t0 = __fsub_rn(x.x, y.x), t1 = __fsub_rn(x.y, y.y), t2 = __fsub_rn(x.z, y.z), t3 = __fsub_rn(x.w, y.w);
                     a0 = __fmaf_rn(t0, t0, a0);
@@ -538,13 +518,15 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
             for (int c = lane; c < nvec; c += 32) {
                 float4 v[RVCR_K];
 #pragma unroll
-                for (int k = 0; k < RVCR_K; ++k)
-                    v[k] = rows[k] ? (RVCR_RC_CS ? __ldcs(rows[k] + c) : __ldg(rows[k] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // What is touched for the last time -- the query row above, these 8 rows, the output row -- is loaded / stored
+                // evict-first (ld.global.cs / st.global.cs): it then does not push the candidate rows that other warps still
+                // have to gather out of L2.  Tail kernel 11.3 -> 10.3 ms at C5 (round 2, call Q); loading the candidate rows
+                // evict-last on top of that changed nothing (10.5).
+                for (int k = 0; k < RVCR_K; ++k) v[k] = rows[k] ? __ldcs(rows[k] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 f0 = reinterpret_cast<const float4*>(sq)[c];
                 const float4 o = blend_vec(v, wk, f0, ba.r32, ba.omr32);
                 if (BLEND == 2) post_store(ba.post, qi, d, c, o, f0);
-                else if (RVCR_RC_CS) __stcs(o4 + c, o);
-                else o4[c] = o;
+                else __stcs(o4 + c, o);
             }
         }
     }
