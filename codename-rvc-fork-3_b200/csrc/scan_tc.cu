@@ -466,7 +466,7 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
         if (nc > 0 || BLEND) {
             __syncwarp();
             const float4* q4 = reinterpret_cast<const float4*>(query_row(q, ba.push, qi, d));
-            for (int c = lane; c < nvec; c += 32) reinterpret_cast<float4*>(sq)[c] = __ldcs(q4 + c);   // (streaming: see the gather below)
+            for (int c = lane; c < nvec; c += 32) reinterpret_cast<float4*>(sq)[c] = BLEND == 3 ? q4[c] : __ldcs(q4 + c);   // (streaming: see the gather below)
             __syncwarp();
         }
         if (nc > 0) {
@@ -522,10 +522,14 @@ scan_recheck_kernel(const float* __restrict__ q, const int32_t* __restrict__ qor
                 // evict-first (ld.global.cs / st.global.cs): it then does not push the candidate rows that other warps still
                 // have to gather out of L2.  Tail kernel 11.3 -> 10.3 ms at C5 (round 2, call Q); loading the candidate rows
                 // evict-last on top of that changed nothing (10.5).
-                for (int k = 0; k < RVCR_K; ++k) v[k] = rows[k] ? __ldcs(rows[k] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // (The multi-GPU instantiation, BLEND == 3, keeps the plain loads / stores it was validated with on 2 and 8 GPUs:
+                // its query and output rows live in peer memory.)
+                for (int k = 0; k < RVCR_K; ++k)
+                    v[k] = rows[k] ? (BLEND == 3 ? __ldg(rows[k] + c) : __ldcs(rows[k] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 f0 = reinterpret_cast<const float4*>(sq)[c];
                 const float4 o = blend_vec(v, wk, f0, ba.r32, ba.omr32);
                 if (BLEND == 2) post_store(ba.post, qi, d, c, o, f0);
+                else if (BLEND == 3) o4[c] = o;
                 else __stcs(o4 + c, o);
             }
         }
