@@ -1063,7 +1063,7 @@ int rvcr_set_option(rvcr_index* h, const char* key, int64_t value) {
     if (!h || !key) return RVCR_ERR_INVALID;
     std::lock_guard<std::mutex> lock(h->mu);
     if (!strcmp(key, "coarse_mode")) {
-        if (value < 0 || value > 4) return RVCR_ERR_INVALID;   // 4: experimental e4m3 operands, never chosen by auto
+        if (value < 0 || value > 4) return RVCR_ERR_INVALID;   // 4: e4m3 operands (auto picks them only through the coarse_f8_auto probe)
         h->opt.coarse_mode = value;
     } else if (!strcmp(key, "profile")) {
         h->opt.profile = value ? 1 : 0;

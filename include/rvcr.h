@@ -294,11 +294,12 @@ RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, i
 /* keys: "coarse_mode" 0 = auto (tcgen05 from "coarse_tc_min_flops" = 6.4e7 flop per call, else the exact FFMA kernel:
  *                     same bits, lower fixed cost), 1 = exact FFMA kernel, 2 = tcgen05 bf16 + exact re-check,
  *                     3 = tcgen05 3-way split bf16 + exact re-check
- *                     4 = tcgen05 e4m3 operands + exact re-check (experimental, explicit only: twice the tensor rate, a
- *                         much wider margin -- pays off when few centroids lie near the best one, else queries fall
- *                         back to the exact kernel; results are identical either way)
- *       "coarse_f8_auto" 0 (default) / 1: in auto mode, probe coarse_mode 4 on the first 8 192 queries of the first call of
- *                     >= 65 536 queries per centroid set and keep it when <= 0.5 % of the probe fell back (experimental);
+ *                     4 = tcgen05 e4m3 operands + exact re-check: twice the tensor rate, a much wider margin -- pays off
+ *                         when few centroids lie near the best one, else queries fall back to the exact kernel; results
+ *                         are identical either way (auto picks it only through the probe below)
+ *       "coarse_f8_auto" 1 (default) / 0: in auto mode, probe coarse_mode 4 on the first 8 192 queries of the first call of
+ *                     >= 65 536 queries per centroid set and keep it when <= 0.5 % of the probe fell back (a later call that
+ *                     falls back for > 2 % of its queries switches it off again);
  *                     "coarse_f8_decision" (read only) tells the outcome: 0 not probed, 1 e4m3, -1 bf16
  *       "nan_on_zero_score" 1 (default, reference behaviour: exact-match query -> NaN row)
  *       "profile" 0/1 record per-phase CUDA events (see rvcr_get_phase_ms)
@@ -307,8 +308,9 @@ RVCR_API int rvcr_merge_topk(const float* D_all_dev, const int64_t* I_all_dev, i
  *                     in shared memory per work item (0 streams both operands through the L2)
  *       "fused_blend" 1 (default): with the tcgen05 scan the exact re-check kernel also applies the 1/score^2 weights and
  *                     the index_rate blend (the 8 neighbour rows are still in cache); 0 = separate gather_blend kernel
- *       "scan_impl" 0 (default) auto: 5 for calls of >= "scan_tc_min_queries" (1024) queries, else 4;
- *                   5 tcgen05 tf32 scan + exact re-check; 1-4 exact FFMA scans
+ *       "scan_impl" 0 (default) auto: 5 for calls of >= "scan_tc_min_queries" (1024) queries, else the exact FFMA scan;
+ *                   5 tcgen05 tf32 scan + exact re-check; 1-4 the exact FFMA scan (one kernel since round 2; the
+ *                   values are kept for callers that set them)
  *       "kmeans_niter" 10 (default): Lloyd iterations of rvcr_index_train (0 = the initial centroids only) */
 RVCR_API int rvcr_set_option(rvcr_index* h, const char* key, int64_t value);
 RVCR_API int rvcr_get_option(rvcr_index* h, const char* key, int64_t* value_out);
