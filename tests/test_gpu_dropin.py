@@ -158,4 +158,6 @@ def test_extract_index_auto_path_with_gpu_minibatch_kmeans(rvcr, tmp_path, capsy
     have = np.minimum(sizes[probed], 8)
     assert np.array_equal((I >= 0).sum(axis=1), have)
     assert ((I >= 0) == (np.arange(8)[None, :] < have[:, None])).all()
+    # blob centres are 2 * 768 * 0.30^2 = 138 apart (squared), a row is 768 * 0.14^2 = 15 from a k-means centre of its own
+    # blob: the median nearest centre must be a same-blob one (half the inter-blob distance as the line)
     assert (have >= 1).mean() > 0.99 and np.median(D[have >= 1, 0]) < 0.5 * 2 * 768 * 0.30 ** 2
