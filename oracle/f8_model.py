@@ -41,3 +41,41 @@ def coarse_values(q, cent):
     rel = 0.53 + d / 2097152
     margin = rel * np.sqrt(qn2) * cmax + (qn2 + cmax * cmax) / 1048576
     return v8, vtrue, margin
+
+
+def bf16_round(x):
+    """float64 value of round-to-nearest-even bfloat16 (torch's conversion)."""
+    import torch
+    return torch.from_numpy(np.asarray(x, np.float32)).to(torch.bfloat16).to(torch.float64).numpy()
+
+
+def rigorous_margin(q, cent, kind):
+    """numpy restatement of tc_margin / make_margin (csrc/coarse_tc.cu) for kind = "bf16" (coarse_mode 2) or "e4m3" (coarse_mode
+    4): (v_lp, vtrue, margin) with v_lp = ||c||^2 - 2 <q', c'> from the low-precision operands q', c' (products and sums exact,
+    float64), vtrue the float64 value, and margin(q) built from the EXACT residual norms r = ||x - x'||:
+        E = r_q c_max + (|q| + r_q) max_j r_c ;  margin = 4.008 E + acc_rel (|q| + r_q)(c_max + r_c) + abs_rel (|q|^2 + c_max^2).
+    The kernel's contract is |v_lp - vtrue| <= margin / 2 for every (query, centroid) pair."""
+    q64, c64 = np.asarray(q, np.float64), np.asarray(cent, np.float64)
+    d = q64.shape[1]
+    if kind == "bf16":
+        ql, cl = bf16_round(q64), bf16_round(c64)
+        acc_rel = 1.02 * d / 2097152
+    elif kind == "e4m3":
+        sc = f8_scale(np.abs(c64).max())
+        sq = f8_scale(np.abs(q64).max(axis=1))
+        ql = e4m3_round(q64 * sq[:, None]) / sq[:, None]
+        cl = e4m3_round(c64 * sc) / sc
+        acc_rel = max(1.02 * d / 2097152, 1.0 / 512)
+    else:
+        raise ValueError(kind)
+    abs_rel = 1.01 * (4 * (d // 8 + 5) + 2 * (d // 32 + 5) + 8) / 16777216
+    cn = (c64 ** 2).sum(1)
+    qn = np.sqrt((q64 ** 2).sum(1))
+    cmax = np.sqrt(cn.max())
+    rq = np.sqrt(((q64 - ql) ** 2).sum(1))
+    rc = np.sqrt(((c64 - cl) ** 2).sum(1)).max()
+    e = rq * cmax + (qn + rq) * rc
+    margin = 4.008 * e + acc_rel * (qn + rq) * (cmax + rc) + abs_rel * (qn * qn + cmax * cmax)
+    v_lp = cn[None, :] - 2.0 * (ql @ cl.T)
+    vtrue = cn[None, :] - 2.0 * (q64 @ c64.T)
+    return v_lp, vtrue, margin
