@@ -79,3 +79,42 @@ def rigorous_margin(q, cent, kind):
     v_lp = cn[None, :] - 2.0 * (ql @ cl.T)
     vtrue = cn[None, :] - 2.0 * (q64 @ c64.T)
     return v_lp, vtrue, margin
+
+
+def _f32_bits(x):
+    return np.asarray(x, np.float32).view(np.uint32)
+
+
+def tf32_rna(x):
+    """cvt.rna.tf32.f32: round to nearest, ties away from zero, to 10 mantissa bits (low 13 bits cleared); float64 value."""
+    b = _f32_bits(x).astype(np.uint64)
+    r = ((b + 0x1000) & 0xFFFFE000).astype(np.uint32)       # add half an ulp of the kept part to the magnitude bits, truncate
+    return r.view(np.float32).astype(np.float64)
+
+
+def tf32_trunc(x):
+    """what the tensor core keeps of a raw fp32 operand: the top 19 bits (sign, exponent, 10 mantissa bits); float64 value."""
+    return (_f32_bits(x) & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64)
+
+
+def scan_margin(q, rows):
+    """numpy restatement of the tensor-core list scan's approximate values and margin (csrc/scan_tc.cu): the stored rows enter
+    as y_hi (top 19 bits) + y_lo (the exact remainder, of which the tensor core again keeps the top 19 bits), the queries as
+    tf32(q) rounded to nearest; v = ||y||^2 - 2 <tf32(q), y_hi + y_lo'>.  margin(q) = 4.04 y_max (||q - tf32(q)|| + acc_rel ||q||)
+    + abs_margin (||q||^2 + y_max^2) with acc_rel = 2^-20 + d 2^-21, abs_margin = 2^-19 (scan_tc_range).  A row with
+    v <= U + margin is a candidate, U >= the 8th smallest v: the contract is 2 |v - vtrue| <= margin / 2 ... i.e. two
+    approximate values further apart than margin are ordered like the true ones.  Returns (v, vtrue, margin)."""
+    q64, y64 = np.asarray(q, np.float64), np.asarray(rows, np.float64)
+    d = q64.shape[1]
+    qt = tf32_rna(q)
+    yhi = tf32_trunc(rows)
+    ylo = tf32_trunc((y64 - yhi).astype(np.float32))      # y - y_hi is exact in fp32
+    yn = (y64 ** 2).sum(1)
+    v = yn[None, :] - 2.0 * (qt @ (yhi + ylo).T)
+    vtrue = yn[None, :] - 2.0 * (q64 @ y64.T)
+    qn2 = (q64 ** 2).sum(1)
+    ql = np.sqrt(((q64 - qt) ** 2).sum(1))
+    ymax = np.sqrt(yn.max())
+    acc_rel = 1.0 / 1048576 + d / 2097152
+    margin = 4.04 * ymax * (ql + acc_rel * np.sqrt(qn2)) + (qn2 + ymax * ymax) / 524288
+    return v, vtrue, margin

@@ -80,3 +80,20 @@ def test_tie_zone_against_blas_order_on_real_features():
         dq, dx = int((a_q != b_q).sum()), int((a_x != b_x).sum())
         print(f"jitter {jitter}: canonical vs BLAS-order argmin differ for {dq} of {len(q)} queries, {dx} of {len(x)} stored rows")
         assert dq <= 2 and dx <= 20
+
+
+def test_scan_margin_bounds_the_tf32_error_on_real_features():
+    """The list scan's validated split precision (csrc/scan_tc.cu) on real rows: two approximate values v further apart than
+    margin(q) must be ordered like the true distances, i.e. |v - vtrue| <= margin / 4 leaves the documented factor 2 for the
+    tensor core's own fp32 accumulation (not modelled here: the products are summed exactly)."""
+    from oracle import f8_model
+    x, cent, q = real_problem(6_000, 400, 64)
+    v, vtrue, margin = f8_model.scan_margin(q, x)
+    ratio = (np.abs(v - vtrue) / margin[:, None]).max()
+    assert ratio <= 0.25, ratio
+    # the candidate set {v <= 8th smallest v + margin} holds the true top-8 of every query
+    kth = np.sort(v, axis=1)[:, 7]
+    cand = v <= (kth + margin)[:, None]
+    top8 = np.argsort(vtrue, axis=1, kind="stable")[:, :8]
+    assert np.take_along_axis(cand, top8, axis=1).all()
+    print(f"tf32 scan: worst |v - v_true| / margin = {ratio:.3f}; candidates per query mean {cand.sum(1).mean():.1f} (8 compulsory)")
